@@ -1,0 +1,189 @@
+"""CPU tests: the oracle (oracle/vm_oracle.py) against the golden vectors produced by the
+unmodified reference, and against cv2 / scipy where those are importable.
+
+Bars: uint8 outputs, masks, .flo parse bit-exact; float alpha / composites
+|got-ref| <= 1e-5*|ref| + 1e-6; change_illumination +-1 LSB.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import vm_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def close(a, b, rtol=1e-5, atol=1e-6):
+    return np.allclose(a, b, rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_flow_warp_and_mask(golden, tag):
+    fg, fb, ff = golden[f"flow_{tag}_fg"], golden[f"flow_{tag}_fb"], golden[f"flow_{tag}_ff"]
+    alpha, bgr = fg[..., 3] / 255., np.ascontiguousarray(fg[..., :3])
+    assert np.array_equal(O.warp_bgr(bgr, fb), golden[f"flow_{tag}_warp_bgr"])
+    assert np.array_equal(O.warp_img(np.ascontiguousarray(fg[..., 3]), fb), golden[f"flow_{tag}_warp_alpha_u8"])
+    wa = O.warp_img(alpha, fb)
+    assert np.array_equal(wa, golden[f"flow_{tag}_warp_alpha"])          # float64 path is bit-equal
+    assert np.array_equal(O.warp_img(alpha.astype(np.float32), fb), golden[f"flow_{tag}_warp_alpha_f32"])
+    ca = O.correct_alpha(fb, ff, wa.copy())
+    assert np.array_equal(ca, golden[f"flow_{tag}_corrected"])
+    assert (ca != wa).any(), "fixture must exercise the occlusion mask"
+
+
+def test_correct_alpha_loop_matches_vectorised(golden):
+    fb, ff = golden["flow_a_fb"][:24, :30], golden["flow_a_ff"][:24, :30]
+    a = np.random.default_rng(0).random((24, 30))
+    assert np.array_equal(O.correct_alpha_loop(fb, ff, a.copy()), O.correct_alpha(fb, ff, a.copy()))
+
+
+def test_remap_special_values(golden):
+    fg, fb = golden["special_fg"], golden["special_fb"]
+    assert np.array_equal(O.warp_bgr(np.ascontiguousarray(fg[..., :3]), fb), golden["special_warp_bgr"])
+    assert np.array_equal(O.warp_img(fg[..., 3] / 255., fb), golden["special_warp_alpha"])
+
+
+@pytest.mark.parametrize("tag,n", [("a", 5), ("b", 4), ("c", 5)])
+def test_tps_transform_and_warp(golden, tag, n):
+    grid, dgrid, fg = golden[f"tps_{tag}_grid"], golden[f"tps_{tag}_defgrid"], golden[f"tps_{tag}_fg"]
+    h, w = fg.shape[:2]
+    (t0, t1), _, _ = O.tps_inverse_transform(grid, dgrid, h, w)
+    assert t0.shape == (h + 1, w + 1)
+    assert np.array_equal(t0, golden[f"tps_{tag}_t0"]) and np.array_equal(t1, golden[f"tps_{tag}_t1"])
+    res = O.tps_warp_images(grid, dgrid, [fg[..., 0], fg[..., 1], fg[..., 2], fg[..., 3] / 255.], (0, 0, h, w))
+    for got, key in zip(res, "bgr"):
+        assert np.array_equal(got, golden[f"tps_{tag}_{key}"])
+    assert np.array_equal(res[3], golden[f"tps_{tag}_alpha"])
+
+
+def test_deform_grid_rng_contract(golden):
+    np.random.seed(1234)
+    g, d = O.deform_grid(108, 192)
+    assert np.array_equal(g, golden["grid_108x192_n5"]) and np.array_equal(d, golden["defgrid_108x192_n5"])
+    np.random.seed(1234)
+    g, d = O.deform_grid(64, 64, n=4)
+    assert np.array_equal(g, golden["grid_64x64_n4"]) and np.array_equal(d, golden["defgrid_64x64_n4"])
+
+
+def test_warp_image_chain(golden):
+    fg = golden["wi_fg"]
+    h, w = fg.shape[:2]
+    bgr, alpha = np.ascontiguousarray(fg[..., :3]), fg[..., 3] / 255.
+    grids = (golden["wi_grid"], golden["wi_defgrid"])
+    p1 = ((3, -2), 7.5, 1.1, (52, 31))
+    p2 = ((-4, 5), 0., 1.07, (w // 2, h // 2))
+    assert np.array_equal(O.warp_image(bgr, p1), golden["wi_p1_bgr"])
+    assert np.array_equal(O.warp_image(alpha, p1), golden["wi_p1_alpha"])
+    assert np.array_equal(O.warp_image(bgr, p2), golden["wi_p2_bgr"])
+    assert np.array_equal(O.warp_image(bgr, p1, thin=grids), golden["wi_p1_thin_bgr"])
+    assert np.array_equal(O.warp_image(alpha, p1, thin=grids), golden["wi_p1_thin_alpha"])
+
+
+def test_illumination_and_stats(golden):
+    bgr = golden["ci_bgr"]
+    assert np.array_equal(O.bgr2hsv_u8(bgr), golden["ci_hsv"])
+    got = O.change_illumination(bgr, 1.03, 0.8, -0.02).astype(int)
+    assert np.abs(got - golden["ci_out"].astype(int)).max() <= 1       # HSV2BGR: +-1 LSB target
+    alpha = golden["wi_fg"][..., 3] / 255.
+    assert O.object_size(alpha) == float(golden["stats_size"])
+    assert tuple(O.fg_center(alpha)) == tuple(golden["stats_center"])
+
+
+def test_augment_end_to_end(golden):
+    fg = golden["wi_fg"]
+    bgr, alpha = np.ascontiguousarray(fg[..., :3]), fg[..., 3] / 255.
+    np.random.seed(77)
+    nfg, nbg, nal = O.augment(bgr, golden["aug_bg"], alpha)
+    assert np.array_equal(nal, golden["aug_alpha_out"])
+    assert np.abs(nfg.astype(int) - golden["aug_fg_out"].astype(int)).max() <= 1
+    assert np.abs(nbg.astype(int) - golden["aug_bg_out"].astype(int)).max() <= 1
+
+
+def test_composite_and_uint16_quirk(golden):
+    fg = golden["wi_fg"]
+    bgr, alpha = np.ascontiguousarray(fg[..., :3]), fg[..., 3] / 255.
+    assert np.array_equal(O.create_composite_image(bgr, golden["aug_bg"], alpha), golden["cmp_out"])
+    assert np.array_equal(O.fg_from_uint16(golden["u16_in"]), golden["u16_out"])
+
+
+@pytest.mark.parametrize("k", [1, 2])
+def test_reference_owned_golden_cmp_png(golden, k):
+    """cmp1.png / cmp2.png (reference test_data) == rint(composite(read_fg_img(in006x), bg))."""
+    img8 = O.fg_from_uint16(golden[f"cmp{k}_raw16"])
+    alpha, bgr = O.split_fg(img8)
+    cmp_ = O.create_composite_image(bgr, golden[f"cmp{k}_bg"], alpha)
+    assert np.array_equal(np.rint(cmp_).astype(np.uint8), golden[f"cmp{k}_gold"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_c4_pipeline(golden, tag):
+    fg, fb, ff = golden[f"flow_{tag}_fg"], golden[f"flow_{tag}_fb"], golden[f"flow_{tag}_ff"]
+    grids = (golden[f"c4_{tag}_grid"], golden[f"c4_{tag}_defgrid"])
+    cmp_, a2 = O.pipeline_c4(fg, fb, ff, grids, golden[f"c4_{tag}_bg"])
+    assert np.array_equal(a2, golden[f"c4_{tag}_alpha"])
+    assert np.array_equal(cmp_, golden[f"c4_{tag}_cmp"])
+
+
+def test_flo_roundtrip(tmp_path, golden):
+    with open(os.path.join(ROOT, "tests", "golden", "tiny.flo"), "rb") as f:
+        buf = f.read()
+    flow, ok = O.parse_flo(buf)
+    assert ok and np.array_equal(flow, golden["flo_tiny"])
+    bad = bytearray(buf); bad[0] ^= 0xFF
+    flow2, ok2 = O.parse_flo(bytes(bad))
+    assert not ok2 and np.array_equal(flow2, flow)                     # bad magic: data still returned
+    with pytest.raises(ValueError):
+        O.parse_flo(buf[:-8])                                          # truncated payload
+
+
+# ---- differential tests against the third-party kernels, where importable -------------
+
+def test_remap_vs_cv2_random():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for (h, w) in ((37, 53), (64, 64)):
+        src8 = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        src64 = rng.random((h, w))
+        for sigma in (2, 50, 1e5):
+            flow = rng.normal(0, sigma, (h, w, 2)).astype(np.float32)
+            mx, my = O.flow_map(flow)
+            m = np.stack([mx, my], -1)
+            assert np.array_equal(O.warp_img(src8, flow), cv2.remap(src8, m, None, cv2.INTER_LINEAR))
+            assert np.array_equal(O.warp_img(src64, flow), cv2.remap(src64, m, None, cv2.INTER_LINEAR))
+
+
+def test_warp_affine_vs_cv2_random():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(1)
+    src8 = rng.integers(0, 256, (45, 70, 3), dtype=np.uint8)
+    src64 = rng.random((46, 71))
+    for _ in range(6):
+        M = cv2.getRotationMatrix2D((rng.uniform(0, 70), rng.uniform(0, 45)), rng.uniform(-10, 10),
+                                    rng.uniform(1, 1.15))
+        assert np.array_equal(O.rotation_matrix_2d((0, 0), 0, 1), cv2.getRotationMatrix2D((0, 0), 0, 1))
+        assert np.array_equal(O.warp_affine(src8, M, (70, 45)), cv2.warpAffine(src8, M, (70, 45)))
+        assert np.array_equal(O.warp_affine(src64, M, (70, 45)), cv2.warpAffine(src64, M, (70, 45)))
+
+
+def test_map_coordinates_vs_scipy_random():
+    ndi = pytest.importorskip("scipy.ndimage")
+    rng = np.random.default_rng(2)
+    img8 = rng.integers(0, 256, (33, 47), dtype=np.uint8)
+    img64 = rng.random((33, 47))
+    t0 = rng.uniform(-2, 35, (40, 50)); t1 = rng.uniform(-2, 49, (40, 50))
+    t0[0, 0], t1[0, 0] = 0.0, 46.0
+    t0[0, 1], t1[0, 1] = 32.0, 0.5
+    t0[0, 2], t1[0, 2] = np.nextafter(32.0, 64), 3.0
+    t0[0, 3], t1[0, 3] = 2.5, 7.5
+    assert np.array_equal(O.map_coordinates_linear(img8, t0, t1), ndi.map_coordinates(img8, [t0, t1], order=1))
+    assert np.array_equal(O.map_coordinates_linear(img64, t0, t1), ndi.map_coordinates(img64, [t0, t1], order=1))
+
+
+def test_bgr2hsv_vs_cv2_exhaustive_slice():
+    cv2 = pytest.importorskip("cv2")
+    v = np.arange(256, dtype=np.uint8)
+    for b in (0, 1, 77, 128, 254, 255):
+        g, r = np.meshgrid(v, v)
+        bgr = np.stack([np.full_like(g, b), g, r], -1)
+        assert np.array_equal(O.bgr2hsv_u8(bgr), cv2.cvtColor(bgr, cv2.COLOR_BGR2HSV))
