@@ -1,0 +1,169 @@
+/*
+ * vm_b200.h - C ABI of libvm_sm100a.so: the B200 (sm_100a) replacement for the per-frame
+ * data path of tangih/video-matting (flow.py, tps.py, augmentation.py, reader.py).
+ *
+ * The reference has no FFI: its hot path is a set of Python module-level functions that
+ * bottom out in OpenCV / SciPy / NumPy CPU kernels.  Each entry point below replaces one of
+ * those call sites (reference file:line given per function) and is what a Python-side
+ * binding (ctypes) loads.  Conventions:
+ *
+ *   - plain C: pointers + sizes, no C++/torch types.  Unless the name ends in `_host`, every
+ *     data pointer is a DEVICE pointer on the current CUDA device, dense row-major,
+ *     channel-last (OpenCV layout), no padding.
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).  Calls
+ *     only enqueue work; nothing allocates, frees or synchronises inside the library.
+ *   - return value: 0 = VM_OK, otherwise a VM_ERR_* code; `vm_last_error_string()` returns
+ *     a thread-local description.  Nothing throws across the boundary.
+ *   - `status` arguments point to a DEVICE `int32[VM_STATUS_WORDS]` block the kernels OR /
+ *     add into; the host binding reads it to reproduce the reference's exceptions
+ *     (IndexError / ValueError in flow.correct_alpha) and to count knife-edge events.
+ *   - flow fields are float32 (H,W,2) = (dx, dy) in pixels on the OUTPUT grid pointing into
+ *     the SOURCE (reader.py:29, flow.py:13-17).
+ */
+#ifndef VM_B200_H
+#define VM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VM_OK            0
+#define VM_ERR_ARG       1   /* bad size / null pointer / unsupported combination        */
+#define VM_ERR_CUDA      2   /* a CUDA runtime call or launch failed                     */
+
+/* element types of generic (drop-in) entry points */
+#define VM_U8   0
+#define VM_F32  1
+#define VM_F64  2
+
+/* layout of a status block (device int32[VM_STATUS_WORDS]) */
+#define VM_STATUS_WORDS        8
+#define VM_STATUS_INDEX_ERR    0   /* # pixels where flow.py:46 would raise IndexError     */
+#define VM_STATUS_NAN_ERR      1   /* # pixels where int(nan/inf) would raise ValueError   */
+#define VM_STATUS_MASKED       2   /* # pixels zeroed by the consistency test              */
+#define VM_STATUS_TPS_OUTSIDE  3   /* # TPS samples outside [0,n-1] (map_coordinates -> 0) */
+#define VM_STATUS_SLOW_TILES   4   /* # tiles of a fused kernel that took the gather path  */
+
+int         vm_version(void);
+const char *vm_last_error_string(void);
+/* Upload the log table used by the TPS kernels to the current device (idempotent, per
+ * device; called lazily by the TPS entry points, exposed so that it can be done up front). */
+int         vm_init(void);
+
+/* ---- flow.warp_img / flow.warp_bgr : cv2.remap(INTER_LINEAR, BORDER_CONSTANT 0) ---------
+ * reference: flow.py:9-18 (1 channel), flow.py:21-33 (3 channels, per-channel remap).
+ * src is (sh, sw, channels) of `dtype`; flow and dst are on the (h, w) output grid.
+ * uint8: bit-exact fixed-point bilinear; float32/float64: float32 table weights, sum in the
+ * source precision, left to right (bit-equal to OpenCV 4.13).                              */
+int vm_flow_warp(const void *src, int dtype, int channels, int sh, int sw,
+                 const float *flow, int h, int w, void *dst, void *stream);
+
+/* ---- flow.correct_alpha : forward/backward consistency mask ------------------------------
+ * reference: flow.py:36-65.  `vm_occlusion_mask` evaluates flow.py:41-48 for every pixel and
+ * writes mask[i,j] = (err > 15) as uint8; IndexError / NaN conditions are counted in
+ * `status`.  `vm_apply_mask` is flow.py:49-50 (alpha[mask] = 0, in place).                 */
+int vm_occlusion_mask(const float *backward, const float *forward, int h, int w,
+                      uint8_t *mask, int32_t *status, void *stream);
+int vm_apply_mask(void *alpha, int dtype, const uint8_t *mask, int64_t n, void *stream);
+
+/* ---- reader.create_composite_image : I = alpha*F + (1-alpha)*B ---------------------------
+ * reference: reader.py:72-79.  fg/bg (h,w,3) of fg_dtype/bg_dtype, alpha (h,w) float64,
+ * out (h,w,3) float64, evaluated as tri*fg + (1-tri)*bg in float64.                        */
+int vm_composite(const void *fg, int fg_dtype, const void *bg, int bg_dtype,
+                 const double *alpha, int h, int w, double *out, void *stream);
+
+/* ---- tps._make_warp / _calculate_f : coarse-grid TPS evaluation ---------------------------
+ * reference: tps.py:101-110, 120-121 as called from tps.py:47-51.  For each of `n` frames:
+ * ctrl (N,2) float64 control points (row, col), coef (N+3,2) float64 from the host solve
+ * (tps.py:119), coarse point (k,l) = (k*step_x + x0, l*step_y + y0); writes coarse (n, 2, nx, ny)
+ * float64.  U(r) = r^2 log r is evaluated as 0.5*r2*log(r2) in float64.                    */
+int vm_tps_coarse(const double *ctrl, const double *coef, int n, int N,
+                  int nx, int ny, double step_x, double step_y, double x0, double y0,
+                  double *coarse, void *stream);
+
+/* Axis tables of the bilinear up-sampling of the coarse transform (tps.py:55-63): for output
+ * index i in [0, len]: frac = modf((steps-1)*i/len), i0, i1 = min(i0+1, steps-1).  They depend
+ * on the frame size only and are computed once on the host by the binding.                 */
+typedef struct { double frac; int32_t i0; int32_t i1; } vm_axis_entry;
+
+/* ---- tps._make_inverse_warp : materialise the (h+1, w+1) transform ------------------------
+ * reference: tps.py:55-74, same operation order.  out (2, h+1, w+1) float64.               */
+int vm_tps_upsample(const double *coarse, int nx, int ny,
+                    const vm_axis_entry *rows, const vm_axis_entry *cols, int h, int w,
+                    double *out, void *stream);
+
+/* ---- tps.warp_images : up-sample + scipy.ndimage.map_coordinates(order=1) ------------------
+ * reference: tps.py:34 (+ 55-74).  src (sh, sw, channels) of dtype (uint8 or float64), dst
+ * (oh, ow, channels), oh <= h+1, ow <= w+1 rows/cols of the transform.  uint8 output is
+ * floor(v + 0.5) clamped, float64 is v (same operation order as scipy).                    */
+int vm_tps_warp(const void *src, int dtype, int channels, int sh, int sw,
+                const double *coarse, int nx, int ny,
+                const vm_axis_entry *rows, const vm_axis_entry *cols,
+                int oh, int ow, void *dst, int32_t *status, void *stream);
+
+/* scipy.ndimage.map_coordinates(order=1, mode='constant', cval=0) with an explicit transform
+ * (tps.py:34 when approximate_grid is None/1): t0/t1 (oh, ow) float64 row / column coords.  */
+int vm_map_coordinates(const void *src, int dtype, int channels, int sh, int sw,
+                       const double *t0, const double *t1, int oh, int ow, void *dst,
+                       int32_t *status, void *stream);
+
+/* ---- cv2.warpAffine (INTER_LINEAR, BORDER_CONSTANT 0), legacy fixed-point path -----------
+ * reference: augmentation.py:59-62.  M is the forward 2x3 matrix (row-major, 6 doubles,
+ * HOST pointer); inversion and the AB_BITS=10 coordinate generation follow OpenCV.         */
+int vm_warp_affine(const void *src, int dtype, int channels, int sh, int sw,
+                   const double *M_host, int dh, int dw, void *dst, void *stream);
+
+/* ---- augmentation.change_illumination ----------------------------------------------------
+ * reference: augmentation.py:88-99.  BGR2HSV integer model (exact), S/V gamma in float64
+ * with truncation, HSV2BGR float model (+-1 LSB of cv2).                    */
+int vm_change_illumination(const uint8_t *bgr, int64_t npx, double a, double b, double c,
+                           uint8_t *out, void *stream);
+/* Same with the 256-entry S/V transfer table supplied by the caller (HOST pointer), so that a
+ * NumPy host can build it with the reference's own expression (augmentation.py:91-98).     */
+int vm_illumination_lut(const uint8_t *bgr, int64_t npx, const uint8_t *lut_host,
+                        uint8_t *out, void *stream);
+
+/* ---- augmentation.object_size / fg_center -------------------------------------------------
+ * reference: augmentation.py:10-21.  out (device uint64[3]) += {count(alpha != 0),
+ * sum of row indices, sum of column indices}; caller zeroes `out` first.                   */
+int vm_alpha_stats(const void *alpha, int dtype, int h, int w, unsigned long long *out,
+                   void *stream);
+
+/* ======================= fused clip-level kernels (canonical layouts) =====================
+ * fg     : (n, h, w, 4) uint8  BGRA, alpha = A/255  (reader.py:16-17)
+ * flows  : (n, h, w, 2) float32
+ * bg     : (n_bg, h, w, 3) uint8 BGR, frame f uses bg[f % n_bg]
+ */
+
+/* warp_bgr + warp_img + correct_alpha in one pass (flow.py:9-65).
+ * out_bgr (n,h,w,3) uint8 bit-exact; out_alpha (n,h,w) float32 (<= 1e-6 rel of the float64
+ * reference).  forward may be NULL (no consistency test).  27 B/px of HBM traffic.         */
+int vm_flow_warp_mask_bgra(const uint8_t *fg, const float *backward, const float *forward,
+                           int n, int h, int w, uint8_t *out_bgr, float *out_alpha,
+                           int32_t *status, void *stream);
+
+/* TPS warp of a BGRA frame + composite onto bg (tps.py:14-34, reader.py:72-79), i.e.
+ * warp_image(.., identity affine, thin) for fg and alpha followed by create_composite_image.
+ * out (n,h,w,4) float32 = {B, G, R composite (0..255), warped alpha}.  23 B/px.             */
+int vm_tps_composite_bgra(const uint8_t *fg, const uint8_t *bg, int n_bg,
+                          const double *coarse, int nx, int ny,
+                          const vm_axis_entry *rows, const vm_axis_entry *cols,
+                          int n, int h, int w, float *out, int32_t *status, void *stream);
+
+/* flow warp + consistency mask + TPS + composite in one pass (SURVEY 8d "C4 pipeline").
+ * 39 B/px.  `scratch`: device workspace of vm_flow_tps_scratch_bytes(n,h,w) bytes (may be
+ * NULL when that is 0).                                                                     */
+int64_t vm_flow_tps_scratch_bytes(int n, int h, int w);
+int vm_flow_tps_composite_bgra(const uint8_t *fg, const float *backward, const float *forward,
+                               const uint8_t *bg, int n_bg,
+                               const double *coarse, int nx, int ny,
+                               const vm_axis_entry *rows, const vm_axis_entry *cols,
+                               int n, int h, int w, float *out, void *scratch,
+                               int32_t *status, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VM_B200_H */

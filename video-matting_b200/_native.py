@@ -1,0 +1,136 @@
+"""ctypes binding of libvm_sm100a.so (the C ABI declared in include/vm_b200.h).
+
+There is no CPU fallback: if the library is missing it is built with nvcc; if that fails, or
+no CUDA device is present when a kernel is requested, the call raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _build
+
+VM_U8, VM_F32, VM_F64 = 0, 1, 2
+STATUS_WORDS = 8
+STATUS_INDEX_ERR, STATUS_NAN_ERR, STATUS_MASKED, STATUS_TPS_OUTSIDE, STATUS_SLOW_TILES = 0, 1, 2, 3, 4
+
+_c = ctypes
+_P, _I, _L, _D = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_double
+
+# name -> argtypes (restype int unless stated); must list every symbol of include/vm_b200.h
+SIGNATURES = {
+    "vm_version": [],
+    "vm_last_error_string": [],
+    "vm_init": [],
+    "vm_flow_warp": [_P, _I, _I, _I, _I, _P, _I, _I, _P, _P],
+    "vm_occlusion_mask": [_P, _P, _I, _I, _P, _P, _P],
+    "vm_apply_mask": [_P, _I, _P, _L, _P],
+    "vm_composite": [_P, _I, _P, _I, _P, _I, _I, _P, _P],
+    "vm_tps_coarse": [_P, _P, _I, _I, _I, _I, _D, _D, _D, _D, _P, _P],
+    "vm_tps_upsample": [_P, _I, _I, _P, _P, _I, _I, _P, _P],
+    "vm_tps_warp": [_P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _I, _I, _P, _P, _P],
+    "vm_map_coordinates": [_P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P],
+    "vm_warp_affine": [_P, _I, _I, _I, _I, _P, _I, _I, _P, _P],
+    "vm_change_illumination": [_P, _L, _D, _D, _D, _P, _P],
+    "vm_illumination_lut": [_P, _L, _P, _P, _P],
+    "vm_alpha_stats": [_P, _I, _I, _I, _P, _P],
+    "vm_flow_warp_mask_bgra": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "vm_tps_composite_bgra": [_P, _P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P],
+    "vm_flow_tps_scratch_bytes": [_I, _I, _I],
+    "vm_flow_tps_composite_bgra": [_P, _P, _P, _P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+}
+
+_lib = None
+
+
+class VmError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load(build_if_missing=True):
+    """Load (building first if needed) the shared library; raises if that is impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing and _build.needs_build():
+        try:
+            _build.build()
+        except Exception as e:  # a stale .so is better than nothing only if it exists
+            if not os.path.exists(_build.LIB):
+                raise VmError(f"libvm_sm100a.so is missing and could not be built: {e}") from e
+    if not os.path.exists(_build.LIB):
+        raise VmError("libvm_sm100a.so is missing (run __graft_entry__.build())")
+    lib = ctypes.CDLL(_build.LIB)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError = header / library mismatch: be loud
+        fn.argtypes = argtypes
+        fn.restype = _c.c_int
+    lib.vm_last_error_string.restype = _c.c_char_p
+    lib.vm_flow_tps_scratch_bytes.restype = _c.c_int64
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise VmError(f"libvm_sm100a: error {rc}: {load().vm_last_error_string().decode()}")
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise VmError("video_matting_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+_DT = {torch.uint8: VM_U8, torch.float32: VM_F32, torch.float64: VM_F64}
+
+
+def dtype_code(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype} (uint8, float32, float64 only)") from None
+
+
+def to_device(x, dtype=None):
+    """(CUDA tensor, kind) for a numpy array, CPU tensor or CUDA tensor; kind in
+    {'numpy', 'cpu', 'cuda'} tells the caller what to hand back."""
+    require_cuda()
+    if isinstance(x, torch.Tensor):
+        kind = "cuda" if x.is_cuda else "cpu"
+        t = x
+    else:
+        kind = "numpy"
+        a = np.ascontiguousarray(x)
+        if not a.flags.writeable:
+            a = a.copy()
+        t = torch.from_numpy(a)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    if not t.is_cuda:
+        t = t.cuda(non_blocking=True)
+    return t.contiguous(), kind
+
+
+def from_device(t, kind):
+    if kind == "cuda":
+        return t
+    if kind == "cpu":
+        return t.cpu()
+    return t.cpu().numpy()
+
+
+def new_status(device=None):
+    return torch.zeros(STATUS_WORDS, dtype=torch.int32, device=device or "cuda")

@@ -1,0 +1,163 @@
+"""Drop-in replacement for the reference ``augmentation`` module (reference
+augmentation.py:10-166): random TPS + affine warps of foreground / alpha / background and
+HSV illumination jitter, with the reference's global-``np.random`` draw order."""
+import os
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import pipeline as P
+from . import reader, tps
+
+
+def _stats(alpha):
+    a, _ = N.to_device(alpha)
+    if a.dtype not in (torch.uint8, torch.float32, torch.float64):
+        a = a.to(torch.float64)
+    cnt, si, sj = (int(v) for v in P.alpha_stats(a).cpu())
+    return cnt, si, sj
+
+
+def object_size(alpha):
+    """typical side of foreground image - reference augmentation.py:10-14."""
+    return np.sqrt(_stats(alpha)[0])
+
+
+def fg_center(alpha):
+    """barycenter (x, y) of the foreground - reference augmentation.py:17-21."""
+    cnt, si, sj = _stats(alpha)
+    if cnt == 0:
+        raise ValueError("cannot convert float NaN to integer")       # int(np.mean([]))
+    return int(sj / cnt), int(si / cnt)
+
+
+def deform_grid(h, w, n=5):
+    """regular n x n grid and a randomly perturbed copy - reference augmentation.py:24-41.
+    Draws from the global np.random stream: x first (if the point is not on a vertical edge),
+    then y (if not on a horizontal edge), row-major over the grid."""
+    bound = min(w, h) * 0.05
+    rows = (h / (n - 1)) * np.arange(n)
+    cols = (w / (n - 1)) * np.arange(n)
+    grid = np.transpose([np.repeat(rows, n), np.tile(cols, n)])
+    moved = grid.copy()
+    for k, (y, x) in enumerate(grid):
+        if 0. < x < w:
+            moved[k, 1] += np.random.uniform(-bound, bound)
+        if 0. < y < h:
+            moved[k, 0] += np.random.uniform(-bound, bound)
+    return grid, moved
+
+
+def _rotation_matrix(center, angle, scale):
+    """cv2.getRotationMatrix2D in float64."""
+    ang = angle * (np.pi / 180.)
+    al, be = np.cos(ang) * scale, np.sin(ang) * scale
+    cx, cy = float(center[0]), float(center[1])
+    return np.array([[al, be, (1 - al) * cx - be * cy], [-be, al, be * cx + (1 - al) * cy]])
+
+
+def warp_image(img, params, thin=None):
+    """warp image according to given parameters - reference augmentation.py:44-63:
+    optional TPS deformation, integer translation, then rotation/scale about ``center``."""
+    (tu, tv), rot, scale, center = params
+    src, kind = N.to_device(img)
+    h, w = src.shape[:2]
+    if thin is not None:
+        grid, def_grid = thin
+        plan = P.get_plan((0, 0, h, w), 2, src.device)
+        coarse = tps._coarse_for(grid, def_grid, plan)
+        if src.dim() == 3 and src.shape[2] != 3:
+            raise RuntimeError("invalid shape for coordinate array")
+        src = P.tps_warp(src, coarse, plan)                           # (h+1, w+1[, 3])
+    mt = np.float32([[1, 0, tu], [0, 1, tv]])
+    translated = P.warp_affine(src, mt, (w, h))
+    rotated = P.warp_affine(translated, _rotation_matrix(center, rot, scale), (w, h))
+    return N.from_device(rotated, kind)
+
+
+def identity(m, n):
+    """array s.t. arr[i, j] = [i+1, j+1] - reference augmentation.py:66-70."""
+    v1, v2 = np.arange(1, n + 1), np.arange(1, m + 1)
+    return np.transpose([np.repeat(v2, n), np.tile(v1, m)]).reshape(m, n, 2)
+
+
+def synthetize_flow(fg_params, bg_params, grids, warped_alpha):
+    """reference augmentation.py:73-85.  Kept for API completeness: like the reference it
+    fails (RuntimeError) because a 2-channel image cannot go through the TPS path."""
+    h, w = warped_alpha.shape[:2]
+    id_fg, id_bg = identity(h, w), identity(h, w)
+    w_fg = warp_image(id_fg, fg_params, thin=grids)
+    w_bg = warp_image(id_bg, bg_params)
+    bi_alpha = np.zeros((h, w, 2), dtype=float)
+    bi_alpha[:, :, 0] = warped_alpha
+    bi_alpha[:, :, 1] = warped_alpha
+    return np.multiply(bi_alpha, w_fg - id_fg) + np.multiply(1. - bi_alpha, w_bg - id_bg)
+
+
+def illumination_lut(a, b, c):
+    """S/V transfer table of change_illumination: the reference expression
+    (augmentation.py:91-98) evaluated by numpy on the 256 possible uint8 inputs."""
+    x = np.arange(256, dtype=np.uint8)
+    new = np.clip(a * np.power(x / 255., b) + c, 0., 1.)
+    return (255. * new).astype(np.uint8)
+
+
+def change_illumination(bgr, a, b, c):
+    """randomly changes illumination via [H]SV transformation - reference augmentation.py:88-99."""
+    src, kind = N.to_device(bgr)
+    if src.dtype != torch.uint8:
+        raise TypeError("change_illumination expects a uint8 BGR image")
+    return N.from_device(P.illumination(src, illumination_lut(a, b, c)), kind)
+
+
+def augment(fg, bg, alpha):
+    """randomly modify input image to create synthetic data - reference augmentation.py:102-135.
+    Same 40 global np.random draws, in the same order, as the reference."""
+    bound_translate, bound_rotate, bound_scale = 0.05, 10, 0.15
+    h, w = fg.shape[:2]
+    a_dev, _ = N.to_device(alpha)
+    fg_size = object_size(a_dev)
+    tu_bg = int(np.random.uniform(-w * bound_translate, w * bound_translate))
+    tv_bg = int(np.random.uniform(-h * bound_translate, h * bound_translate))
+    scale_bg = np.random.uniform(1., 1. + bound_scale)
+    new_bg = warp_image(bg, ((tu_bg, tv_bg), 0., scale_bg, (w // 2, h // 2)))
+    grid, def_grid = deform_grid(h, w)
+    tu_fg = int(np.random.uniform(-fg_size * bound_translate, fg_size * bound_translate))
+    tv_fg = int(np.random.uniform(-fg_size * bound_translate, fg_size * bound_translate))
+    rot_fg = np.random.uniform(-bound_rotate, bound_rotate)
+    scale_fg = np.random.uniform(1., 1. + bound_scale)
+    params_fg = (tu_fg, tv_fg), rot_fg, scale_fg, fg_center(a_dev)
+    new_fg = warp_image(fg, params_fg, thin=(grid, def_grid))
+    new_alpha = warp_image(alpha, params_fg, thin=(grid, def_grid))
+    a = np.random.uniform(0.95, 1.05)
+    b = np.random.uniform(0.7, 1.3)
+    c = np.random.uniform(-0.07, 0.07)
+    return change_illumination(new_fg, a, b, c), change_illumination(new_bg, a, b, c), new_alpha
+
+
+def augmentation(dim_dataset, voc_dataset, sig_dataset):
+    """create synthetic data for video matting (DIM mattes over VOC backgrounds) - reference
+    augmentation.py:138-166.  Disk layout and file names follow the reference."""
+    import cv2
+    n = 50
+    paths = [os.path.join(dim_dataset, 'fg', folder, f)
+             for folder in ('DIM_TEST', 'DIM_TRAIN')
+             for f in os.listdir(os.path.join(dim_dataset, 'fg', folder))]
+    voc_list = [os.path.join(voc_dataset, f) for f in os.listdir(voc_dataset)]
+    dst_fg = os.path.join(sig_dataset, 'fg', 'augmented')
+    dst_bg = os.path.join(sig_dataset, 'bg', 'augmented')
+    for k, path in enumerate(paths):
+        alpha, fg = reader.read_fg_img(path)
+        name = os.path.basename(path).split('.')[0]
+        print('Processing image {} ({}/{})'.format(name, k + 1, len(paths)))
+        a8 = (255. * alpha.reshape((alpha.shape[0], alpha.shape[1], 1))).astype(np.uint8)
+        cv2.imwrite(os.path.join(dst_fg, '{}_fg_ref.png'.format(name)), np.concatenate((fg, a8), axis=2))
+        for i in range(n):
+            bg = cv2.imread(voc_list[np.random.randint(len(voc_list))])
+            bg = cv2.resize(bg, dsize=(fg.shape[1], fg.shape[0]), interpolation=cv2.INTER_LINEAR)
+            nfg, nbg, nal = augment(fg, bg, alpha)
+            na8 = (255. * nal.reshape((nal.shape[0], nal.shape[1], 1))).astype(np.uint8)
+            cv2.imwrite(os.path.join(dst_bg, '{}_bg_ref_{:04d}.png'.format(name, i)), bg)
+            cv2.imwrite(os.path.join(dst_bg, '{}_bg_{:04d}.png'.format(name, i)), nbg)
+            cv2.imwrite(os.path.join(dst_fg, '{}_fg_{:04d}.png'.format(name, i)), np.concatenate((nfg, na8), axis=2))

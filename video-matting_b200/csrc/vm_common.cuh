@@ -1,0 +1,216 @@
+// Shared device helpers for libvm_sm100a.so (compiled with -fmad=false: every fused
+// multiply-add in these kernels is an explicit fma()/__fmaf_rn so that the float64 paths
+// keep the reference's operation order bit for bit).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <limits.h>
+#include "../../include/vm_b200.h"
+
+void vm_set_error(const char *fmt, ...);
+int  vm_check_launch(const char *what);
+
+#define VM_REQUIRE(cond, msg)                                   \
+    do { if (!(cond)) { vm_set_error("%s: %s", __func__, msg); return VM_ERR_ARG; } } while (0)
+
+static inline unsigned vm_blocks(int64_t n, int per_block) {
+    int64_t b = (n + per_block - 1) / per_block;
+    return (unsigned)(b < 1 ? 1 : b);
+}
+
+// ---------------------------------------------------------------------------------------
+// cv2.remap / warpAffine fixed-point tap rule
+// ---------------------------------------------------------------------------------------
+
+// cvRound(m * 32) with the x86 cvtps2dq "integer indefinite" for NaN / out-of-range.
+__device__ __forceinline__ int vm_cvround_x32(float m) {
+    float v = __fmul_rn(m, 32.0f);
+    if (!(fabsf(v) < 2147483648.0f)) return INT_MIN;
+    return __float2int_rn(v);
+}
+
+// cvRound(double) -> int32 (cvtsd2si semantics)
+__device__ __forceinline__ int vm_cvround_f64(double v) {
+    if (!(fabs(v) < 2147483648.0)) return INT_MIN;
+    return __double2int_rn(v);
+}
+
+__device__ __forceinline__ int vm_sat_s16(int v) { return max(-32768, min(32767, v)); }
+
+// flow.py:13-17 : map = float32(int64 grid + float32 flow)  ==  fp32 rn(float(j) + dx)
+__device__ __forceinline__ float vm_map_coord(int j, float d) { return __fadd_rn((float)j, d); }
+
+template <typename T> struct VmTap;   // per-dtype bilinear accumulation
+
+template <> struct VmTap<uint8_t> {
+    // (sum S*w + 16384) >> 15 with w = wx*wy*32  ==  (sum S*wx*wy + 512) >> 10
+    static __device__ __forceinline__ uint8_t blend(int s00, int s01, int s10, int s11, int fx, int fy) {
+        int w00 = (32 - fx) * (32 - fy), w01 = fx * (32 - fy), w10 = (32 - fx) * fy, w11 = fx * fy;
+        return (uint8_t)((s00 * w00 + s01 * w01 + s10 * w10 + s11 * w11 + 512) >> 10);
+    }
+};
+template <> struct VmTap<float> {
+    static __device__ __forceinline__ float blend(float s00, float s01, float s10, float s11, int fx, int fy) {
+        float ax = (float)fx * 0.03125f, ay = (float)fy * 0.03125f;           // exact
+        float w00 = __fmul_rn(1.f - ax, 1.f - ay), w01 = __fmul_rn(ax, 1.f - ay);
+        float w10 = __fmul_rn(1.f - ax, ay), w11 = __fmul_rn(ax, ay);          // exact products
+        float acc = __fmul_rn(s00, w00);
+        acc = __fadd_rn(acc, __fmul_rn(s01, w01));
+        acc = __fadd_rn(acc, __fmul_rn(s10, w10));
+        acc = __fadd_rn(acc, __fmul_rn(s11, w11));
+        return acc;
+    }
+};
+template <> struct VmTap<double> {
+    static __device__ __forceinline__ double blend(double s00, double s01, double s10, double s11, int fx, int fy) {
+        float ax = (float)fx * 0.03125f, ay = (float)fy * 0.03125f;
+        double w00 = (double)__fmul_rn(1.f - ax, 1.f - ay), w01 = (double)__fmul_rn(ax, 1.f - ay);
+        double w10 = (double)__fmul_rn(1.f - ax, ay), w11 = (double)__fmul_rn(ax, ay);
+        double acc = __dmul_rn(s00, w00);
+        acc = __dadd_rn(acc, __dmul_rn(s01, w01));
+        acc = __dadd_rn(acc, __dmul_rn(s10, w10));
+        acc = __dadd_rn(acc, __dmul_rn(s11, w11));
+        return acc;
+    }
+};
+
+// Bilinear sample of a (H, W, C) image at fixed-point position (SX, SY) in 1/32 px; taps
+// outside the image read 0 (BORDER_CONSTANT).  Writes C values to dst.
+template <typename T, int C>
+__device__ __forceinline__ void vm_sample_fixed(const T *__restrict__ src, int H, int W,
+                                                int SX, int SY, T *__restrict__ dst) {
+    const int ix = vm_sat_s16(SX >> 5), iy = vm_sat_s16(SY >> 5);
+    const int fx = SX & 31, fy = SY & 31;
+    const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
+    const bool y0 = (unsigned)iy < (unsigned)H, y1 = (unsigned)(iy + 1) < (unsigned)H;
+    const T *r0 = src + ((int64_t)iy * W + ix) * C;
+    const T *r1 = r0 + (int64_t)W * C;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        T s00 = (y0 && x0) ? __ldg(r0 + c) : T(0);
+        T s01 = (y0 && x1) ? __ldg(r0 + C + c) : T(0);
+        T s10 = (y1 && x0) ? __ldg(r1 + c) : T(0);
+        T s11 = (y1 && x1) ? __ldg(r1 + C + c) : T(0);
+        dst[c] = VmTap<T>::blend(s00, s01, s10, s11, fx, fy);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// BGRA foreground: flow-warped pixel = {B, G, R bit-exact uint8, alpha numerator TA}
+// where warp_img(A/255.)[q] = TA / (1024 * 255) exactly (integer weights wx*wy sum to 1024).
+// ---------------------------------------------------------------------------------------
+#define VM_ALPHA_DEN 261120.0   /* 1024 * 255 */
+
+struct VmWarped { uint32_t bgr; uint32_t ta; };   // bgr: B | G<<8 | R<<16
+
+__device__ __forceinline__ uint32_t vm_ldg_bgra(const uint8_t *__restrict__ fg, int64_t px) {
+    return __ldg(reinterpret_cast<const uint32_t *>(fg) + px);
+}
+
+// 4 BGRA taps blended with integer weights.  s?? are packed BGRA words.
+__device__ __forceinline__ VmWarped vm_blend_bgra(uint32_t s00, uint32_t s01, uint32_t s10,
+                                                  uint32_t s11, int fx, int fy) {
+    const int w00 = (32 - fx) * (32 - fy), w01 = fx * (32 - fy), w10 = (32 - fx) * fy, w11 = fx * fy;
+    VmWarped o;
+    uint32_t b = ((s00 & 255u) * w00 + (s01 & 255u) * w01 + (s10 & 255u) * w10 + (s11 & 255u) * w11 + 512u) >> 10;
+    uint32_t g = (((s00 >> 8) & 255u) * w00 + ((s01 >> 8) & 255u) * w01 + ((s10 >> 8) & 255u) * w10 +
+                  ((s11 >> 8) & 255u) * w11 + 512u) >> 10;
+    uint32_t r = (((s00 >> 16) & 255u) * w00 + ((s01 >> 16) & 255u) * w01 + ((s10 >> 16) & 255u) * w10 +
+                  ((s11 >> 16) & 255u) * w11 + 512u) >> 10;
+    o.ta = (s00 >> 24) * w00 + (s01 >> 24) * w01 + (s10 >> 24) * w10 + (s11 >> 24) * w11;
+    o.bgr = b | (g << 8) | (r << 16);
+    return o;
+}
+
+// warp_bgr / warp_img at integer output position (i, j) given its backward flow vector.
+__device__ __forceinline__ VmWarped vm_flow_warp_bgra(const uint8_t *__restrict__ fg, int H, int W,
+                                                      int i, int j, float2 fb) {
+    const int SX = vm_cvround_x32(vm_map_coord(j, fb.x));
+    const int SY = vm_cvround_x32(vm_map_coord(i, fb.y));
+    const int ix = vm_sat_s16(SX >> 5), iy = vm_sat_s16(SY >> 5);
+    const int fx = SX & 31, fy = SY & 31;
+    const int64_t base = (int64_t)iy * W + ix;
+    uint32_t s00, s01, s10, s11;
+    if ((unsigned)ix < (unsigned)(W - 1) && (unsigned)iy < (unsigned)(H - 1)) {
+        s00 = vm_ldg_bgra(fg, base);     s01 = vm_ldg_bgra(fg, base + 1);
+        s10 = vm_ldg_bgra(fg, base + W); s11 = vm_ldg_bgra(fg, base + W + 1);
+    } else {
+        const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
+        const bool y0 = (unsigned)iy < (unsigned)H, y1 = (unsigned)(iy + 1) < (unsigned)H;
+        s00 = (y0 && x0) ? vm_ldg_bgra(fg, base) : 0u;
+        s01 = (y0 && x1) ? vm_ldg_bgra(fg, base + 1) : 0u;
+        s10 = (y1 && x0) ? vm_ldg_bgra(fg, base + W) : 0u;
+        s11 = (y1 && x1) ? vm_ldg_bgra(fg, base + W + 1) : 0u;
+    }
+    return vm_blend_bgra(s00, s01, s10, s11, fx, fy);
+}
+
+// flow.py:41-48 at pixel (i, j).  Returns 1 if err > 15 (alpha must be zeroed); flags:
+// bit0 = IndexError condition, bit1 = NaN/inf condition (reference would raise).
+__device__ __forceinline__ int vm_consistency(const float2 *__restrict__ forward, int H, int W,
+                                              int i, int j, float2 fb, int &flags) {
+    const float a = __fadd_rn(fb.x, (float)j), b = __fadd_rn(fb.y, (float)i);
+    if (!isfinite(a) || !isfinite(b)) { flags |= 2; return 1; }      // int(nan/inf) raises
+    // Python ints do not overflow: min() clamps the top; anything below -W / -H cannot be
+    // wrapped and raises IndexError.
+    const int j0 = (a >= (float)W) ? W - 1 : ((a <= -1.0e9f) ? -W - 1 : min(__float2int_rz(a), W - 1));
+    const int i0 = (b >= (float)H) ? H - 1 : ((b <= -1.0e9f) ? -H - 1 : min(__float2int_rz(b), H - 1));
+    const int jw = j0 < 0 ? j0 + W : j0, iw = i0 < 0 ? i0 + H : i0;
+    if (jw < 0 || iw < 0) { flags |= 1; return 1; }
+    const float2 ff = __ldg(forward + (int64_t)iw * W + jw);
+    const float c = __fadd_rn(ff.x, (float)j0), d = __fadd_rn(ff.y, (float)i0);
+    if (!isfinite(c) || !isfinite(d)) { flags |= 2; return 1; }
+    // |c| may exceed int32: Python ints do not overflow, min() clamps the top, the bottom
+    // only grows the error -> masked either way.
+    const float cc = fmaxf(c, -1.0e9f), dd = fmaxf(d, -1.0e9f);
+    const int j1 = (cc >= (float)W) ? W - 1 : min(__float2int_rz(cc), W - 1);
+    const int i1 = (dd >= (float)H) ? H - 1 : min(__float2int_rz(dd), H - 1);
+    const long long di = (long long)i1 - i, dj = (long long)j1 - j;
+    return (di * di + dj * dj > 225) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// scipy.ndimage.map_coordinates(order=1, mode='constant', cval=0)
+// ---------------------------------------------------------------------------------------
+struct VmBilin64 { double a0, a1, b0, b1; int i0, i1, j0, j1; bool inside; };
+
+__device__ __forceinline__ VmBilin64 vm_mapcoord_setup(double t0, double t1, int H, int W) {
+    VmBilin64 s;
+    s.inside = (t0 >= 0.0) && (t0 <= (double)(H - 1)) && (t1 >= 0.0) && (t1 <= (double)(W - 1));
+    const double f0 = floor(t0), f1 = floor(t1);
+    s.i0 = s.inside ? (int)f0 : 0;
+    s.j0 = s.inside ? (int)f1 : 0;
+    const double a = t0 - f0, b = t1 - f1;
+    s.a0 = 1.0 - a; s.a1 = 1.0 - s.a0;          // scipy: w1 = 1 - w0
+    s.b0 = 1.0 - b; s.b1 = 1.0 - s.b0;
+    s.i1 = min(s.i0 + 1, H - 1);
+    s.j1 = min(s.j0 + 1, W - 1);
+    return s;
+}
+
+__device__ __forceinline__ double vm_mapcoord_blend(const VmBilin64 &s, double s00, double s01,
+                                                    double s10, double s11) {
+    double v = __dmul_rn(__dmul_rn(s00, s.a0), s.b0);
+    v = __dadd_rn(v, __dmul_rn(__dmul_rn(s01, s.a0), s.b1));
+    v = __dadd_rn(v, __dmul_rn(__dmul_rn(s10, s.a1), s.b0));
+    v = __dadd_rn(v, __dmul_rn(__dmul_rn(s11, s.a1), s.b1));
+    return v;
+}
+
+__device__ __forceinline__ uint8_t vm_round_half_up_u8(double v) {
+    const double r = floor(v + 0.5);
+    return (uint8_t)(r < 0.0 ? 0 : (r > 255.0 ? 255 : (int)r));
+}
+
+// ---------------------------------------------------------------------------------------
+// bilinear up-sampling of the coarse TPS transform (tps.py:55-74)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double vm_upsample_exact(double t00, double t01, double t10, double t11,
+                                                    double xf, double yf) {
+    const double x1 = 1.0 - xf, y1 = 1.0 - yf;
+    double v = __dmul_rn(__dmul_rn(t00, x1), y1);
+    v = __dadd_rn(v, __dmul_rn(__dmul_rn(t01, x1), yf));
+    v = __dadd_rn(v, __dmul_rn(__dmul_rn(t10, xf), y1));
+    v = __dadd_rn(v, __dmul_rn(__dmul_rn(t11, xf), yf));
+    return v;
+}

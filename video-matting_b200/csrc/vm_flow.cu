@@ -1,0 +1,227 @@
+// Flow warp, forward/backward consistency mask and compositing kernels.
+// Reference behaviour: flow.py:9-65, reader.py:72-79 (see include/vm_b200.h).
+#include "vm_common.cuh"
+
+// ---------------------------------------------------------------------------------------
+// generic drop-in kernels (any size, any of uint8/float32/float64, 1/3/4 channels)
+// ---------------------------------------------------------------------------------------
+template <typename T, int C>
+__global__ void __launch_bounds__(256)
+k_flow_warp(const T *__restrict__ src, int sh, int sw, const float2 *__restrict__ flow,
+            int h, int w, T *__restrict__ dst) {
+    const int64_t n = (int64_t)h * w;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(p / w), j = (int)(p - (int64_t)i * w);
+        const float2 f = __ldg(flow + p);
+        const int SX = vm_cvround_x32(vm_map_coord(j, f.x));
+        const int SY = vm_cvround_x32(vm_map_coord(i, f.y));
+        T out[C];
+        vm_sample_fixed<T, C>(src, sh, sw, SX, SY, out);
+#pragma unroll
+        for (int c = 0; c < C; ++c) dst[p * C + c] = out[c];
+    }
+}
+
+template <typename T>
+static int launch_flow_warp(const void *src, int channels, int sh, int sw, const float *flow,
+                            int h, int w, void *dst, cudaStream_t st) {
+    const int64_t n = (int64_t)h * w;
+    const unsigned grid = min(vm_blocks(n, 256), 148u * 32u);
+    const float2 *f2 = reinterpret_cast<const float2 *>(flow);
+    switch (channels) {
+    case 1: k_flow_warp<T, 1><<<grid, 256, 0, st>>>((const T *)src, sh, sw, f2, h, w, (T *)dst); break;
+    case 3: k_flow_warp<T, 3><<<grid, 256, 0, st>>>((const T *)src, sh, sw, f2, h, w, (T *)dst); break;
+    case 4: k_flow_warp<T, 4><<<grid, 256, 0, st>>>((const T *)src, sh, sw, f2, h, w, (T *)dst); break;
+    default: vm_set_error("vm_flow_warp: channels must be 1, 3 or 4"); return VM_ERR_ARG;
+    }
+    return vm_check_launch("vm_flow_warp");
+}
+
+extern "C" int vm_flow_warp(const void *src, int dtype, int channels, int sh, int sw,
+                            const float *flow, int h, int w, void *dst, void *stream) {
+    VM_REQUIRE(src && flow && dst, "null pointer");
+    VM_REQUIRE(sh > 0 && sw > 0 && h >= 0 && w >= 0, "bad size");
+    if ((int64_t)h * w == 0) return VM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+    case VM_U8:  return launch_flow_warp<uint8_t>(src, channels, sh, sw, flow, h, w, dst, st);
+    case VM_F32: return launch_flow_warp<float>(src, channels, sh, sw, flow, h, w, dst, st);
+    case VM_F64: return launch_flow_warp<double>(src, channels, sh, sw, flow, h, w, dst, st);
+    }
+    vm_set_error("vm_flow_warp: unsupported dtype %d", dtype);
+    return VM_ERR_ARG;
+}
+
+__global__ void __launch_bounds__(256)
+k_occlusion_mask(const float2 *__restrict__ bwd, const float2 *__restrict__ fwd, int h, int w,
+                 uint8_t *__restrict__ mask, int32_t *__restrict__ status) {
+    const int64_t n = (int64_t)h * w;
+    int idx_err = 0, nan_err = 0, masked = 0;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(p / w), j = (int)(p - (int64_t)i * w);
+        int flags = 0;
+        const int m = vm_consistency(fwd, h, w, i, j, __ldg(bwd + p), flags);
+        mask[p] = (uint8_t)(m && !flags);
+        idx_err += flags & 1; nan_err += (flags >> 1) & 1; masked += (m && !flags);
+    }
+    if (status) {
+        if (idx_err) atomicAdd(status + VM_STATUS_INDEX_ERR, idx_err);
+        if (nan_err) atomicAdd(status + VM_STATUS_NAN_ERR, nan_err);
+        if (masked) atomicAdd(status + VM_STATUS_MASKED, masked);
+    }
+}
+
+extern "C" int vm_occlusion_mask(const float *backward, const float *forward, int h, int w,
+                                 uint8_t *mask, int32_t *status, void *stream) {
+    VM_REQUIRE(backward && forward && mask, "null pointer");
+    VM_REQUIRE(h >= 0 && w >= 0, "bad size");
+    const int64_t n = (int64_t)h * w;
+    if (n == 0) return VM_OK;
+    k_occlusion_mask<<<min(vm_blocks(n, 256), 148u * 32u), 256, 0, (cudaStream_t)stream>>>(
+        (const float2 *)backward, (const float2 *)forward, h, w, mask, status);
+    return vm_check_launch("vm_occlusion_mask");
+}
+
+template <typename T>
+__global__ void k_apply_mask(T *__restrict__ alpha, const uint8_t *__restrict__ mask, int64_t n) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+         p += (int64_t)gridDim.x * blockDim.x)
+        if (mask[p]) alpha[p] = T(0);
+}
+
+extern "C" int vm_apply_mask(void *alpha, int dtype, const uint8_t *mask, int64_t n, void *stream) {
+    VM_REQUIRE(alpha && mask, "null pointer");
+    if (n <= 0) return VM_OK;
+    const unsigned grid = min(vm_blocks(n, 256), 148u * 32u);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+    case VM_U8:  k_apply_mask<uint8_t><<<grid, 256, 0, st>>>((uint8_t *)alpha, mask, n); break;
+    case VM_F32: k_apply_mask<float><<<grid, 256, 0, st>>>((float *)alpha, mask, n); break;
+    case VM_F64: k_apply_mask<double><<<grid, 256, 0, st>>>((double *)alpha, mask, n); break;
+    default: vm_set_error("vm_apply_mask: unsupported dtype %d", dtype); return VM_ERR_ARG;
+    }
+    return vm_check_launch("vm_apply_mask");
+}
+
+// reader.py:72-79: tri*fg + (1-tri)*bg in float64, no FMA contraction.
+template <typename TF, typename TB>
+__global__ void k_composite(const TF *__restrict__ fg, const TB *__restrict__ bg,
+                            const double *__restrict__ alpha, int64_t npx, double *__restrict__ out) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npx;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        const double a = alpha[p], na = __dadd_rn(1.0, -a);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            out[p * 3 + c] = __dadd_rn(__dmul_rn(a, (double)fg[p * 3 + c]), __dmul_rn(na, (double)bg[p * 3 + c]));
+    }
+}
+
+extern "C" int vm_composite(const void *fg, int fg_dtype, const void *bg, int bg_dtype,
+                            const double *alpha, int h, int w, double *out, void *stream) {
+    VM_REQUIRE(fg && bg && alpha && out, "null pointer");
+    const int64_t n = (int64_t)h * w;
+    if (n <= 0) return VM_OK;
+    const unsigned grid = min(vm_blocks(n, 256), 148u * 32u);
+    cudaStream_t st = (cudaStream_t)stream;
+#define VM_CMP(TF, TB) k_composite<TF, TB><<<grid, 256, 0, st>>>((const TF *)fg, (const TB *)bg, alpha, n, out)
+    if (fg_dtype == VM_U8 && bg_dtype == VM_U8) VM_CMP(uint8_t, uint8_t);
+    else if (fg_dtype == VM_U8 && bg_dtype == VM_F64) VM_CMP(uint8_t, double);
+    else if (fg_dtype == VM_F64 && bg_dtype == VM_U8) VM_CMP(double, uint8_t);
+    else if (fg_dtype == VM_F64 && bg_dtype == VM_F64) VM_CMP(double, double);
+    else if (fg_dtype == VM_F32 && bg_dtype == VM_F32) VM_CMP(float, float);
+    else if (fg_dtype == VM_U8 && bg_dtype == VM_F32) VM_CMP(uint8_t, float);
+    else if (fg_dtype == VM_F32 && bg_dtype == VM_U8) VM_CMP(float, uint8_t);
+    else { vm_set_error("vm_composite: unsupported dtype pair %d/%d", fg_dtype, bg_dtype); return VM_ERR_ARG; }
+#undef VM_CMP
+    return vm_check_launch("vm_composite");
+}
+
+// ---------------------------------------------------------------------------------------
+// fused C2 kernel: warp_bgr + warp_img + correct_alpha on BGRA frames, 27 B/px.
+//
+// CTA = 256 threads = 8 warps; tile = 128 px wide x 8 rows; each thread owns 4 consecutive
+// pixels of one row: two 16-byte flow loads, 16 BGRA taps through the read-only path (tap rows
+// of vertically adjacent warps overlap in L1), 4 nearest forward-flow gathers, then one
+// 16-byte alpha store and 12 bytes of BGR (three 4-byte stores; a thread's 4 px * 3 B are
+// 4-byte aligned because the thread's first pixel index is a multiple of 4).
+// ---------------------------------------------------------------------------------------
+#define C2_TW 128
+#define C2_TH 8
+
+template <bool HAS_FWD>
+__global__ void __launch_bounds__(256)
+k_flow_warp_mask_bgra(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd,
+                      const float2 *__restrict__ fwd, int h, int w, int tiles_x, int tiles_y,
+                      uint8_t *__restrict__ out_bgr, float *__restrict__ out_alpha,
+                      int32_t *__restrict__ status) {
+    const int tile = blockIdx.x;
+    const int frame = tile / (tiles_x * tiles_y);
+    const int t = tile - frame * tiles_x * tiles_y;
+    const int ty = t / tiles_x, tx = t - ty * tiles_x;
+    const int i = ty * C2_TH + (threadIdx.x >> 5);
+    const int j = tx * C2_TW + (threadIdx.x & 31) * 4;
+    if (i >= h || j >= w) return;
+    const int64_t fbase = (int64_t)frame * h * w;
+    const uint8_t *fgf = fg + fbase * 4;
+    const float2 *bf = bwd + fbase;
+    const float2 *ff = HAS_FWD ? fwd + fbase : nullptr;
+    const int64_t p = (int64_t)i * w + j;
+    int flags = 0;
+    if (j + 3 < w && (w & 3) == 0) {
+        const float4 f01 = __ldg(reinterpret_cast<const float4 *>(bf + p));
+        const float4 f23 = __ldg(reinterpret_cast<const float4 *>(bf + p + 2));
+        const float2 fl[4] = {{f01.x, f01.y}, {f01.z, f01.w}, {f23.x, f23.y}, {f23.z, f23.w}};
+        VmWarped wv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) wv[k] = vm_flow_warp_bgra(fgf, h, w, i, j + k, fl[k]);
+        float al[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int m = 0;
+            if (HAS_FWD) m = vm_consistency(ff, h, w, i, j + k, fl[k], flags);
+            al[k] = m ? 0.f : __fdiv_rn((float)wv[k].ta, (float)VM_ALPHA_DEN);
+        }
+        // 12 bytes of BGR: b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3
+        const uint32_t c0 = wv[0].bgr, c1 = wv[1].bgr, c2 = wv[2].bgr, c3 = wv[3].bgr;
+        uint32_t *ob = reinterpret_cast<uint32_t *>(out_bgr + (fbase + p) * 3);
+        ob[0] = c0 | (c1 << 24);
+        ob[1] = (c1 >> 8) | (c2 << 16);
+        ob[2] = (c2 >> 16) | (c3 << 8);
+        *reinterpret_cast<float4 *>(out_alpha + fbase + p) = make_float4(al[0], al[1], al[2], al[3]);
+    } else {
+        for (int k = 0; k < 4 && j + k < w; ++k) {
+            const float2 f = __ldg(bf + p + k);
+            const VmWarped wv = vm_flow_warp_bgra(fgf, h, w, i, j + k, f);
+            int m = 0;
+            if (HAS_FWD) m = vm_consistency(ff, h, w, i, j + k, f, flags);
+            uint8_t *ob = out_bgr + (fbase + p + k) * 3;
+            ob[0] = (uint8_t)wv.bgr; ob[1] = (uint8_t)(wv.bgr >> 8); ob[2] = (uint8_t)(wv.bgr >> 16);
+            out_alpha[fbase + p + k] = m ? 0.f : __fdiv_rn((float)wv.ta, (float)VM_ALPHA_DEN);
+        }
+    }
+    if (HAS_FWD && flags && status) {
+        if (flags & 1) atomicAdd(status + VM_STATUS_INDEX_ERR, 1);
+        if (flags & 2) atomicAdd(status + VM_STATUS_NAN_ERR, 1);
+    }
+}
+
+extern "C" int vm_flow_warp_mask_bgra(const uint8_t *fg, const float *backward, const float *forward,
+                                      int n, int h, int w, uint8_t *out_bgr, float *out_alpha,
+                                      int32_t *status, void *stream) {
+    VM_REQUIRE(fg && backward && out_bgr && out_alpha, "null pointer");
+    VM_REQUIRE(n >= 0 && h > 0 && w > 0, "bad size");
+    if (n == 0) return VM_OK;
+    const int tiles_x = (w + C2_TW - 1) / C2_TW, tiles_y = (h + C2_TH - 1) / C2_TH;
+    const int64_t tiles = (int64_t)n * tiles_x * tiles_y;
+    VM_REQUIRE(tiles < (1ll << 31), "too many tiles for one launch");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (forward)
+        k_flow_warp_mask_bgra<true><<<(unsigned)tiles, 256, 0, st>>>(
+            fg, (const float2 *)backward, (const float2 *)forward, h, w, tiles_x, tiles_y, out_bgr, out_alpha, status);
+    else
+        k_flow_warp_mask_bgra<false><<<(unsigned)tiles, 256, 0, st>>>(
+            fg, (const float2 *)backward, nullptr, h, w, tiles_x, tiles_y, out_bgr, out_alpha, status);
+    return vm_check_launch("vm_flow_warp_mask_bgra");
+}

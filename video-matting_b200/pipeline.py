@@ -1,0 +1,353 @@
+"""Device-resident API of the B200 video-matting data path.
+
+Everything here takes and returns CUDA tensors in the canonical layouts and only
+enqueues work on the current stream - no host synchronisation, no allocation beyond the
+outputs.  The drop-in modules (flow.py, tps.py, augmentation.py, reader.py) are thin
+NumPy-compatible wrappers over these functions.
+
+Canonical layouts
+    fg     (n, H, W, 4) uint8  BGRA, alpha = A/255          (reference reader.py:16-17)
+    flow   (n, H, W, 2) float32 (dx, dy)                    (reference reader.py:29)
+    bg     (n_bg, H, W, 3) uint8 BGR
+    out    (n, H, W, 4) float32 {B, G, R composite, alpha'} / (n,H,W,3) uint8 + (n,H,W) float32
+"""
+import ctypes
+import functools
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+AXIS_DTYPE = np.dtype([("frac", "<f8"), ("i0", "<i4"), ("i1", "<i4")])
+
+
+# ----------------------------------------------------------------------------------------
+# generic single-image ops (any size; uint8 / float32 / float64)
+# ----------------------------------------------------------------------------------------
+
+def flow_warp(src, flow):
+    """cv2.remap(src, grid + flow, INTER_LINEAR) - reference flow.py:9-33.
+    src (sh, sw) or (sh, sw, C) with C in {1,3,4}; flow (h, w, 2) float32."""
+    lib = N.load()
+    assert flow.dtype == torch.float32 and flow.dim() == 3 and flow.shape[2] == 2
+    src = src.contiguous()
+    flow = flow.contiguous()
+    ch = 1 if src.dim() == 2 else src.shape[2]
+    h, w = flow.shape[:2]
+    shape = (h, w) if src.dim() == 2 else (h, w, ch)
+    dst = torch.empty(shape, dtype=src.dtype, device=src.device)
+    N.check(lib.vm_flow_warp(N.ptr(src), N.dtype_code(src), ch, src.shape[0], src.shape[1],
+                             N.ptr(flow), h, w, N.ptr(dst), N.stream_ptr()))
+    return dst
+
+
+def occlusion_mask(backward, forward, status=None):
+    """uint8 mask of the pixels reference flow.py:41-50 zeroes; status counts the pixels
+    where the reference would raise (IndexError / ValueError)."""
+    lib = N.load()
+    backward = backward.contiguous()
+    forward = forward.contiguous()
+    h, w = backward.shape[:2]
+    if status is None:
+        status = N.new_status(backward.device)
+    mask = torch.empty((h, w), dtype=torch.uint8, device=backward.device)
+    # the reference indexes `forward` with coordinates clamped to backward's size
+    if forward.shape[1] != w or forward.shape[0] < h:
+        raise IndexError("forward flow must have backward's width and at least its height")
+    N.check(lib.vm_occlusion_mask(N.ptr(backward), N.ptr(forward), h, w, N.ptr(mask), N.ptr(status),
+                                  N.stream_ptr()))
+    return mask, status
+
+
+def apply_mask(alpha, mask):
+    """alpha[mask] = 0 in place (reference flow.py:49-50)."""
+    lib = N.load()
+    assert alpha.is_contiguous() and mask.is_contiguous() and alpha.numel() == mask.numel()
+    N.check(lib.vm_apply_mask(N.ptr(alpha), N.dtype_code(alpha), N.ptr(mask), alpha.numel(), N.stream_ptr()))
+    return alpha
+
+
+def composite(fg, bg, alpha):
+    """alpha*fg + (1-alpha)*bg in float64 - reference reader.py:72-79."""
+    lib = N.load()
+    fg, bg = fg.contiguous(), bg.contiguous()
+    alpha = alpha.to(torch.float64).contiguous()
+    h, w = fg.shape[:2]
+    assert fg.shape == (h, w, 3) and bg.shape == (h, w, 3) and alpha.shape == (h, w)
+    out = torch.empty((h, w, 3), dtype=torch.float64, device=fg.device)
+    N.check(lib.vm_composite(N.ptr(fg), N.dtype_code(fg), N.ptr(bg), N.dtype_code(bg), N.ptr(alpha), h, w,
+                             N.ptr(out), N.stream_ptr()))
+    return out
+
+
+def warp_affine(src, M, dsize):
+    """cv2.warpAffine(src, M, (dw, dh)) default flags - reference augmentation.py:59-62."""
+    lib = N.load()
+    src = src.contiguous()
+    dw, dh = int(dsize[0]), int(dsize[1])
+    ch = 1 if src.dim() == 2 else src.shape[2]
+    Mh = np.ascontiguousarray(np.asarray(M, dtype=np.float64).reshape(6))
+    dst = torch.empty((dh, dw) if src.dim() == 2 else (dh, dw, ch), dtype=src.dtype, device=src.device)
+    N.check(lib.vm_warp_affine(N.ptr(src), N.dtype_code(src), ch, src.shape[0], src.shape[1],
+                               Mh.ctypes.data_as(ctypes.c_void_p), dh, dw, N.ptr(dst), N.stream_ptr()))
+    return dst
+
+
+def illumination(bgr, lut):
+    """BGR2HSV -> S,V through a 256-entry table -> HSV2BGR (reference augmentation.py:88-99)."""
+    lib = N.load()
+    bgr = bgr.contiguous()
+    assert bgr.dtype == torch.uint8 and bgr.shape[-1] == 3
+    lut = np.ascontiguousarray(lut, dtype=np.uint8)
+    assert lut.shape == (256,)
+    out = torch.empty_like(bgr)
+    N.check(lib.vm_illumination_lut(N.ptr(bgr), bgr.numel() // 3, lut.ctypes.data_as(ctypes.c_void_p),
+                                    N.ptr(out), N.stream_ptr()))
+    return out
+
+
+def alpha_stats(alpha):
+    """device uint64[3] = {count(alpha != 0), sum(rows), sum(cols)} (augmentation.py:10-21)."""
+    lib = N.load()
+    alpha = alpha.contiguous()
+    h, w = alpha.shape
+    out = torch.zeros(3, dtype=torch.int64, device=alpha.device)
+    N.check(lib.vm_alpha_stats(N.ptr(alpha), N.dtype_code(alpha), h, w, N.ptr(out), N.stream_ptr()))
+    return out
+
+
+def map_coordinates(src, t0, t1, status=None):
+    """scipy.ndimage.map_coordinates(src, [t0, t1], order=1) - reference tps.py:34."""
+    lib = N.load()
+    src = src.contiguous()
+    t0 = t0.to(torch.float64).contiguous()
+    t1 = t1.to(torch.float64).contiguous()
+    ch = 1 if src.dim() == 2 else src.shape[2]
+    oh, ow = t0.shape
+    dst = torch.empty((oh, ow) if src.dim() == 2 else (oh, ow, ch), dtype=src.dtype, device=src.device)
+    N.check(lib.vm_map_coordinates(N.ptr(src), N.dtype_code(src), ch, src.shape[0], src.shape[1], N.ptr(t0),
+                                   N.ptr(t1), oh, ow, N.ptr(dst), N.ptr(status), N.stream_ptr()))
+    return dst
+
+
+# ----------------------------------------------------------------------------------------
+# thin-plate spline: host solve + device evaluation
+# ----------------------------------------------------------------------------------------
+
+def _tps_kernel_matrix(points):
+    """L = [[K, P], [P^T, 0]], K_ab = U(|P_a - P_b|), U(r) = r^2 log r (reference tps.py:78-98).
+    The expression order is the reference's so that L - and therefore numpy's truncated
+    pseudo-inverse of it - is bit-identical."""
+    pts = np.asarray(points, dtype=np.float64)
+    n = len(pts)
+    d0 = np.subtract.outer(pts[:, 0], pts[:, 0])
+    d1 = np.subtract.outer(pts[:, 1], pts[:, 1])
+    r = np.sqrt(d0 ** 2 + d1 ** 2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        K = (r ** 2) * np.where(r < 1e-100, 0, np.log(r))
+    L = np.zeros((n + 3, n + 3))
+    L[:n, :n] = K
+    L[:n, n] = 1.0
+    L[:n, n + 1:] = pts
+    L[n:, :n] = L[:n, n:].T
+    return L
+
+
+def tps_solve(src_points, dst_points):
+    """Spline coefficients (N+3, 2) mapping src_points onto dst_points: numpy's own
+    ``dot(pinv(L), V)`` (reference tps.py:113-119) - called, not re-implemented, because the
+    rcond=1e-15 truncation is active for 1080p/4K grids."""
+    dst = np.asarray(dst_points, dtype=np.float64)
+    V = np.zeros((len(dst) + 3, 2))
+    V[:len(dst)] = dst
+    return np.dot(np.linalg.pinv(_tps_kernel_matrix(src_points)), V)
+
+
+def axis_table(lo, hi, steps):
+    """Up-sampling indices/fractions for one axis (reference tps.py:55-63)."""
+    new = np.arange(lo, hi + 1)
+    frac, idx = np.modf((steps - 1) * (new - lo) / float(hi - lo))
+    i0 = idx.astype(int)
+    i1 = (i0 + 1).clip(0, steps - 1).astype(int)
+    tab = np.zeros(len(new), dtype=AXIS_DTYPE)
+    tab["frac"], tab["i0"], tab["i1"] = frac, i0, i1
+    return tab
+
+
+class TpsPlan:
+    """Everything about the TPS evaluation that depends on the output region only."""
+
+    def __init__(self, region, approximate_grid=2, device=None):
+        x_min, y_min, x_max, y_max = region
+        if approximate_grid is None:
+            approximate_grid = 1
+        self.region = (x_min, y_min, x_max, y_max)
+        self.approximate_grid = approximate_grid
+        self.x_steps = (x_max - x_min) / approximate_grid
+        self.y_steps = (y_max - y_min) / approximate_grid
+        self.nx, self.ny = int(self.x_steps), int(self.y_steps)
+        if self.nx < 2 or self.ny < 2:
+            raise ValueError("output region too small for the TPS grid")
+        # np.mgrid[a:b:n*1j] -> arange(n) * ((b - a) / (n - 1)) + a
+        self.step_x = (x_max - x_min) / float(self.nx - 1)
+        self.step_y = (y_max - y_min) / float(self.ny - 1)
+        self.device = torch.device(device if device is not None else "cuda")
+        if approximate_grid != 1:
+            self.out_h, self.out_w = x_max - x_min + 1, y_max - y_min + 1
+            rows = axis_table(x_min, x_max, self.x_steps)
+            cols = axis_table(y_min, y_max, self.y_steps)
+            self.rows = torch.from_numpy(rows.view(np.uint8).copy()).to(self.device)
+            self.cols = torch.from_numpy(cols.view(np.uint8).copy()).to(self.device)
+        else:
+            self.out_h, self.out_w = self.nx, self.ny
+            self.rows = self.cols = None
+
+
+@functools.lru_cache(maxsize=32)
+def _cached_plan(region, approximate_grid, device_index):
+    return TpsPlan(region, approximate_grid, torch.device("cuda", device_index))
+
+
+def get_plan(region, approximate_grid=2, device=None):
+    dev = torch.device(device if device is not None else "cuda")
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    return _cached_plan(tuple(int(v) for v in region), approximate_grid, idx)
+
+
+def tps_coarse(ctrl, coef, plan, out=None):
+    """Evaluate the spline on the coarse grid of ``plan``.  ctrl (n, N, 2), coef (n, N+3, 2)
+    float64 CUDA tensors -> coarse (n, 2, nx, ny) float64."""
+    lib = N.load()
+    ctrl = ctrl.to(torch.float64).contiguous()
+    coef = coef.to(torch.float64).contiguous()
+    n, Np = ctrl.shape[0], ctrl.shape[1]
+    assert coef.shape == (n, Np + 3, 2)
+    if out is None:
+        out = torch.empty((n, 2, plan.nx, plan.ny), dtype=torch.float64, device=ctrl.device)
+    N.check(lib.vm_tps_coarse(N.ptr(ctrl), N.ptr(coef), n, Np, plan.nx, plan.ny, plan.step_x, plan.step_y,
+                              float(plan.region[0]), float(plan.region[1]), N.ptr(out), N.stream_ptr()))
+    return out
+
+
+def tps_transform(coarse, plan):
+    """(2, H+1, W+1) float64 inverse transform (reference tps._make_inverse_warp)."""
+    lib = N.load()
+    assert coarse.shape == (2, plan.nx, plan.ny)
+    if plan.approximate_grid == 1:
+        return coarse
+    h, w = plan.out_h - 1, plan.out_w - 1
+    out = torch.empty((2, h + 1, w + 1), dtype=torch.float64, device=coarse.device)
+    N.check(lib.vm_tps_upsample(N.ptr(coarse), plan.nx, plan.ny, N.ptr(plan.rows), N.ptr(plan.cols), h, w,
+                                N.ptr(out), N.stream_ptr()))
+    return out
+
+
+def tps_warp(src, coarse, plan, out_hw=None, status=None):
+    """Fused up-sample + map_coordinates of one image (reference tps.warp_images, one entry)."""
+    lib = N.load()
+    src = src.contiguous()
+    if plan.approximate_grid == 1:
+        return map_coordinates(src, coarse[0], coarse[1], status)
+    ch = 1 if src.dim() == 2 else src.shape[2]
+    oh, ow = out_hw if out_hw is not None else (plan.out_h, plan.out_w)
+    assert oh <= plan.out_h and ow <= plan.out_w
+    dst = torch.empty((oh, ow) if src.dim() == 2 else (oh, ow, ch), dtype=src.dtype, device=src.device)
+    N.check(lib.vm_tps_warp(N.ptr(src), N.dtype_code(src), ch, src.shape[0], src.shape[1], N.ptr(coarse),
+                            plan.nx, plan.ny, N.ptr(plan.rows), N.ptr(plan.cols), oh, ow, N.ptr(dst),
+                            N.ptr(status), N.stream_ptr()))
+    return dst
+
+
+def solve_grids(grids, device=None):
+    """Host solve for a batch of (regular grid, deformed grid) pairs as used by
+    augmentation.warp_image(..., thin=grids): the system is built from the DEFORMED grid and maps
+    back onto the regular one (reference tps.py:51).  Returns CUDA (ctrl, coef)."""
+    ctrl = np.stack([np.asarray(d, dtype=np.float64) for (_, d) in grids])
+    coef = np.stack([tps_solve(d, g) for (g, d) in grids])
+    dev = torch.device(device if device is not None else "cuda")
+    return torch.from_numpy(ctrl).to(dev), torch.from_numpy(coef).to(dev)
+
+
+# ----------------------------------------------------------------------------------------
+# fused clip-level kernels
+# ----------------------------------------------------------------------------------------
+
+def _check_clip(fg, h, w):
+    assert fg.dtype == torch.uint8 and fg.dim() == 4 and fg.shape[3] == 4 and fg.is_contiguous(), \
+        "fg must be a contiguous (n, H, W, 4) uint8 BGRA tensor"
+
+
+def flow_warp_mask(fg, backward, forward=None, out_bgr=None, out_alpha=None, status=None):
+    """warp_bgr + warp_img + correct_alpha for a clip (reference flow.py:9-65), one pass.
+    Returns (bgr uint8 (n,H,W,3), alpha float32 (n,H,W), status)."""
+    lib = N.load()
+    n, h, w = fg.shape[:3]
+    _check_clip(fg, h, w)
+    assert backward.dtype == torch.float32 and backward.shape == (n, h, w, 2) and backward.is_contiguous()
+    if forward is not None:
+        assert forward.dtype == torch.float32 and forward.shape == (n, h, w, 2) and forward.is_contiguous()
+    if out_bgr is None:
+        out_bgr = torch.empty((n, h, w, 3), dtype=torch.uint8, device=fg.device)
+    if out_alpha is None:
+        out_alpha = torch.empty((n, h, w), dtype=torch.float32, device=fg.device)
+    if status is None:
+        status = N.new_status(fg.device)
+    N.check(lib.vm_flow_warp_mask_bgra(N.ptr(fg), N.ptr(backward), N.ptr(forward), n, h, w, N.ptr(out_bgr),
+                                       N.ptr(out_alpha), N.ptr(status), N.stream_ptr()))
+    return out_bgr, out_alpha, status
+
+
+def tps_composite(fg, bg, ctrl, coef, plan=None, out=None, coarse=None, status=None):
+    """TPS warp of fg/alpha + composite onto bg (C3).  Returns (out float32 (n,H,W,4), status)."""
+    lib = N.load()
+    n, h, w = fg.shape[:3]
+    _check_clip(fg, h, w)
+    assert bg.dtype == torch.uint8 and bg.dim() == 4 and bg.shape[1:] == (h, w, 3) and bg.is_contiguous()
+    plan = plan or get_plan((0, 0, h, w), 2, fg.device)
+    coarse = tps_coarse(ctrl, coef, plan, out=coarse)
+    if out is None:
+        out = torch.empty((n, h, w, 4), dtype=torch.float32, device=fg.device)
+    if status is None:
+        status = N.new_status(fg.device)
+    N.check(lib.vm_tps_composite_bgra(N.ptr(fg), N.ptr(bg), bg.shape[0], N.ptr(coarse), plan.nx, plan.ny,
+                                      N.ptr(plan.rows), N.ptr(plan.cols), n, h, w, N.ptr(out), N.ptr(status),
+                                      N.stream_ptr()))
+    return out, status
+
+
+def flow_tps_composite(fg, backward, forward, bg, ctrl, coef, plan=None, out=None, coarse=None,
+                       scratch=None, status=None):
+    """flow warp + consistency mask + TPS + composite (SURVEY 8d C4 pipeline), 39 B/px.
+    Returns (out float32 (n,H,W,4), status)."""
+    lib = N.load()
+    n, h, w = fg.shape[:3]
+    _check_clip(fg, h, w)
+    assert backward.dtype == torch.float32 and backward.shape == (n, h, w, 2) and backward.is_contiguous()
+    if forward is not None:
+        assert forward.dtype == torch.float32 and forward.shape == (n, h, w, 2) and forward.is_contiguous()
+    assert bg.dtype == torch.uint8 and bg.dim() == 4 and bg.shape[1:] == (h, w, 3) and bg.is_contiguous()
+    plan = plan or get_plan((0, 0, h, w), 2, fg.device)
+    coarse = tps_coarse(ctrl, coef, plan, out=coarse)
+    if out is None:
+        out = torch.empty((n, h, w, 4), dtype=torch.float32, device=fg.device)
+    if status is None:
+        status = N.new_status(fg.device)
+    need = lib.vm_flow_tps_scratch_bytes(n, h, w)
+    if need and (scratch is None or scratch.numel() < need):
+        scratch = torch.empty(need, dtype=torch.uint8, device=fg.device)
+    N.check(lib.vm_flow_tps_composite_bgra(N.ptr(fg), N.ptr(backward), N.ptr(forward), N.ptr(bg), bg.shape[0],
+                                           N.ptr(coarse), plan.nx, plan.ny, N.ptr(plan.rows), N.ptr(plan.cols),
+                                           n, h, w, N.ptr(out), N.ptr(scratch), N.ptr(status), N.stream_ptr()))
+    return out, status
+
+
+# ----------------------------------------------------------------------------------------
+# clip sharding: independent clips, no collective on the data path
+# ----------------------------------------------------------------------------------------
+
+def shard_range(n_units, rank, world):
+    """Contiguous slice [lo, hi) of n_units owned by ``rank`` (sizes differ by at most 1)."""
+    base, rem = divmod(n_units, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
