@@ -274,8 +274,15 @@ def solve_grids(grids, device=None):
 # ----------------------------------------------------------------------------------------
 
 def _check_clip(fg, h, w):
-    assert fg.dtype == torch.uint8 and fg.dim() == 4 and fg.shape[3] == 4 and fg.is_contiguous(), \
-        "fg must be a contiguous (n, H, W, 4) uint8 BGRA tensor"
+    assert fg.dtype == torch.uint8 and fg.dim() == 4 and fg.shape[3] == 4, \
+        "fg must be an (n, H, W, 4) uint8 BGRA tensor"
+
+
+def _flow_arg(flow, n, h, w, name):
+    if flow is None:
+        return None
+    assert flow.dtype == torch.float32 and flow.shape == (n, h, w, 2), f"{name} must be (n, H, W, 2) float32"
+    return flow.contiguous()
 
 
 def flow_warp_mask(fg, backward, forward=None, out_bgr=None, out_alpha=None, status=None):
@@ -284,9 +291,8 @@ def flow_warp_mask(fg, backward, forward=None, out_bgr=None, out_alpha=None, sta
     lib = N.load()
     n, h, w = fg.shape[:3]
     _check_clip(fg, h, w)
-    assert backward.dtype == torch.float32 and backward.shape == (n, h, w, 2) and backward.is_contiguous()
-    if forward is not None:
-        assert forward.dtype == torch.float32 and forward.shape == (n, h, w, 2) and forward.is_contiguous()
+    fg = fg.contiguous()
+    backward, forward = _flow_arg(backward, n, h, w, "backward"), _flow_arg(forward, n, h, w, "forward")
     if out_bgr is None:
         out_bgr = torch.empty((n, h, w, 3), dtype=torch.uint8, device=fg.device)
     if out_alpha is None:
@@ -303,7 +309,8 @@ def tps_composite(fg, bg, ctrl, coef, plan=None, out=None, coarse=None, status=N
     lib = N.load()
     n, h, w = fg.shape[:3]
     _check_clip(fg, h, w)
-    assert bg.dtype == torch.uint8 and bg.dim() == 4 and bg.shape[1:] == (h, w, 3) and bg.is_contiguous()
+    assert bg.dtype == torch.uint8 and bg.dim() == 4 and bg.shape[1:] == (h, w, 3)
+    fg, bg = fg.contiguous(), bg.contiguous()
     plan = plan or get_plan((0, 0, h, w), 2, fg.device)
     coarse = tps_coarse(ctrl, coef, plan, out=coarse)
     if out is None:
@@ -323,10 +330,9 @@ def flow_tps_composite(fg, backward, forward, bg, ctrl, coef, plan=None, out=Non
     lib = N.load()
     n, h, w = fg.shape[:3]
     _check_clip(fg, h, w)
-    assert backward.dtype == torch.float32 and backward.shape == (n, h, w, 2) and backward.is_contiguous()
-    if forward is not None:
-        assert forward.dtype == torch.float32 and forward.shape == (n, h, w, 2) and forward.is_contiguous()
-    assert bg.dtype == torch.uint8 and bg.dim() == 4 and bg.shape[1:] == (h, w, 3) and bg.is_contiguous()
+    backward, forward = _flow_arg(backward, n, h, w, "backward"), _flow_arg(forward, n, h, w, "forward")
+    assert bg.dtype == torch.uint8 and bg.dim() == 4 and bg.shape[1:] == (h, w, 3)
+    fg, bg = fg.contiguous(), bg.contiguous()
     plan = plan or get_plan((0, 0, h, w), 2, fg.device)
     coarse = tps_coarse(ctrl, coef, plan, out=coarse)
     if out is None:
@@ -351,3 +357,101 @@ def shard_range(n_units, rank, world):
     base, rem = divmod(n_units, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+# ----------------------------------------------------------------------------------------
+# host-buffer entry: the call a NumPy user makes for a whole clip (PCIe inside)
+# ----------------------------------------------------------------------------------------
+
+class HostClipRunner:
+    """flow warp + mask + TPS + composite for clips that live in HOST memory.
+
+    Frames are streamed through two device slots in chunks: H2D copies, the fused kernels and
+    the D2H copy of the result run on three streams so that the PCIe transfers of neighbouring
+    chunks overlap the kernels.  Inputs should be pinned (torch ``pin_memory()``) for the
+    copies to be asynchronous; pageable NumPy arrays work but serialise.
+    """
+
+    def __init__(self, h, w, chunk=8, device=None):
+        N.require_cuda()
+        self.h, self.w, self.chunk = h, w, chunk
+        self.device = torch.device(device if device is not None else "cuda")
+        d = self.device
+        self.plan = get_plan((0, 0, h, w), 2, d)
+        self.slots = []
+        for _ in range(2):
+            self.slots.append(dict(
+                fg=torch.empty((chunk, h, w, 4), dtype=torch.uint8, device=d),
+                fb=torch.empty((chunk, h, w, 2), dtype=torch.float32, device=d),
+                ff=torch.empty((chunk, h, w, 2), dtype=torch.float32, device=d),
+                bg=torch.empty((chunk, h, w, 3), dtype=torch.uint8, device=d),
+                out=torch.empty((chunk, h, w, 4), dtype=torch.float32, device=d),
+                coarse=torch.empty((chunk, 2, self.plan.nx, self.plan.ny), dtype=torch.float64, device=d),
+                loaded=torch.cuda.Event(), computed=torch.cuda.Event(), drained=torch.cuda.Event()))
+        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(d) for _ in range(3))
+        self.status = N.new_status(d)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    @staticmethod
+    def _as_tensor(x):
+        return x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+
+    def run(self, fg, backward, forward, bg, grids, out):
+        """fg (n,H,W,4) u8, flows (n,H,W,2) f32, bg (n,H,W,3) u8 host arrays/tensors, ``grids``
+        a list of n (grid, deformed grid) pairs, ``out`` a host (n,H,W,4) float32 buffer."""
+        fg, backward, forward, bg, out = map(self._as_tensor, (fg, backward, forward, bg, out))
+        n = fg.shape[0]
+        ctrl_all = np.stack([np.asarray(d, dtype=np.float64) for (_, d) in grids])
+        coef_all = np.stack([tps_solve(d, g) for (g, d) in grids])
+        ctrl_d = torch.from_numpy(ctrl_all).to(self.device, non_blocking=True)
+        coef_d = torch.from_numpy(coef_all).to(self.device, non_blocking=True)
+        self.h2d_bytes = ctrl_all.nbytes + coef_all.nbytes
+        self.d2h_bytes = 0
+        cur = torch.cuda.current_stream(self.device)
+        for s in (self.s_in, self.s_run, self.s_out):
+            s.wait_stream(cur)
+        for ci, lo in enumerate(range(0, n, self.chunk)):
+            hi = min(lo + self.chunk, n)
+            m = hi - lo
+            slot = self.slots[ci & 1]
+            with torch.cuda.stream(self.s_in):
+                if ci >= 2:
+                    self.s_in.wait_event(slot["computed"])        # inputs of chunk ci-2 consumed
+                for key, src in (("fg", fg), ("fb", backward), ("ff", forward), ("bg", bg)):
+                    slot[key][:m].copy_(src[lo:hi], non_blocking=True)
+                    self.h2d_bytes += src[lo:hi].numel() * src.element_size()
+                slot["loaded"].record(self.s_in)
+            with torch.cuda.stream(self.s_run):
+                self.s_run.wait_event(slot["loaded"])
+                if ci >= 2:
+                    self.s_run.wait_event(slot["drained"])        # output of chunk ci-2 copied out
+                flow_tps_composite(slot["fg"][:m], slot["fb"][:m], slot["ff"][:m], slot["bg"][:m],
+                                   ctrl_d[lo:hi], coef_d[lo:hi], plan=self.plan, out=slot["out"][:m],
+                                   coarse=slot["coarse"][:m], status=self.status)
+                slot["computed"].record(self.s_run)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(slot["computed"])
+                out[lo:hi].copy_(slot["out"][:m], non_blocking=True)
+                self.d2h_bytes += slot["out"][:m].numel() * 4
+                slot["drained"].record(self.s_out)
+        for s in (self.s_in, self.s_run, self.s_out):
+            cur.wait_stream(s)
+        return out
+
+
+_runners = {}
+
+
+def flow_tps_composite_host(fg, backward, forward, bg, grids, out=None, chunk=8):
+    """NumPy/host-tensor front end of the C4 pipeline (H2D, kernels, D2H inside).  Returns the
+    host (n,H,W,4) float32 result; synchronises before returning."""
+    n, h, w = fg.shape[:3]
+    key = (h, w, chunk, torch.cuda.current_device())
+    if key not in _runners:
+        _runners[key] = HostClipRunner(h, w, chunk)
+    if out is None:
+        out = torch.empty((n, h, w, 4), dtype=torch.float32).pin_memory()
+    res = _runners[key].run(fg, backward, forward, bg, grids, out)
+    torch.cuda.current_stream().synchronize()
+    return res
