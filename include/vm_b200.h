@@ -45,6 +45,7 @@ extern "C" {
 #define VM_STATUS_MASKED       2   /* # pixels zeroed by the consistency test              */
 #define VM_STATUS_TPS_OUTSIDE  3   /* # TPS samples outside [0,n-1] (map_coordinates -> 0) */
 #define VM_STATUS_SLOW_TILES   4   /* # tiles of a fused kernel that took the gather path  */
+#define VM_STATUS_BAD_TABLE    5   /* # tiles skipped: axis tables inconsistent with a /2 grid */
 
 int         vm_version(void);
 const char *vm_last_error_string(void);
@@ -146,22 +147,34 @@ int vm_flow_warp_mask_bgra(const uint8_t *fg, const float *backward, const float
 
 /* TPS warp of a BGRA frame + composite onto bg (tps.py:14-34, reader.py:72-79), i.e.
  * warp_image(.., identity affine, thin) for fg and alpha followed by create_composite_image.
- * out (n,h,w,4) float32 = {B, G, R composite (0..255), warped alpha}.  23 B/px.             */
+ * The coarse-grid spline evaluation (tps.py:101-121) is fused in: ctrl (n,N,2) / coef (n,N+3,2)
+ * float64 as for vm_tps_coarse, coarse point (k,l) = (k*step_x, l*step_y).
+ * out (n,h,w,4) float32 = {B, G, R composite (0..255), warped alpha}.  23 B/px.
+ * `scratch`: device workspace of vm_fused_scratch_bytes(n,nx,ny) bytes, only touched by the
+ * gather variant (N > 64 control points or vm_set_option("fused_variant", 1)).              */
+int64_t vm_fused_scratch_bytes(int n, int nx, int ny);
 int vm_tps_composite_bgra(const uint8_t *fg, const uint8_t *bg, int n_bg,
-                          const double *coarse, int nx, int ny,
+                          const double *ctrl, const double *coef, int N,
+                          int nx, int ny, double step_x, double step_y,
                           const vm_axis_entry *rows, const vm_axis_entry *cols,
-                          int n, int h, int w, float *out, int32_t *status, void *stream);
+                          int n, int h, int w, float *out, void *scratch,
+                          int32_t *status, void *stream);
 
-/* flow warp + consistency mask + TPS + composite in one pass (SURVEY 8d "C4 pipeline").
- * 39 B/px.  `scratch`: device workspace of vm_flow_tps_scratch_bytes(n,h,w) bytes (may be
- * NULL when that is 0).                                                                     */
-int64_t vm_flow_tps_scratch_bytes(int n, int h, int w);
+/* flow warp + consistency mask + TPS + composite in one pass (SURVEY 8d "C4 pipeline"):
+ * warp_bgr/warp_img (flow.py:9-33), correct_alpha (flow.py:36-65), warp_image(identity affine,
+ * thin) (augmentation.py:44-63 -> tps.py:14-123), create_composite_image (reader.py:72-79).
+ * 39 B/px.  forward may be NULL (no consistency test).                                      */
 int vm_flow_tps_composite_bgra(const uint8_t *fg, const float *backward, const float *forward,
                                const uint8_t *bg, int n_bg,
-                               const double *coarse, int nx, int ny,
+                               const double *ctrl, const double *coef, int N,
+                               int nx, int ny, double step_x, double step_y,
                                const vm_axis_entry *rows, const vm_axis_entry *cols,
                                int n, int h, int w, float *out, void *scratch,
                                int32_t *status, void *stream);
+
+/* Tuning / test switches: "fused_variant" 0 = shared-memory tiled kernel (default), 1 =
+ * per-pixel gather kernel; "tile_h" 32 or 64 (rows per tile of the tiled kernel).           */
+int vm_set_option(const char *key, int value);
 
 #ifdef __cplusplus
 }

@@ -271,8 +271,21 @@ def test_augment_golden(vm, golden):
 
 # ------------------------------------------------------------------------- fused C3 / C4
 
+VARIANTS = [(0, 64), (0, 32), (1, 64)]       # (fused_variant, tile_h): tiled 64, tiled 32, gather
+
+
+@pytest.fixture(params=VARIANTS, ids=["tiled64", "tiled32", "gather"])
+def variant(request, vm):
+    v, th = request.param
+    vm.pipeline.set_fused_variant(v)
+    vm._native.set_option("tile_h", th)
+    yield request.param
+    vm.pipeline.set_fused_variant(0)
+    vm._native.set_option("tile_h", 64)
+
+
 @pytest.mark.parametrize("tag", ["a", "b", "c"])
-def test_fused_c4_golden(vm, golden, tag):
+def test_fused_c4_golden(vm, golden, tag, variant):
     fg, fb, ff = golden[f"flow_{tag}_fg"], golden[f"flow_{tag}_fb"], golden[f"flow_{tag}_ff"]
     grids = (golden[f"c4_{tag}_grid"], golden[f"c4_{tag}_defgrid"])
     P = vm.pipeline
@@ -286,8 +299,8 @@ def test_fused_c4_golden(vm, golden, tag):
     assert np.count_nonzero(bad) <= 1, "composite differs beyond knife-edge flips"
 
 
-@pytest.mark.parametrize("shape,n_ctrl", [((64, 64), 4), ((61, 83), 5), ((128, 96), 5)])
-def test_fused_c3_c4_vs_oracle(vm, shape, n_ctrl):
+@pytest.mark.parametrize("shape,n_ctrl", [((64, 64), 4), ((61, 83), 5), ((128, 96), 5), ((200, 333), 5), ((4, 6), 2)])
+def test_fused_c3_c4_vs_oracle(vm, shape, n_ctrl, variant):
     h, w = shape
     n = 2
     P = vm.pipeline
@@ -307,6 +320,26 @@ def test_fused_c3_c4_vs_oracle(vm, shape, n_ctrl):
         for got, rc, ra in ((out3[k], r3, a3), (out4[k], r4, a4)):
             assert close(got[..., 3], ra, 1e-6)
             assert np.count_nonzero(~np.isclose(got[..., :3], rc, rtol=RTOL, atol=1e-5)) <= 1
+
+
+def test_fused_degenerate_grid_takes_gather_path(vm):
+    """A grid that folds the frame (source box of a tile larger than shared memory) must still
+    match the oracle, through the per-tile gather path, and be counted."""
+    h, w = 256, 320
+    P = vm.pipeline
+    frame = O.synth_frame(77, h, w)
+    fb, ff = O.synth_flows(77, h, w)
+    bg = O.synth_background(3, h, w)
+    grid, dgrid = O.synth_grids(5, h, w, 5)
+    dgrid = grid + (dgrid - grid) * 6.0          # 30 % displacements: strongly stretched tiles
+    ctrl, coef = P.solve_grids([(grid, dgrid)])
+    out, st = P.flow_tps_composite(dev(frame[None]), dev(fb[None]), dev(ff[None]), dev(bg[None]), ctrl, coef)
+    rc, ra = O.pipeline_c4(frame, fb, ff, (grid, dgrid), bg)
+    got = out[0].cpu().numpy()
+    assert close(got[..., 3], ra, 1e-6)
+    assert np.count_nonzero(~np.isclose(got[..., :3], rc, rtol=RTOL, atol=1e-5)) <= 1
+    assert int(st[4]) > 0, "expected at least one tile on the gather path"
+    assert int(st[5]) == 0
 
 
 # -------------------------------------------------------- full-size, size-independent properties

@@ -13,7 +13,7 @@ from . import _build
 
 VM_U8, VM_F32, VM_F64 = 0, 1, 2
 STATUS_WORDS = 8
-STATUS_INDEX_ERR, STATUS_NAN_ERR, STATUS_MASKED, STATUS_TPS_OUTSIDE, STATUS_SLOW_TILES = 0, 1, 2, 3, 4
+STATUS_INDEX_ERR, STATUS_NAN_ERR, STATUS_MASKED, STATUS_TPS_OUTSIDE, STATUS_SLOW_TILES, STATUS_BAD_TABLE = 0, 1, 2, 3, 4, 5
 
 _c = ctypes
 _P, _I, _L, _D = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_double
@@ -36,9 +36,10 @@ SIGNATURES = {
     "vm_illumination_lut": [_P, _L, _P, _P, _P],
     "vm_alpha_stats": [_P, _I, _I, _I, _P, _P],
     "vm_flow_warp_mask_bgra": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
-    "vm_tps_composite_bgra": [_P, _P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P],
-    "vm_flow_tps_scratch_bytes": [_I, _I, _I],
-    "vm_flow_tps_composite_bgra": [_P, _P, _P, _P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "vm_fused_scratch_bytes": [_I, _I, _I],
+    "vm_tps_composite_bgra": [_P, _P, _I, _P, _P, _I, _I, _I, _D, _D, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "vm_flow_tps_composite_bgra": [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _D, _D, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "vm_set_option": [_c.c_char_p, _I],
 }
 
 _lib = None
@@ -71,7 +72,7 @@ def load(build_if_missing=True):
         fn.argtypes = argtypes
         fn.restype = _c.c_int
     lib.vm_last_error_string.restype = _c.c_char_p
-    lib.vm_flow_tps_scratch_bytes.restype = _c.c_int64
+    lib.vm_fused_scratch_bytes.restype = _c.c_int64
     _lib = lib
     return lib
 
@@ -134,3 +135,8 @@ def from_device(t, kind):
 
 def new_status(device=None):
     return torch.zeros(STATUS_WORDS, dtype=torch.int32, device=device or "cuda")
+
+
+def set_option(key, value):
+    """Tuning / test switches of the library (see vm_set_option in include/vm_b200.h)."""
+    check(load().vm_set_option(key.encode(), int(value)))

@@ -214,3 +214,100 @@ __device__ __forceinline__ double vm_upsample_exact(double t00, double t01, doub
     v = __dadd_rn(v, __dmul_rn(__dmul_rn(t11, xf), yf));
     return v;
 }
+
+
+// ---------------------------------------------------------------------------------------
+// Instruction-lean fast paths used by the fused kernels.  Each one is exact (same integers
+// as the generic functions above) inside a guarded range and reports when it cannot be used.
+// ---------------------------------------------------------------------------------------
+
+// rne(32*m) for |m| < 65536 without a conversion instruction: (32m + 1.5*2^23) keeps the
+// integer in the mantissa; 32m is exact so this is a single rounding = cvRound(m*32).
+__device__ __forceinline__ int vm_fix5_fast(float m) {
+    return __float_as_int(__fmaf_rn(m, 32.f, 12582912.f)) - 0x4B400000;
+}
+
+// uint8 (already isolated in the low byte of `u`, value < 2^23) -> float, no conversion pipe.
+__device__ __forceinline__ float vm_u2f(uint32_t u) { return __uint_as_float(u | 0x4B000000u) - 8388608.f; }
+__device__ __forceinline__ float vm_byte2f(uint32_t word, int byte) {
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650 + byte)) - 8388608.f;
+}
+
+struct VmFlowPx { uint32_t bgr; uint32_t ta; int masked; };
+
+// warp_bgr / warp_img / correct_alpha for the pixel (i, j) of a BGRA frame: fast path for
+// in-range coordinates, otherwise the generic routines.  fi/fj = (float)i / (float)j.
+template <bool MASK>
+__device__ __forceinline__ VmFlowPx vm_flow_px(const uint32_t *__restrict__ fg32, const float2 *__restrict__ fwd,
+                                               int H, int W, int i, int j, float fi, float fj, float2 fb,
+                                               int &flags) {
+    VmFlowPx o;
+    const float mx = __fadd_rn(fj, fb.x), my = __fadd_rn(fi, fb.y);
+    if (fmaxf(fabsf(mx), fabsf(my)) < 60000.f) {                 // false for NaN
+        const int SX = vm_fix5_fast(mx), SY = vm_fix5_fast(my);
+        const int ix = SX >> 5, iy = SY >> 5, fx = SX & 31, fy = SY & 31;
+        uint32_t s00, s01, s10, s11;
+        const int base = (int)((unsigned)iy * (unsigned)W + (unsigned)ix);
+        if ((unsigned)ix < (unsigned)(W - 1) && (unsigned)iy < (unsigned)(H - 1)) {
+            const uint32_t *p = fg32 + base;
+            s00 = __ldg(p); s01 = __ldg(p + 1); s10 = __ldg(p + W); s11 = __ldg(p + W + 1);
+        } else {
+            const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
+            const bool y0 = (unsigned)iy < (unsigned)H, y1 = (unsigned)(iy + 1) < (unsigned)H;
+            s00 = (y0 && x0) ? __ldg(fg32 + base) : 0u;
+            s01 = (y0 && x1) ? __ldg(fg32 + base + 1) : 0u;
+            s10 = (y1 && x0) ? __ldg(fg32 + base + W) : 0u;
+            s11 = (y1 && x1) ? __ldg(fg32 + base + W + 1) : 0u;
+        }
+        const uint32_t gx = 32 - fx, gy = 32 - fy;
+        const uint32_t w00 = gx * gy, w01 = fx * gy, w10 = gx * fy, w11 = fx * fy;
+        const uint32_t b = ((s00 & 255u) * w00 + (s01 & 255u) * w01 + (s10 & 255u) * w10 + (s11 & 255u) * w11 + 512u) >> 10;
+        const uint32_t g = (__byte_perm(s00, 0, 0x4441) * w00 + __byte_perm(s01, 0, 0x4441) * w01 +
+                            __byte_perm(s10, 0, 0x4441) * w10 + __byte_perm(s11, 0, 0x4441) * w11 + 512u) >> 10;
+        const uint32_t r = (__byte_perm(s00, 0, 0x4442) * w00 + __byte_perm(s01, 0, 0x4442) * w01 +
+                            __byte_perm(s10, 0, 0x4442) * w10 + __byte_perm(s11, 0, 0x4442) * w11 + 512u) >> 10;
+        o.ta = (s00 >> 24) * w00 + (s01 >> 24) * w01 + (s10 >> 24) * w10 + (s11 >> 24) * w11;
+        o.bgr = b | (g << 8) | (r << 16);
+        o.masked = 0;
+        if (MASK) {
+            // flow.py:44: a = bx + j (same float as mx), trunc toward zero; fast when it lands
+            // inside the frame (no clamp, no wrap)
+            const int j0 = __float2int_rz(mx), i0 = __float2int_rz(my);
+            if ((unsigned)j0 < (unsigned)W && (unsigned)i0 < (unsigned)H) {
+                const float2 ff = __ldg(fwd + (i0 * W + j0));
+                const float c = __fadd_rn(ff.x, (float)j0), d = __fadd_rn(ff.y, (float)i0);
+                if (fmaxf(fabsf(c), fabsf(d)) < 3.0e38f) {
+                    // min(trunc(c), W-1) - j, in float: exact for |.| < 2^24, monotone beyond
+                    const float dj = __fadd_rn(fminf(truncf(c), (float)(W - 1)), -fj);
+                    const float di = __fadd_rn(fminf(truncf(d), (float)(H - 1)), -fi);
+                    o.masked = __fmaf_rn(dj, dj, __fmul_rn(di, di)) > 225.f;
+                } else {
+                    flags |= 2; o.masked = 1;
+                }
+            } else {
+                o.masked = vm_consistency(fwd, H, W, i, j, fb, flags);
+            }
+        }
+    } else {
+        const VmWarped wv = vm_flow_warp_bgra(reinterpret_cast<const uint8_t *>(fg32), H, W, i, j, fb);
+        o.bgr = wv.bgr; o.ta = wv.ta;
+        o.masked = MASK ? vm_consistency(fwd, H, W, i, j, fb, flags) : 0;
+    }
+    return o;
+}
+
+// alpha numerator ta (0..261120) -> signed-complement float: +alpha when alpha <= 1/2,
+// -(1 - alpha) otherwise.  Both alpha and 1 - alpha are then recoverable with ~1e-7 RELATIVE
+// error, which the composite needs (|out - ref| <= 1e-5 rel even where (1-alpha)*B dominates).
+#define VM_ALPHA_INV 3.82965686274509803e-06f      /* 1 / 261120 */
+__device__ __forceinline__ uint32_t vm_alpha_code(uint32_t ta) {
+    const uint32_t nta = 261120u - ta;
+    const float s = (float)min(ta, nta) * VM_ALPHA_INV;
+    return __float_as_uint(s) | ((ta > nta) ? 0x80000000u : 0u);
+}
+__device__ __forceinline__ void vm_alpha_decode(uint32_t code, float &a, float &na) {
+    const float s = fabsf(__uint_as_float(code)), t = 1.f - s;
+    const bool big = (int)code < 0;
+    a = big ? t : s;
+    na = big ? s : t;
+}

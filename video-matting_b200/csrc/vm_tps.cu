@@ -3,6 +3,7 @@
 // kernels.  Reference behaviour: tps.py:14-123, augmentation.py:44-63, reader.py:72-79.
 #include "vm_common.cuh"
 #include <math.h>
+#include <string.h>
 #include <mutex>
 
 // ---------------------------------------------------------------------------------------
@@ -332,13 +333,356 @@ k_tps_composite(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd, 
     }
 }
 
-static int launch_tps_composite(bool flow, const uint8_t *fg, const float *backward, const float *forward,
-                                const uint8_t *bg, int n_bg, const double *coarse, int nx, int ny,
-                                const vm_axis_entry *rows, const vm_axis_entry *cols, int n, int h, int w,
-                                float *out, int32_t *status, void *stream, const char *what) {
+// ---------------------------------------------------------------------------------------
+// Tiled fused kernel (the fast path): one CTA per TT_H x TT_W output tile.
+//
+//   P0  control points / affine part / log table / axis entries of the tile -> shared memory
+//   P1  radial-basis sum on the tile's coarse sub-grid (float64, table log) -> shared memory;
+//       bounding box of the coarse values = bounding box of every fine coordinate of the tile
+//       (the fine transform is a convex combination of coarse values)
+//   P3  the source pixels of that box are produced ONCE into shared memory: for C4 the
+//       flow-warped, consistency-masked pixel {B,G,R uint8 exact, alpha code}; for C3 the
+//       BGRA pixel itself.  Flow, forward flow and BGRA taps come through L1/L2.
+//   P4  per output pixel: float64 up-sampling of the transform, map_coordinates geometry in
+//       float64, colour blend in float32 with an exact float64 re-evaluation whenever the
+//       float32 value is within 5e-4 of a rounding boundary, alpha and (1 - alpha) blended
+//       separately (relative accuracy for the composite), one 16-byte store.
+//
+// HBM traffic is the algorithmic 39 (C4) / 23 (C3) bytes per pixel plus tile halos served by
+// L2.  A tile whose source box does not fit the shared-memory budget (degenerate grids) takes
+// the per-pixel gather path of k_tps_composite and is counted in VM_STATUS_SLOW_TILES.
+// ---------------------------------------------------------------------------------------
+#define TT_W 64
+#define TT_THREADS 256
+#define TT_MAX_N 64
+
+template <int TH> struct TileCfg {
+    static constexpr int CR = TH / 2 + 3;                  // max coarse rows of a tile
+    static constexpr int CC = TT_W / 2 + 3;                // max coarse cols of a tile (35)
+    static constexpr int IMAX = (TH == 64) ? 8448 : 4608;  // source-box entries (8 B each)
+    static constexpr int SEG = (TH == 64) ? 5 : 3;         // coarse points per thread (one row run)
+    static constexpr int NSEG = (CC + SEG - 1) / SEG;      // threads per coarse row
+    static_assert(CR * NSEG <= TT_THREADS, "coarse tile does not fit one pass");
+};
+
+template <int TH> struct __align__(16) TileSmem {
+    double2 logtab[VM_LOG_N];
+    double4 ctrl[TT_MAX_N];                                // {Px, Py, w0/2, w1/2}
+    vm_axis_entry rows[TH];
+    vm_axis_entry cols[TT_W];
+    double2 T[TileCfg<TH>::CR * TileCfg<TH>::CC];          // {row coord, col coord} per coarse point
+    uint2 inter[TileCfg<TH>::IMAX];                        // {B | G<<8 | R<<16, alpha code}
+    double aff[6];
+    int box[4];                                            // rmin, rmax, cmin, cmax (floors)
+    int bad;
+};
+
+// log(x), x > 0 finite (x = 0 gives a finite value, so that 0 * log(0) = 0 as in tps.py:81)
+__device__ __forceinline__ double vm_log_tab_smem(double x, const double2 *__restrict__ tab) {
+    const int hi = __double2hiint(x), lo = __double2loint(x);
+    const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
+    const double2 t = *reinterpret_cast<const double2 *>(
+        reinterpret_cast<const char *>(tab) + ((hi >> (16 - VM_LOG_BITS)) & ((VM_LOG_N - 1) << 4)));
+    // exponent as a double without a conversion instruction: 2^52 + biased_e - (2^52 + 1023)
+    const double ed = __hiloint2double(0x43300000, (int)((unsigned)hi >> 20)) - 4503599627371519.0;
+    const double r = fma(m, t.x, -1.0);                    // |r| <= 2^-11
+    double q = fma(r, -0.25, 1.0 / 3.0);
+    q = fma(r, q, -0.5);
+    q = fma(r, q, 1.0);                                    // log1p(r)/r to 6e-18
+    return fma(ed, 0.6931471805599453094, fma(r, q, t.y));
+}
+
+template <bool FLOW, int TH>
+__global__ void __launch_bounds__(TT_THREADS, (TH == 64) ? 2 : 3)
+k_tps_tiled(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd, const float2 *__restrict__ fwd,
+            const uint8_t *__restrict__ bg, int n_bg, const double *__restrict__ ctrl,
+            const double *__restrict__ coef, int N, int nx, int ny, double step_x, double step_y,
+            const vm_axis_entry *__restrict__ rows, const vm_axis_entry *__restrict__ cols,
+            int h, int w, int tiles_x, int tiles_y, float4 *__restrict__ out, int32_t *__restrict__ status) {
+    using Cfg = TileCfg<TH>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem<TH> &S = *reinterpret_cast<TileSmem<TH> *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int per = tiles_x * tiles_y;
+    const int frame = blockIdx.x / per;
+    const int tl = blockIdx.x - frame * per;
+    const int ty = tl / tiles_x, tx = tl - ty * tiles_x;
+    const int I0 = ty * TH, J0 = tx * TT_W;
+    const int th = min(TH, h - I0), tw = min(TT_W, w - J0);
+    const int64_t fbase = (int64_t)frame * h * w;
+    const uint32_t *fg32 = reinterpret_cast<const uint32_t *>(fg) + fbase;
+    const float2 *bf = FLOW ? bwd + fbase : nullptr;
+    const float2 *ff = (FLOW && fwd) ? fwd + fbase : nullptr;
+
+    // ---- P0 ----------------------------------------------------------------------------
+    {
+        const double *P = ctrl + (int64_t)frame * N * 2;
+        const double *C = coef + (int64_t)frame * (N + 3) * 2;
+        for (int k = tid; k < VM_LOG_N; k += TT_THREADS) S.logtab[k] = g_vm_log_tab[k];
+        if (tid < N) S.ctrl[tid] = make_double4(P[2 * tid], P[2 * tid + 1], 0.5 * C[2 * tid], 0.5 * C[2 * tid + 1]);
+        if (tid < 6) S.aff[tid] = C[(N + tid % 3) * 2 + tid / 3];
+        if (tid < th) S.rows[tid] = vm_ld_axis(rows + I0 + tid);
+        if (tid >= 64 && tid < 64 + tw) S.cols[tid - 64] = vm_ld_axis(cols + J0 + tid - 64);
+        if (tid == 0) { S.box[0] = INT_MAX; S.box[1] = INT_MIN; S.box[2] = INT_MAX; S.box[3] = INT_MIN; S.bad = 0; }
+    }
+    __syncthreads();
+    const int kr0 = S.rows[0].i0, kc0 = S.cols[0].i0;
+    const int nkr = S.rows[th - 1].i1 - kr0 + 1, nkc = S.cols[tw - 1].i1 - kc0 + 1;
+    if (nkr < 1 || nkc < 1 || nkr > Cfg::CR || nkc > Cfg::CC) {      // axis tables are not those of a /2 grid
+        if (status && tid == 0) atomicAdd(status + VM_STATUS_BAD_TABLE, 1);
+        return;
+    }
+
+    // ---- P1: coarse radial-basis evaluation: thread = run of SEG points in one coarse row ---
+    {
+        const int k = tid / Cfg::NSEG, l0 = (tid - k * Cfg::NSEG) * Cfg::SEG;
+        const bool active = k < nkr && l0 < nkc;
+        int rmin = INT_MAX, rmax = INT_MIN, cmin = INT_MAX, cmax = INT_MIN, bad = 0;
+        if (active) {
+            const double x = (double)(kr0 + k) * step_x;
+            double py[Cfg::SEG], s0[Cfg::SEG], s1[Cfg::SEG];
+#pragma unroll
+            for (int m = 0; m < Cfg::SEG; ++m) {
+                py[m] = (double)(kc0 + min(l0 + m, nkc - 1)) * step_y;
+                s0[m] = 0.0; s1[m] = 0.0;
+            }
+            for (int a = 0; a < N; ++a) {
+                const double4 c = S.ctrl[a];
+                const double dx = x - c.x;
+                const double dx2 = dx * dx;
+#pragma unroll
+                for (int m = 0; m < Cfg::SEG; ++m) {
+                    const double dy = py[m] - c.y;
+                    const double r2 = fma(dy, dy, dx2);
+                    const double U = r2 * vm_log_tab_smem(r2, S.logtab);
+                    s0[m] = fma(c.z, U, s0[m]);
+                    s1[m] = fma(c.w, U, s1[m]);
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < Cfg::SEG; ++m) {
+                if (l0 + m < nkc) {
+                    const double v0 = ((S.aff[0] + S.aff[1] * x) + S.aff[2] * py[m]) + s0[m];
+                    const double v1 = ((S.aff[3] + S.aff[4] * x) + S.aff[5] * py[m]) + s1[m];
+                    S.T[k * nkc + l0 + m] = make_double2(v0, v1);
+                    if (!(fabs(v0) < 1.0e9) || !(fabs(v1) < 1.0e9)) bad = 1;
+                    else {
+                        const int f0 = __double2int_rd(v0), f1 = __double2int_rd(v1);
+                        rmin = min(rmin, f0); rmax = max(rmax, f0); cmin = min(cmin, f1); cmax = max(cmax, f1);
+                    }
+                }
+            }
+        }
+        rmin = __reduce_min_sync(0xffffffffu, rmin); rmax = __reduce_max_sync(0xffffffffu, rmax);
+        cmin = __reduce_min_sync(0xffffffffu, cmin); cmax = __reduce_max_sync(0xffffffffu, cmax);
+        bad = __reduce_max_sync(0xffffffffu, bad);
+        if ((tid & 31) == 0) {
+            atomicMin(&S.box[0], rmin); atomicMax(&S.box[1], rmax);
+            atomicMin(&S.box[2], cmin); atomicMax(&S.box[3], cmax);
+            if (bad) atomicOr(&S.bad, 1);
+        }
+    }
+    __syncthreads();
+    // source box actually addressed by in-range pixels: rows [rmin, rmax+1], cols [cmin, cmax+1]
+    const int rmin = max(S.box[0], 0), rmax = min(S.box[1] + 1, h - 1);
+    const int cmin = max(S.box[2], 0), cmax = min(S.box[3] + 1, w - 1);
+    const int RH = max(rmax - rmin + 1, 0), RW = max(cmax - cmin + 1, 0);
+    const bool tiled = !S.bad && RH >= 2 && RW >= 2 && RH <= 4096 && RW <= 4096 && RH * RW <= Cfg::IMAX;
+    int flags = 0;
+
+    // ---- P3: source box -> shared memory (warp per row, up to 3 x 32 columns in flight) -----
+    if (tiled) {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int r = warp; r < RH; r += TT_THREADS / 32) {
+            const int qi = rmin + r;
+            const float fi = (float)qi;
+            for (int c0 = 0; c0 < RW; c0 += 96) {
+                uint2 e[3];
+                bool ok[3];
+                if (FLOW) {
+                    float2 fb[3];
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const int cc = c0 + u * 32 + lane;
+                        ok[u] = cc < RW;
+                        fb[u] = ok[u] ? __ldg(bf + (qi * w + cmin + cc)) : make_float2(0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const int qj = cmin + min(c0 + u * 32 + lane, RW - 1);
+                        VmFlowPx px;
+                        if (ff) px = vm_flow_px<true>(fg32, ff, h, w, qi, qj, fi, (float)qj, fb[u], flags);
+                        else px = vm_flow_px<false>(fg32, ff, h, w, qi, qj, fi, (float)qj, fb[u], flags);
+                        e[u].x = px.bgr;
+                        e[u].y = px.masked ? 0u : vm_alpha_code(px.ta);
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const int cc = c0 + u * 32 + lane;
+                        ok[u] = cc < RW;
+                        const uint32_t sfg = ok[u] ? __ldg(fg32 + (qi * w + cmin + cc)) : 0u;
+                        e[u].x = sfg & 0x00FFFFFFu;
+                        e[u].y = vm_alpha_code((sfg >> 24) * 1024u);       // A/255 = 1024 A / 261120
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 3; ++u)
+                    if (ok[u]) S.inter[r * RW + c0 + u * 32 + lane] = e[u];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- P4: per-pixel resampling + composite ---------------------------------------------
+    const int jc = tid & (TT_W - 1);
+    int outside = 0;
+    if (jc < tw) {
+        const vm_axis_entry ce = S.cols[jc];
+        const int c0 = ce.i0 - kc0, c1 = ce.i1 - kc0;
+        const double yf = ce.frac, y1 = 1.0 - yf;
+        const uint8_t *bgf = bg + (int64_t)(frame % n_bg) * h * w * 3;
+        const int j = J0 + jc;
+        for (int ir = tid / TT_W; ir < th; ir += TT_THREADS / TT_W) {
+            const vm_axis_entry re = S.rows[ir];
+            const int o0 = (re.i0 - kr0) * nkc, o1 = (re.i1 - kr0) * nkc;
+            const double xf = re.frac, x1 = 1.0 - xf;
+            const double2 T00 = S.T[o0 + c0], T01 = S.T[o0 + c1], T10 = S.T[o1 + c0], T11 = S.T[o1 + c1];
+            // bilinear up-sampling of the transform (tps.py:68,73); weights formed once for both
+            // coordinates (differs from the reference's operation order by < 1e-12 px)
+            const double u00 = x1 * y1, u01 = x1 * yf, u10 = xf * y1, u11 = xf * yf;
+            const double t0 = fma(T11.x, u11, fma(T10.x, u10, fma(T01.x, u01, T00.x * u00)));
+            const double t1 = fma(T11.y, u11, fma(T10.y, u10, fma(T01.y, u01, T00.y * u00)));
+            const int i = I0 + ir;
+            const int p32 = i * w + j;
+            const uint8_t *bgp = bgf + (int64_t)p32 * 3;
+            const float bb = vm_u2f(__ldg(bgp)), bgc = vm_u2f(__ldg(bgp + 1)), br = vm_u2f(__ldg(bgp + 2));
+            float cb = 0.f, cg = 0.f, cr = 0.f, a2 = 0.f, na = 1.f;
+            // map_coordinates geometry: floor via round-to-nearest magic + fix-up (no conversion pipe)
+            const double k0 = (t0 + 6755399441055744.0) - 6755399441055744.0;
+            const double k1 = (t1 + 6755399441055744.0) - 6755399441055744.0;
+            const double d0 = t0 - k0, d1 = t1 - k1;                       // in [-0.5, 0.5], exact
+            const int n0 = __double2loint(t0 + 6755399441055744.0) - (d0 < 0.0 ? 1 : 0);
+            const int n1 = __double2loint(t1 + 6755399441055744.0) - (d1 < 0.0 ? 1 : 0);
+            // inside the staged source box (which is clamped to the frame, so this also implies
+            // 0 <= n0 < h-1 and 0 <= n1 < w-1); anything else goes the exact per-pixel way
+            const bool interior = (unsigned)(n0 - rmin) <= (unsigned)(RH - 2) && (unsigned)(n1 - cmin) <= (unsigned)(RW - 2);
+            if (interior && tiled) {
+                const float af = (float)d0 + (d0 < 0.0 ? 1.f : 0.f), bfr = (float)d1 + (d1 < 0.0 ? 1.f : 0.f);
+                const float a0f = 1.f - af, b0f = 1.f - bfr;
+                const float w00 = a0f * b0f, w01 = a0f * bfr, w10 = af * b0f, w11 = af * bfr;
+                const int q = (n0 - rmin) * RW + (n1 - cmin);
+                const uint2 e00 = S.inter[q], e01 = S.inter[q + 1];
+                const uint2 e10 = S.inter[q + RW], e11 = S.inter[q + RW + 1];
+                float col[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float v = __fmaf_rn(vm_byte2f(e11.x, c), w11, __fmaf_rn(vm_byte2f(e10.x, c), w10,
+                                    __fmaf_rn(vm_byte2f(e01.x, c), w01, vm_byte2f(e00.x, c) * w00)));
+                    const float rr = (v + 12582912.f) - 12582912.f;        // nearest integer
+                    col[c] = rr;
+                    if (fabsf(v - rr) > 0.4995f) {       // too close to k + 0.5 for float32: exact path
+                        const VmBilin64 s = vm_mapcoord_setup(t0, t1, h, w);
+                        col[c] = (float)vm_round_half_up_u8(vm_mapcoord_blend(
+                            s, (double)((e00.x >> (8 * c)) & 255u), (double)((e01.x >> (8 * c)) & 255u),
+                            (double)((e10.x >> (8 * c)) & 255u), (double)((e11.x >> (8 * c)) & 255u)));
+                    }
+                }
+                cb = col[0]; cg = col[1]; cr = col[2];
+                float al00, al01, al10, al11, nl00, nl01, nl10, nl11;
+                vm_alpha_decode(e00.y, al00, nl00); vm_alpha_decode(e01.y, al01, nl01);
+                vm_alpha_decode(e10.y, al10, nl10); vm_alpha_decode(e11.y, al11, nl11);
+                a2 = __fmaf_rn(al11, w11, __fmaf_rn(al10, w10, __fmaf_rn(al01, w01, al00 * w00)));
+                na = __fmaf_rn(nl11, w11, __fmaf_rn(nl10, w10, __fmaf_rn(nl01, w01, nl00 * w00)));
+            } else {
+                const VmBilin64 s = vm_mapcoord_setup(t0, t1, h, w);
+                if (s.inside) {
+                    // last row / column of the frame, or a tile on the gather path: float64 throughout
+                    const uint8_t *fg8 = reinterpret_cast<const uint8_t *>(fg32);
+                    const VmSrcPx s00 = vm_src_px<FLOW>(fg8, bf, ff, h, w, s.i0, s.j0, flags);
+                    const VmSrcPx s01 = vm_src_px<FLOW>(fg8, bf, ff, h, w, s.i0, s.j1, flags);
+                    const VmSrcPx s10 = vm_src_px<FLOW>(fg8, bf, ff, h, w, s.i1, s.j0, flags);
+                    const VmSrcPx s11 = vm_src_px<FLOW>(fg8, bf, ff, h, w, s.i1, s.j1, flags);
+                    cb = (float)vm_round_half_up_u8(vm_mapcoord_blend(s, s00.b, s01.b, s10.b, s11.b));
+                    cg = (float)vm_round_half_up_u8(vm_mapcoord_blend(s, s00.g, s01.g, s10.g, s11.g));
+                    cr = (float)vm_round_half_up_u8(vm_mapcoord_blend(s, s00.r, s01.r, s10.r, s11.r));
+                    const double a64 = vm_mapcoord_blend(s, s00.a, s01.a, s10.a, s11.a);
+                    a2 = (float)a64;
+                    na = (float)(1.0 - a64);
+                } else {
+                    outside++;
+                }
+            }
+            float4 o;
+            o.x = __fmaf_rn(a2, cb, na * bb);
+            o.y = __fmaf_rn(a2, cg, na * bgc);
+            o.z = __fmaf_rn(a2, cr, na * br);
+            o.w = a2;
+            out[fbase + p32] = o;
+        }
+    }
+    if (status) {
+        outside = __reduce_add_sync(0xffffffffu, outside);
+        flags = __reduce_or_sync(0xffffffffu, flags);
+        if ((tid & 31) == 0) {
+            if (outside) atomicAdd(status + VM_STATUS_TPS_OUTSIDE, outside);
+            if (flags & 1) atomicAdd(status + VM_STATUS_INDEX_ERR, 1);
+            if (flags & 2) atomicAdd(status + VM_STATUS_NAN_ERR, 1);
+        }
+        if (tid == 0 && !tiled) atomicAdd(status + VM_STATUS_SLOW_TILES, 1);
+    }
+}
+
+// option block (vm_set_option): variant 0 = tiled (default), 1 = per-pixel gather kernels
+static int g_opt_variant = 0;
+static int g_opt_tile_h = 64;
+
+extern "C" int vm_set_option(const char *key, int value) {
+    if (!key) return VM_ERR_ARG;
+    if (!strcmp(key, "fused_variant")) { g_opt_variant = value; return VM_OK; }
+    if (!strcmp(key, "tile_h") && (value == 32 || value == 64)) { g_opt_tile_h = value; return VM_OK; }
+    vm_set_error("vm_set_option: unknown option %s=%d", key, value);
+    return VM_ERR_ARG;
+}
+
+template <bool FLOW, int TH>
+static int launch_tiled(const uint8_t *fg, const float *backward, const float *forward, const uint8_t *bg,
+                        int n_bg, const double *ctrl, const double *coef, int N, int nx, int ny, double step_x,
+                        double step_y, const vm_axis_entry *rows, const vm_axis_entry *cols, int n, int h, int w,
+                        float *out, int32_t *status, cudaStream_t st, const char *what) {
+    const int tiles_x = (w + TT_W - 1) / TT_W, tiles_y = (h + TH - 1) / TH;
+    const int64_t tiles = (int64_t)n * tiles_x * tiles_y;
+    VM_REQUIRE(tiles < (1ll << 31), "too many tiles for one launch");
+    const size_t smem = sizeof(TileSmem<TH>);
+    cudaError_t e = cudaFuncSetAttribute(k_tps_tiled<FLOW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { vm_set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e)); return VM_ERR_CUDA; }
+    k_tps_tiled<FLOW, TH><<<(unsigned)tiles, TT_THREADS, smem, st>>>(
+        fg, (const float2 *)backward, (const float2 *)forward, bg, n_bg, ctrl, coef, N, nx, ny, step_x, step_y,
+        rows, cols, h, w, tiles_x, tiles_y, (float4 *)out, status);
+    return vm_check_launch(what);
+}
+
+static int launch_fused(bool flow, const uint8_t *fg, const float *backward, const float *forward,
+                        const uint8_t *bg, int n_bg, const double *ctrl, const double *coef, int N, int nx, int ny,
+                        double step_x, double step_y, const vm_axis_entry *rows, const vm_axis_entry *cols, int n,
+                        int h, int w, float *out, void *scratch, int32_t *status, void *stream, const char *what) {
     if (n == 0) return VM_OK;
-    dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8, n);
+    int rc = vm_init();
+    if (rc != VM_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (g_opt_variant == 0 && N <= TT_MAX_N && h >= 2 && w >= 2) {
+        if (g_opt_tile_h == 64)
+            return flow ? launch_tiled<true, 64>(fg, backward, forward, bg, n_bg, ctrl, coef, N, nx, ny, step_x, step_y, rows, cols, n, h, w, out, status, st, what)
+                        : launch_tiled<false, 64>(fg, nullptr, nullptr, bg, n_bg, ctrl, coef, N, nx, ny, step_x, step_y, rows, cols, n, h, w, out, status, st, what);
+        return flow ? launch_tiled<true, 32>(fg, backward, forward, bg, n_bg, ctrl, coef, N, nx, ny, step_x, step_y, rows, cols, n, h, w, out, status, st, what)
+                    : launch_tiled<false, 32>(fg, nullptr, nullptr, bg, n_bg, ctrl, coef, N, nx, ny, step_x, step_y, rows, cols, n, h, w, out, status, st, what);
+    }
+    // gather variant: coarse transform through global scratch, then one pixel per thread
+    VM_REQUIRE(scratch, "scratch workspace required for the gather variant");
+    double *coarse = (double *)scratch;
+    rc = vm_tps_coarse(ctrl, coef, n, N, nx, ny, step_x, step_y, 0.0, 0.0, coarse, stream);
+    if (rc != VM_OK) return rc;
+    dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8, n);
     if (flow)
         k_tps_composite<true><<<grid, block, 0, st>>>(fg, (const float2 *)backward, (const float2 *)forward, bg,
                                                       n_bg, coarse, nx, ny, rows, cols, h, w, (float4 *)out, status);
@@ -348,27 +692,27 @@ static int launch_tps_composite(bool flow, const uint8_t *fg, const float *backw
     return vm_check_launch(what);
 }
 
-extern "C" int vm_tps_composite_bgra(const uint8_t *fg, const uint8_t *bg, int n_bg, const double *coarse,
-                                     int nx, int ny, const vm_axis_entry *rows, const vm_axis_entry *cols,
-                                     int n, int h, int w, float *out, int32_t *status, void *stream) {
-    VM_REQUIRE(fg && bg && coarse && rows && cols && out, "null pointer");
-    VM_REQUIRE(n >= 0 && n < 65536 && h > 0 && w > 0 && n_bg >= 1 && nx >= 1 && ny >= 1, "bad size");
-    return launch_tps_composite(false, fg, nullptr, nullptr, bg, n_bg, coarse, nx, ny, rows, cols, n, h, w, out,
-                                status, stream, "vm_tps_composite_bgra");
+extern "C" int64_t vm_fused_scratch_bytes(int n, int nx, int ny) {
+    return (int64_t)n * 2 * nx * ny * (int64_t)sizeof(double);
 }
 
-extern "C" int64_t vm_flow_tps_scratch_bytes(int n, int h, int w) {
-    (void)n; (void)h; (void)w;
-    return 0;
+extern "C" int vm_tps_composite_bgra(const uint8_t *fg, const uint8_t *bg, int n_bg, const double *ctrl,
+                                     const double *coef, int N, int nx, int ny, double step_x, double step_y,
+                                     const vm_axis_entry *rows, const vm_axis_entry *cols, int n, int h, int w,
+                                     float *out, void *scratch, int32_t *status, void *stream) {
+    VM_REQUIRE(fg && bg && ctrl && coef && rows && cols && out, "null pointer");
+    VM_REQUIRE(n >= 0 && n < 65536 && h > 0 && w > 0 && n_bg >= 1 && nx >= 1 && ny >= 1 && N >= 1 && N <= VM_TPS_MAX_N, "bad size");
+    return launch_fused(false, fg, nullptr, nullptr, bg, n_bg, ctrl, coef, N, nx, ny, step_x, step_y, rows, cols,
+                        n, h, w, out, scratch, status, stream, "vm_tps_composite_bgra");
 }
 
 extern "C" int vm_flow_tps_composite_bgra(const uint8_t *fg, const float *backward, const float *forward,
-                                          const uint8_t *bg, int n_bg, const double *coarse, int nx, int ny,
+                                          const uint8_t *bg, int n_bg, const double *ctrl, const double *coef,
+                                          int N, int nx, int ny, double step_x, double step_y,
                                           const vm_axis_entry *rows, const vm_axis_entry *cols, int n, int h,
                                           int w, float *out, void *scratch, int32_t *status, void *stream) {
-    (void)scratch;
-    VM_REQUIRE(fg && backward && bg && coarse && rows && cols && out, "null pointer");
-    VM_REQUIRE(n >= 0 && n < 65536 && h > 0 && w > 0 && n_bg >= 1 && nx >= 1 && ny >= 1, "bad size");
-    return launch_tps_composite(true, fg, backward, forward, bg, n_bg, coarse, nx, ny, rows, cols, n, h, w, out,
-                                status, stream, "vm_flow_tps_composite_bgra");
+    VM_REQUIRE(fg && backward && bg && ctrl && coef && rows && cols && out, "null pointer");
+    VM_REQUIRE(n >= 0 && n < 65536 && h > 0 && w > 0 && n_bg >= 1 && nx >= 1 && ny >= 1 && N >= 1 && N <= VM_TPS_MAX_N, "bad size");
+    return launch_fused(true, fg, backward, forward, bg, n_bg, ctrl, coef, N, nx, ny, step_x, step_y, rows, cols,
+                        n, h, w, out, scratch, status, stream, "vm_flow_tps_composite_bgra");
 }

@@ -304,29 +304,47 @@ def flow_warp_mask(fg, backward, forward=None, out_bgr=None, out_alpha=None, sta
     return out_bgr, out_alpha, status
 
 
-def tps_composite(fg, bg, ctrl, coef, plan=None, out=None, coarse=None, status=None):
-    """TPS warp of fg/alpha + composite onto bg (C3).  Returns (out float32 (n,H,W,4), status)."""
+def _tps_args(ctrl, coef, n):
+    ctrl = ctrl.to(torch.float64).contiguous()
+    coef = coef.to(torch.float64).contiguous()
+    Np = ctrl.shape[1]
+    assert ctrl.shape == (n, Np, 2) and coef.shape == (n, Np + 3, 2), "ctrl (n,N,2) / coef (n,N+3,2) expected"
+    return ctrl, coef, Np
+
+
+def _fused_scratch(lib, n, plan, scratch, device):
+    """Workspace of the gather variant (coarse transform in global memory); the default tiled
+    kernel keeps the coarse transform in shared memory and never touches it."""
+    need = lib.vm_fused_scratch_bytes(n, plan.nx, plan.ny)
+    if scratch is None or scratch.numel() * scratch.element_size() < need:
+        scratch = torch.empty(need, dtype=torch.uint8, device=device)
+    return scratch
+
+
+def tps_composite(fg, bg, ctrl, coef, plan=None, out=None, scratch=None, status=None):
+    """TPS warp of fg/alpha + composite onto bg (C3), spline evaluation fused in.
+    Returns (out float32 (n,H,W,4), status)."""
     lib = N.load()
     n, h, w = fg.shape[:3]
     _check_clip(fg, h, w)
     assert bg.dtype == torch.uint8 and bg.dim() == 4 and bg.shape[1:] == (h, w, 3)
     fg, bg = fg.contiguous(), bg.contiguous()
     plan = plan or get_plan((0, 0, h, w), 2, fg.device)
-    coarse = tps_coarse(ctrl, coef, plan, out=coarse)
+    ctrl, coef, Np = _tps_args(ctrl, coef, n)
     if out is None:
         out = torch.empty((n, h, w, 4), dtype=torch.float32, device=fg.device)
     if status is None:
         status = N.new_status(fg.device)
-    N.check(lib.vm_tps_composite_bgra(N.ptr(fg), N.ptr(bg), bg.shape[0], N.ptr(coarse), plan.nx, plan.ny,
-                                      N.ptr(plan.rows), N.ptr(plan.cols), n, h, w, N.ptr(out), N.ptr(status),
-                                      N.stream_ptr()))
+    scratch = _fused_scratch(lib, n, plan, scratch, fg.device) if (_variant[0] or Np > 64) else scratch
+    N.check(lib.vm_tps_composite_bgra(N.ptr(fg), N.ptr(bg), bg.shape[0], N.ptr(ctrl), N.ptr(coef), Np, plan.nx,
+                                      plan.ny, plan.step_x, plan.step_y, N.ptr(plan.rows), N.ptr(plan.cols),
+                                      n, h, w, N.ptr(out), N.ptr(scratch), N.ptr(status), N.stream_ptr()))
     return out, status
 
 
-def flow_tps_composite(fg, backward, forward, bg, ctrl, coef, plan=None, out=None, coarse=None,
-                       scratch=None, status=None):
-    """flow warp + consistency mask + TPS + composite (SURVEY 8d C4 pipeline), 39 B/px.
-    Returns (out float32 (n,H,W,4), status)."""
+def flow_tps_composite(fg, backward, forward, bg, ctrl, coef, plan=None, out=None, scratch=None, status=None):
+    """flow warp + consistency mask + TPS + composite (SURVEY 8d C4 pipeline), 39 B/px, one
+    kernel.  Returns (out float32 (n,H,W,4), status)."""
     lib = N.load()
     n, h, w = fg.shape[:3]
     _check_clip(fg, h, w)
@@ -334,18 +352,27 @@ def flow_tps_composite(fg, backward, forward, bg, ctrl, coef, plan=None, out=Non
     assert bg.dtype == torch.uint8 and bg.dim() == 4 and bg.shape[1:] == (h, w, 3)
     fg, bg = fg.contiguous(), bg.contiguous()
     plan = plan or get_plan((0, 0, h, w), 2, fg.device)
-    coarse = tps_coarse(ctrl, coef, plan, out=coarse)
+    ctrl, coef, Np = _tps_args(ctrl, coef, n)
     if out is None:
         out = torch.empty((n, h, w, 4), dtype=torch.float32, device=fg.device)
     if status is None:
         status = N.new_status(fg.device)
-    need = lib.vm_flow_tps_scratch_bytes(n, h, w)
-    if need and (scratch is None or scratch.numel() < need):
-        scratch = torch.empty(need, dtype=torch.uint8, device=fg.device)
+    scratch = _fused_scratch(lib, n, plan, scratch, fg.device) if (_variant[0] or Np > 64) else scratch
     N.check(lib.vm_flow_tps_composite_bgra(N.ptr(fg), N.ptr(backward), N.ptr(forward), N.ptr(bg), bg.shape[0],
-                                           N.ptr(coarse), plan.nx, plan.ny, N.ptr(plan.rows), N.ptr(plan.cols),
-                                           n, h, w, N.ptr(out), N.ptr(scratch), N.ptr(status), N.stream_ptr()))
+                                           N.ptr(ctrl), N.ptr(coef), Np, plan.nx, plan.ny, plan.step_x,
+                                           plan.step_y, N.ptr(plan.rows), N.ptr(plan.cols), n, h, w, N.ptr(out),
+                                           N.ptr(scratch), N.ptr(status), N.stream_ptr()))
     return out, status
+
+
+_variant = [0]
+
+
+def set_fused_variant(v):
+    """0 = shared-memory tiled kernel (default), 1 = per-pixel gather kernel (kept as an
+    independent implementation for differential tests)."""
+    N.set_option("fused_variant", int(v))
+    _variant[0] = int(v)
 
 
 # ----------------------------------------------------------------------------------------
@@ -386,7 +413,6 @@ class HostClipRunner:
                 ff=torch.empty((chunk, h, w, 2), dtype=torch.float32, device=d),
                 bg=torch.empty((chunk, h, w, 3), dtype=torch.uint8, device=d),
                 out=torch.empty((chunk, h, w, 4), dtype=torch.float32, device=d),
-                coarse=torch.empty((chunk, 2, self.plan.nx, self.plan.ny), dtype=torch.float64, device=d),
                 loaded=torch.cuda.Event(), computed=torch.cuda.Event(), drained=torch.cuda.Event()))
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(d) for _ in range(3))
         self.status = N.new_status(d)
@@ -428,7 +454,7 @@ class HostClipRunner:
                     self.s_run.wait_event(slot["drained"])        # output of chunk ci-2 copied out
                 flow_tps_composite(slot["fg"][:m], slot["fb"][:m], slot["ff"][:m], slot["bg"][:m],
                                    ctrl_d[lo:hi], coef_d[lo:hi], plan=self.plan, out=slot["out"][:m],
-                                   coarse=slot["coarse"][:m], status=self.status)
+                                   status=self.status)
                 slot["computed"].record(self.s_run)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(slot["computed"])
