@@ -490,135 +490,199 @@ k_tps_tiled(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd, cons
     const bool tiled = !S.bad && RH >= 2 && RW >= 2 && RH <= 4096 && RW <= 4096 && RH * RW <= Cfg::IMAX;
     int flags = 0;
 
-    // ---- P3: source box -> shared memory (warp per row, up to 3 x 32 columns in flight) -----
-    if (tiled) {
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int r = warp; r < RH; r += TT_THREADS / 32) {
-            const int qi = rmin + r;
-            const float fi = (float)qi;
-            for (int c0 = 0; c0 < RW; c0 += 96) {
-                uint2 e[3];
-                bool ok[3];
-                if (FLOW) {
-                    float2 fb[3];
-#pragma unroll
-                    for (int u = 0; u < 3; ++u) {
-                        const int cc = c0 + u * 32 + lane;
-                        ok[u] = cc < RW;
-                        fb[u] = ok[u] ? __ldg(bf + (qi * w + cmin + cc)) : make_float2(0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 3; ++u) {
-                        const int qj = cmin + min(c0 + u * 32 + lane, RW - 1);
-                        VmFlowPx px;
-                        if (ff) px = vm_flow_px<true>(fg32, ff, h, w, qi, qj, fi, (float)qj, fb[u], flags);
-                        else px = vm_flow_px<false>(fg32, ff, h, w, qi, qj, fi, (float)qj, fb[u], flags);
-                        e[u].x = px.bgr;
-                        e[u].y = px.masked ? 0u : vm_alpha_code(px.ta);
-                    }
-                } else {
-#pragma unroll
-                    for (int u = 0; u < 3; ++u) {
-                        const int cc = c0 + u * 32 + lane;
-                        ok[u] = cc < RW;
-                        const uint32_t sfg = ok[u] ? __ldg(fg32 + (qi * w + cmin + cc)) : 0u;
-                        e[u].x = sfg & 0x00FFFFFFu;
-                        e[u].y = vm_alpha_code((sfg >> 24) * 1024u);       // A/255 = 1024 A / 261120
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 3; ++u)
-                    if (ok[u]) S.inter[r * RW + c0 + u * 32 + lane] = e[u];
-            }
+    // ---- P3: source box -> shared memory (warp per row, 3 x 32 columns per step; the flow
+    // vectors of the next step are prefetched while the current one is blended).  The background
+    // tile is fetched asynchronously into the (now dead) log-table space meanwhile.
+    uint8_t *bgt = reinterpret_cast<uint8_t *>(S.logtab);           // [TH][TT_W * 3]
+    const uint8_t *bgf = bg + (int64_t)(frame % n_bg) * h * w * 3;
+    const bool bg_async = (w & 15) == 0 && tw == TT_W && (reinterpret_cast<uintptr_t>(bg) & 15) == 0;
+    if (bg_async) {
+        for (int c = tid; c < th * (TT_W * 3 / 16); c += TT_THREADS) {
+            const int r = c / (TT_W * 3 / 16), k = c - r * (TT_W * 3 / 16);
+            const uint8_t *src = bgf + ((int64_t)(I0 + r) * w + J0) * 3 + k * 16;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(bgt + r * (TT_W * 3) + k * 16);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+        }
+        asm volatile("cp.async.commit_group;");
+    } else {
+        for (int c = tid; c < th * tw * 3; c += TT_THREADS) {
+            const int r = c / (tw * 3), k = c - r * (tw * 3);
+            bgt[r * (TT_W * 3) + k] = __ldg(bgf + ((int64_t)(I0 + r) * w + J0) * 3 + k);
         }
     }
+    if (tiled) {
+        const int warp = tid >> 5, lane = tid & 31;
+        const int ngrp = (RW + 95) / 96;
+        const int nrow = (RH - warp + TT_THREADS / 32 - 1) / (TT_THREADS / 32);   // rows of this warp
+        const int nit = max(nrow, 0) * ngrp;
+        float2 fnext[3];
+        if (FLOW && nit > 0) {
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int cc = u * 32 + lane;
+                fnext[u] = (cc < RW) ? __ldg(bf + ((rmin + warp) * w + cmin + cc)) : make_float2(0.f, 0.f);
+            }
+        }
+        for (int it = 0; it < nit; ++it) {
+            const int rr = it / ngrp, g = it - rr * ngrp;
+            const int r = warp + rr * (TT_THREADS / 32), c0 = g * 96;
+            const int qi = rmin + r;
+            uint2 e[3];
+            if (FLOW) {
+                float2 fb[3];
+#pragma unroll
+                for (int u = 0; u < 3; ++u) fb[u] = fnext[u];
+                if (it + 1 < nit) {
+                    const int rr2 = (it + 1) / ngrp, g2 = (it + 1) - rr2 * ngrp;
+                    const int r2 = warp + rr2 * (TT_THREADS / 32);
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const int cc = g2 * 96 + u * 32 + lane;
+                        fnext[u] = (cc < RW) ? __ldg(bf + ((rmin + r2) * w + cmin + cc)) : make_float2(0.f, 0.f);
+                    }
+                }
+                const float fi = (float)qi;
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int qj = cmin + min(c0 + u * 32 + lane, RW - 1);
+                    VmFlowPx px;
+                    if (ff) px = vm_flow_px<true>(fg32, ff, h, w, qi, qj, fi, (float)qj, fb[u], flags);
+                    else px = vm_flow_px<false>(fg32, ff, h, w, qi, qj, fi, (float)qj, fb[u], flags);
+                    e[u].x = px.bgr;
+                    e[u].y = px.masked ? 0u : vm_alpha_code(px.ta);
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int cc = c0 + u * 32 + lane;
+                    const uint32_t sfg = (cc < RW) ? __ldg(fg32 + (qi * w + cmin + cc)) : 0u;
+                    e[u].x = sfg & 0x00FFFFFFu;
+                    e[u].y = vm_alpha_code((sfg >> 24) * 1024u);       // A/255 = 1024 A / 261120
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+                if (c0 + u * 32 + lane < RW) S.inter[r * RW + c0 + u * 32 + lane] = e[u];
+        }
+    }
+    if (bg_async) asm volatile("cp.async.wait_group 0;");
     __syncthreads();
 
-    // ---- P4: per-pixel resampling + composite ---------------------------------------------
+    // ---- P4: per-pixel resampling + composite (two rows per step for ILP) --------------------
     const int jc = tid & (TT_W - 1);
     int outside = 0;
     if (jc < tw) {
         const vm_axis_entry ce = S.cols[jc];
         const int c0 = ce.i0 - kc0, c1 = ce.i1 - kc0;
         const double yf = ce.frac, y1 = 1.0 - yf;
-        const uint8_t *bgf = bg + (int64_t)(frame % n_bg) * h * w * 3;
         const int j = J0 + jc;
-        for (int ir = tid / TT_W; ir < th; ir += TT_THREADS / TT_W) {
-            const vm_axis_entry re = S.rows[ir];
-            const int o0 = (re.i0 - kr0) * nkc, o1 = (re.i1 - kr0) * nkc;
-            const double xf = re.frac, x1 = 1.0 - xf;
-            const double2 T00 = S.T[o0 + c0], T01 = S.T[o0 + c1], T10 = S.T[o1 + c0], T11 = S.T[o1 + c1];
-            // bilinear up-sampling of the transform (tps.py:68,73); weights formed once for both
-            // coordinates (differs from the reference's operation order by < 1e-12 px)
-            const double u00 = x1 * y1, u01 = x1 * yf, u10 = xf * y1, u11 = xf * yf;
-            const double t0 = fma(T11.x, u11, fma(T10.x, u10, fma(T01.x, u01, T00.x * u00)));
-            const double t1 = fma(T11.y, u11, fma(T10.y, u10, fma(T01.y, u01, T00.y * u00)));
-            const int i = I0 + ir;
-            const int p32 = i * w + j;
-            const uint8_t *bgp = bgf + (int64_t)p32 * 3;
-            const float bb = vm_u2f(__ldg(bgp)), bgc = vm_u2f(__ldg(bgp + 1)), br = vm_u2f(__ldg(bgp + 2));
-            float cb = 0.f, cg = 0.f, cr = 0.f, a2 = 0.f, na = 1.f;
-            // map_coordinates geometry: floor via round-to-nearest magic + fix-up (no conversion pipe)
-            const double k0 = (t0 + 6755399441055744.0) - 6755399441055744.0;
-            const double k1 = (t1 + 6755399441055744.0) - 6755399441055744.0;
-            const double d0 = t0 - k0, d1 = t1 - k1;                       // in [-0.5, 0.5], exact
-            const int n0 = __double2loint(t0 + 6755399441055744.0) - (d0 < 0.0 ? 1 : 0);
-            const int n1 = __double2loint(t1 + 6755399441055744.0) - (d1 < 0.0 ? 1 : 0);
-            // inside the staged source box (which is clamped to the frame, so this also implies
-            // 0 <= n0 < h-1 and 0 <= n1 < w-1); anything else goes the exact per-pixel way
-            const bool interior = (unsigned)(n0 - rmin) <= (unsigned)(RH - 2) && (unsigned)(n1 - cmin) <= (unsigned)(RW - 2);
-            if (interior && tiled) {
+        constexpr int RSTEP = TT_THREADS / TT_W;                       // 4 rows between a thread's pixels
+        for (int ir0 = tid / TT_W; ir0 < th; ir0 += 2 * RSTEP) {
+            float4 o[2];
+            double t0v[2], t1v[2];
+            uint2 ev[2][4];
+            float wv[2][4];
+            bool fast[2], live[2];
+            unsigned unc = 0;
+#pragma unroll
+            for (int z = 0; z < 2; ++z) {
+                const int ir = ir0 + z * RSTEP;
+                live[z] = ir < th;
+                const vm_axis_entry re = S.rows[min(ir, th - 1)];
+                const int o0 = (re.i0 - kr0) * nkc, o1 = (re.i1 - kr0) * nkc;
+                const double xf = re.frac, x1 = 1.0 - xf;
+                const double2 T00 = S.T[o0 + c0], T01 = S.T[o0 + c1], T10 = S.T[o1 + c0], T11 = S.T[o1 + c1];
+                // bilinear up-sampling of the transform (tps.py:68,73); weights formed once for
+                // both coordinates (differs from the reference's operation order by < 1e-12 px)
+                const double u00 = x1 * y1, u01 = x1 * yf, u10 = xf * y1, u11 = xf * yf;
+                const double t0 = fma(T11.x, u11, fma(T10.x, u10, fma(T01.x, u01, T00.x * u00)));
+                const double t1 = fma(T11.y, u11, fma(T10.y, u10, fma(T01.y, u01, T00.y * u00)));
+                t0v[z] = t0; t1v[z] = t1;
+                // map_coordinates geometry: floor via round-to-nearest magic + fix-up
+                const double m0 = t0 + 6755399441055744.0, m1 = t1 + 6755399441055744.0;
+                const double d0 = t0 - (m0 - 6755399441055744.0), d1 = t1 - (m1 - 6755399441055744.0);
+                const int n0 = __double2loint(m0) - (d0 < 0.0 ? 1 : 0);
+                const int n1 = __double2loint(m1) - (d1 < 0.0 ? 1 : 0);
+                // inside the staged source box (which is clamped to the frame, so this also implies
+                // 0 <= n0 < h-1 and 0 <= n1 < w-1); anything else goes the exact per-pixel way
+                fast[z] = tiled && (unsigned)(n0 - rmin) <= (unsigned)(RH - 2) && (unsigned)(n1 - cmin) <= (unsigned)(RW - 2);
+                const int q = fast[z] ? (n0 - rmin) * RW + (n1 - cmin) : 0, qs = fast[z] ? RW : 0;
+                ev[z][0] = S.inter[q]; ev[z][1] = S.inter[q + 1];
+                ev[z][2] = S.inter[q + qs]; ev[z][3] = S.inter[q + qs + 1];
                 const float af = (float)d0 + (d0 < 0.0 ? 1.f : 0.f), bfr = (float)d1 + (d1 < 0.0 ? 1.f : 0.f);
                 const float a0f = 1.f - af, b0f = 1.f - bfr;
-                const float w00 = a0f * b0f, w01 = a0f * bfr, w10 = af * b0f, w11 = af * bfr;
-                const int q = (n0 - rmin) * RW + (n1 - cmin);
-                const uint2 e00 = S.inter[q], e01 = S.inter[q + 1];
-                const uint2 e10 = S.inter[q + RW], e11 = S.inter[q + RW + 1];
+                wv[z][0] = a0f * b0f; wv[z][1] = a0f * bfr; wv[z][2] = af * b0f; wv[z][3] = af * bfr;
+            }
+#pragma unroll
+            for (int z = 0; z < 2; ++z) {
+                const int ir = min(ir0 + z * RSTEP, th - 1);
+                const uint8_t *bp = bgt + ir * (TT_W * 3) + jc * 3;
+                const float bb = vm_u2f(bp[0]), bgc = vm_u2f(bp[1]), br = vm_u2f(bp[2]);
                 float col[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const float v = __fmaf_rn(vm_byte2f(e11.x, c), w11, __fmaf_rn(vm_byte2f(e10.x, c), w10,
-                                    __fmaf_rn(vm_byte2f(e01.x, c), w01, vm_byte2f(e00.x, c) * w00)));
-                    const float rr = (v + 12582912.f) - 12582912.f;        // nearest integer
-                    col[c] = rr;
-                    if (fabsf(v - rr) > 0.4995f) {       // too close to k + 0.5 for float32: exact path
-                        const VmBilin64 s = vm_mapcoord_setup(t0, t1, h, w);
-                        col[c] = (float)vm_round_half_up_u8(vm_mapcoord_blend(
-                            s, (double)((e00.x >> (8 * c)) & 255u), (double)((e01.x >> (8 * c)) & 255u),
-                            (double)((e10.x >> (8 * c)) & 255u), (double)((e11.x >> (8 * c)) & 255u)));
+                    const float v = __fmaf_rn(vm_byte2f(ev[z][3].x, c), wv[z][3], __fmaf_rn(vm_byte2f(ev[z][2].x, c), wv[z][2],
+                                    __fmaf_rn(vm_byte2f(ev[z][1].x, c), wv[z][1], vm_byte2f(ev[z][0].x, c) * wv[z][0])));
+                    col[c] = (v + 12582912.f) - 12582912.f;              // nearest integer
+                    if (fabsf(v - col[c]) > 0.4995f) unc |= 1u << (z * 4 + c);   // float32 cannot decide
+                }
+                float al[4], nl[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) vm_alpha_decode(ev[z][k].y, al[k], nl[k]);
+                const float a2 = __fmaf_rn(al[3], wv[z][3], __fmaf_rn(al[2], wv[z][2], __fmaf_rn(al[1], wv[z][1], al[0] * wv[z][0])));
+                const float na = __fmaf_rn(nl[3], wv[z][3], __fmaf_rn(nl[2], wv[z][2], __fmaf_rn(nl[1], wv[z][1], nl[0] * wv[z][0])));
+                o[z].x = __fmaf_rn(a2, col[0], na * bb);
+                o[z].y = __fmaf_rn(a2, col[1], na * bgc);
+                o[z].z = __fmaf_rn(a2, col[2], na * br);
+                o[z].w = a2;
+                if (!fast[z]) unc |= 8u << (z * 4);
+            }
+            if (unc) {
+                // rare: exact float64 re-evaluation (knife-edge samples, frame borders, gather tiles)
+#pragma unroll
+                for (int z = 0; z < 2; ++z) {
+                    if (!((unc >> (z * 4)) & 15u) || !live[z]) continue;
+                    const int ir = ir0 + z * RSTEP;
+                    const uint8_t *bp = bgt + ir * (TT_W * 3) + jc * 3;
+                    const float bb = vm_u2f(bp[0]), bgc = vm_u2f(bp[1]), br = vm_u2f(bp[2]);
+                    const VmBilin64 s = vm_mapcoord_setup(t0v[z], t1v[z], h, w);
+                    if (fast[z]) {
+                        float col[3];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            col[c] = (float)vm_round_half_up_u8(vm_mapcoord_blend(
+                                s, (double)((ev[z][0].x >> (8 * c)) & 255u), (double)((ev[z][1].x >> (8 * c)) & 255u),
+                                (double)((ev[z][2].x >> (8 * c)) & 255u), (double)((ev[z][3].x >> (8 * c)) & 255u)));
+                        float al[4], nl[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) vm_alpha_decode(ev[z][k].y, al[k], nl[k]);
+                        const float a2 = o[z].w;
+                        const float na = __fmaf_rn(nl[3], wv[z][3], __fmaf_rn(nl[2], wv[z][2], __fmaf_rn(nl[1], wv[z][1], nl[0] * wv[z][0])));
+                        o[z].x = __fmaf_rn(a2, col[0], na * bb);
+                        o[z].y = __fmaf_rn(a2, col[1], na * bgc);
+                        o[z].z = __fmaf_rn(a2, col[2], na * br);
+                    } else if (s.inside) {
+                        // last row / column of the frame, or a tile on the gather path
+                        const uint8_t *fg8 = reinterpret_cast<const uint8_t *>(fg32);
+                        const VmSrcPx s00 = vm_src_px<FLOW>(fg8, bf, ff, h, w, s.i0, s.j0, flags);
+                        const VmSrcPx s01 = vm_src_px<FLOW>(fg8, bf, ff, h, w, s.i0, s.j1, flags);
+                        const VmSrcPx s10 = vm_src_px<FLOW>(fg8, bf, ff, h, w, s.i1, s.j0, flags);
+                        const VmSrcPx s11 = vm_src_px<FLOW>(fg8, bf, ff, h, w, s.i1, s.j1, flags);
+                        const float cb = (float)vm_round_half_up_u8(vm_mapcoord_blend(s, s00.b, s01.b, s10.b, s11.b));
+                        const float cg = (float)vm_round_half_up_u8(vm_mapcoord_blend(s, s00.g, s01.g, s10.g, s11.g));
+                        const float cr = (float)vm_round_half_up_u8(vm_mapcoord_blend(s, s00.r, s01.r, s10.r, s11.r));
+                        const double a64 = vm_mapcoord_blend(s, s00.a, s01.a, s10.a, s11.a);
+                        const float a2 = (float)a64, na = (float)(1.0 - a64);
+                        o[z] = make_float4(__fmaf_rn(a2, cb, na * bb), __fmaf_rn(a2, cg, na * bgc), __fmaf_rn(a2, cr, na * br), a2);
+                    } else {
+                        o[z] = make_float4(bb, bgc, br, 0.f);
+                        outside++;
                     }
                 }
-                cb = col[0]; cg = col[1]; cr = col[2];
-                float al00, al01, al10, al11, nl00, nl01, nl10, nl11;
-                vm_alpha_decode(e00.y, al00, nl00); vm_alpha_decode(e01.y, al01, nl01);
-                vm_alpha_decode(e10.y, al10, nl10); vm_alpha_decode(e11.y, al11, nl11);
-                a2 = __fmaf_rn(al11, w11, __fmaf_rn(al10, w10, __fmaf_rn(al01, w01, al00 * w00)));
-                na = __fmaf_rn(nl11, w11, __fmaf_rn(nl10, w10, __fmaf_rn(nl01, w01, nl00 * w00)));
-            } else {
-                const VmBilin64 s = vm_mapcoord_setup(t0, t1, h, w);
-                if (s.inside) {
-                    // last row / column of the frame, or a tile on the gather path: float64 throughout
-                    const uint8_t *fg8 = reinterpret_cast<const uint8_t *>(fg32);
-                    const VmSrcPx s00 = vm_src_px<FLOW>(fg8, bf, ff, h, w, s.i0, s.j0, flags);
-                    const VmSrcPx s01 = vm_src_px<FLOW>(fg8, bf, ff, h, w, s.i0, s.j1, flags);
-                    const VmSrcPx s10 = vm_src_px<FLOW>(fg8, bf, ff, h, w, s.i1, s.j0, flags);
-                    const VmSrcPx s11 = vm_src_px<FLOW>(fg8, bf, ff, h, w, s.i1, s.j1, flags);
-                    cb = (float)vm_round_half_up_u8(vm_mapcoord_blend(s, s00.b, s01.b, s10.b, s11.b));
-                    cg = (float)vm_round_half_up_u8(vm_mapcoord_blend(s, s00.g, s01.g, s10.g, s11.g));
-                    cr = (float)vm_round_half_up_u8(vm_mapcoord_blend(s, s00.r, s01.r, s10.r, s11.r));
-                    const double a64 = vm_mapcoord_blend(s, s00.a, s01.a, s10.a, s11.a);
-                    a2 = (float)a64;
-                    na = (float)(1.0 - a64);
-                } else {
-                    outside++;
-                }
             }
-            float4 o;
-            o.x = __fmaf_rn(a2, cb, na * bb);
-            o.y = __fmaf_rn(a2, cg, na * bgc);
-            o.z = __fmaf_rn(a2, cr, na * br);
-            o.w = a2;
-            out[fbase + p32] = o;
+#pragma unroll
+            for (int z = 0; z < 2; ++z)
+                if (live[z]) out[fbase + (I0 + ir0 + z * RSTEP) * w + j] = o[z];
         }
     }
     if (status) {
