@@ -135,6 +135,7 @@ def run_ours(args):
     out = torch.empty((CLIP, H, W, 4), dtype=torch.float32, device=dev)
     status = vm._native.new_status(dev)
     lib = vm._native.load()
+    scratch = torch.empty(lib.vm_fused_scratch_bytes(CLIP, H, W), dtype=torch.uint8, device=dev)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     marks = []
@@ -145,7 +146,7 @@ def run_ours(args):
         vm._native.check(lib.vm_flow_tps_composite_bgra(
             fg.data_ptr(), fb.data_ptr(), ff.data_ptr(), bg.data_ptr(), bg.shape[0], ctrl.data_ptr(),
             coef.data_ptr(), NCTRL * NCTRL, plan.nx, plan.ny, plan.step_x, plan.step_y, plan.rows.data_ptr(),
-            plan.cols.data_ptr(), CLIP, H, W, out.data_ptr(), None, status.data_ptr(),
+            plan.cols.data_ptr(), CLIP, H, W, out.data_ptr(), scratch.data_ptr(), status.data_ptr(),
             torch.cuda.current_stream().cuda_stream))
         e2.record()
         if timed:

@@ -150,9 +150,9 @@ int vm_flow_warp_mask_bgra(const uint8_t *fg, const float *backward, const float
  * The coarse-grid spline evaluation (tps.py:101-121) is fused in: ctrl (n,N,2) / coef (n,N+3,2)
  * float64 as for vm_tps_coarse, coarse point (k,l) = (k*step_x, l*step_y).
  * out (n,h,w,4) float32 = {B, G, R composite (0..255), warped alpha}.  23 B/px.
- * `scratch`: device workspace of vm_fused_scratch_bytes(n,nx,ny) bytes, only touched by the
- * gather variant (N > 64 control points or vm_set_option("fused_variant", 1)).              */
-int64_t vm_fused_scratch_bytes(int n, int nx, int ny);
+ * `scratch`: device workspace of vm_fused_scratch_bytes(n,h,w) bytes (see below; may be NULL
+ * for this entry point unless the per-pixel gather variant is selected).                    */
+int64_t vm_fused_scratch_bytes(int n, int h, int w);
 int vm_tps_composite_bgra(const uint8_t *fg, const uint8_t *bg, int n_bg,
                           const double *ctrl, const double *coef, int N,
                           int nx, int ny, double step_x, double step_y,
@@ -160,10 +160,12 @@ int vm_tps_composite_bgra(const uint8_t *fg, const uint8_t *bg, int n_bg,
                           int n, int h, int w, float *out, void *scratch,
                           int32_t *status, void *stream);
 
-/* flow warp + consistency mask + TPS + composite in one pass (SURVEY 8d "C4 pipeline"):
+/* flow warp + consistency mask + TPS + composite (SURVEY 8d "C4 pipeline"):
  * warp_bgr/warp_img (flow.py:9-33), correct_alpha (flow.py:36-65), warp_image(identity affine,
  * thin) (augmentation.py:44-63 -> tps.py:14-123), create_composite_image (reader.py:72-79).
- * 39 B/px.  forward may be NULL (no consistency test).                                      */
+ * 39 algorithmic B/px.  forward may be NULL (no consistency test).  The default variant runs
+ * two kernels per chunk of frames - stage A writes the flow-warped pixel {bgr, alpha code}
+ * (8 B/px) into `scratch`, stage B resamples it - with the chunk sized to stay in L2.        */
 int vm_flow_tps_composite_bgra(const uint8_t *fg, const float *backward, const float *forward,
                                const uint8_t *bg, int n_bg,
                                const double *ctrl, const double *coef, int N,
@@ -172,8 +174,9 @@ int vm_flow_tps_composite_bgra(const uint8_t *fg, const float *backward, const f
                                int n, int h, int w, float *out, void *scratch,
                                int32_t *status, void *stream);
 
-/* Tuning / test switches: "fused_variant" 0 = shared-memory tiled kernel (default), 1 =
- * per-pixel gather kernel; "tile_h" 32 or 64 (rows per tile of the tiled kernel).           */
+/* Tuning / test switches: "fused_variant" 0 = split pipeline (default), 1 = per-pixel gather
+ * kernel, 2 = single shared-memory tiled kernel; "tile_h" 32 or 64 (rows per tile of variant
+ * 2); "chunk_frames" frames per stage-A/stage-B pair of variant 0.                          */
 int vm_set_option(const char *key, int value);
 
 #ifdef __cplusplus

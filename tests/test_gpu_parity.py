@@ -271,17 +271,17 @@ def test_augment_golden(vm, golden):
 
 # ------------------------------------------------------------------------- fused C3 / C4
 
-VARIANTS = [(0, 64), (0, 32), (1, 64)]       # (fused_variant, tile_h): tiled 64, tiled 32, gather
+VARIANTS = [(0, 32), (2, 64), (2, 32), (1, 32)]   # (fused_variant, tile_h): split, tiled 64, tiled 32, gather
 
 
-@pytest.fixture(params=VARIANTS, ids=["tiled64", "tiled32", "gather"])
+@pytest.fixture(params=VARIANTS, ids=["split", "tiled64", "tiled32", "gather"])
 def variant(request, vm):
     v, th = request.param
     vm.pipeline.set_fused_variant(v)
     vm._native.set_option("tile_h", th)
     yield request.param
     vm.pipeline.set_fused_variant(0)
-    vm._native.set_option("tile_h", 64)
+    vm._native.set_option("tile_h", 32)
 
 
 @pytest.mark.parametrize("tag", ["a", "b", "c"])
@@ -333,7 +333,11 @@ def test_fused_degenerate_grid_takes_gather_path(vm):
     grid, dgrid = O.synth_grids(5, h, w, 5)
     dgrid = grid + (dgrid - grid) * 6.0          # 30 % displacements: strongly stretched tiles
     ctrl, coef = P.solve_grids([(grid, dgrid)])
-    out, st = P.flow_tps_composite(dev(frame[None]), dev(fb[None]), dev(ff[None]), dev(bg[None]), ctrl, coef)
+    P.set_fused_variant(2)
+    try:
+        out, st = P.flow_tps_composite(dev(frame[None]), dev(fb[None]), dev(ff[None]), dev(bg[None]), ctrl, coef)
+    finally:
+        P.set_fused_variant(0)
     rc, ra = O.pipeline_c4(frame, fb, ff, (grid, dgrid), bg)
     got = out[0].cpu().numpy()
     assert close(got[..., 3], ra, 1e-6)

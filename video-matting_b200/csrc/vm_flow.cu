@@ -157,16 +157,16 @@ __device__ __forceinline__ float vm_alpha_f32(uint32_t ta) {
     return (ta > nta) ? 1.f - s : s;
 }
 
-template <bool HAS_FWD>
-__global__ void __launch_bounds__(256)
+// PACKED = false: out_bgr (n,h,w,3) uint8 + out_alpha (n,h,w) float32 (the C2 result);
+// PACKED = true : out_bgr is a (n,h,w) uint2 array {B|G<<8|R<<16, alpha code} - the stage-A
+// intermediate of the split C4 pipeline (see vm_tps.cu), out_alpha unused.
+template <bool HAS_FWD, bool PACKED>
+__global__ void __launch_bounds__(256, 6)
 k_flow_warp_mask_bgra(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd,
                       const float2 *__restrict__ fwd, int h, int w, int tiles_x, int tiles_y,
                       uint8_t *__restrict__ out_bgr, float *__restrict__ out_alpha,
                       int32_t *__restrict__ status) {
-    const int tile = blockIdx.x;
-    const int frame = tile / (tiles_x * tiles_y);
-    const int t = tile - frame * tiles_x * tiles_y;
-    const int ty = t / tiles_x, tx = t - ty * tiles_x;
+    const int frame = blockIdx.z, ty = blockIdx.y, tx = blockIdx.x;     // 3-D grid: no integer division
     const int i = ty * C2_TH + (threadIdx.x >> 5);
     const int j = tx * C2_TW + (threadIdx.x & 31) * 4;
     if (i >= h || j >= w) return;
@@ -185,6 +185,14 @@ k_flow_warp_mask_bgra(const uint8_t *__restrict__ fg, const float2 *__restrict__
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             px[k] = vm_flow_px<HAS_FWD>(fg32, ff, h, w, i, j + k, fi, fj + (float)k, fl[k], flags);
+        if (PACKED) {
+            uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<uint2 *>(out_bgr) + fbase + p);
+            op[0] = make_uint4(px[0].bgr, px[0].masked ? 0u : vm_alpha_code(px[0].ta),
+                               px[1].bgr, px[1].masked ? 0u : vm_alpha_code(px[1].ta));
+            op[1] = make_uint4(px[2].bgr, px[2].masked ? 0u : vm_alpha_code(px[2].ta),
+                               px[3].bgr, px[3].masked ? 0u : vm_alpha_code(px[3].ta));
+            goto done;
+        }
         float al[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) al[k] = px[k].masked ? 0.f : vm_alpha_f32(px[k].ta);
@@ -199,15 +207,34 @@ k_flow_warp_mask_bgra(const uint8_t *__restrict__ fg, const float2 *__restrict__
         for (int k = 0; k < 4 && j + k < w; ++k) {
             const float2 f = __ldg(bf + p + k);
             const VmFlowPx px = vm_flow_px<HAS_FWD>(fg32, ff, h, w, i, j + k, fi, fj + (float)k, f, flags);
+            if (PACKED) {
+                reinterpret_cast<uint2 *>(out_bgr)[fbase + p + k] = make_uint2(px.bgr, px.masked ? 0u : vm_alpha_code(px.ta));
+                continue;
+            }
             uint8_t *ob = out_bgr + (fbase + p + k) * 3;
             ob[0] = (uint8_t)px.bgr; ob[1] = (uint8_t)(px.bgr >> 8); ob[2] = (uint8_t)(px.bgr >> 16);
             out_alpha[fbase + p + k] = px.masked ? 0.f : vm_alpha_f32(px.ta);
         }
     }
+done:
     if (HAS_FWD && flags && status) {
         if (flags & 1) atomicAdd(status + VM_STATUS_INDEX_ERR, 1);
         if (flags & 2) atomicAdd(status + VM_STATUS_NAN_ERR, 1);
     }
+}
+
+// stage A of the split C4 pipeline: (n,h,w) uint2 {bgr, alpha code}
+int vm_launch_flow_stage(const uint8_t *fg, const float *backward, const float *forward, int n, int h, int w,
+                         void *packed, int32_t *status, cudaStream_t st) {
+    const int tiles_x = (w + C2_TW - 1) / C2_TW, tiles_y = (h + C2_TH - 1) / C2_TH;
+    const dim3 tiles(tiles_x, tiles_y, n);
+    if (forward)
+        k_flow_warp_mask_bgra<true, true><<<tiles, 256, 0, st>>>(fg, (const float2 *)backward, (const float2 *)forward, h, w,
+                                                                 tiles_x, tiles_y, (uint8_t *)packed, nullptr, status);
+    else
+        k_flow_warp_mask_bgra<false, true><<<tiles, 256, 0, st>>>(fg, (const float2 *)backward, nullptr, h, w, tiles_x,
+                                                                  tiles_y, (uint8_t *)packed, nullptr, status);
+    return vm_check_launch("vm_flow_stage");
 }
 
 extern "C" int vm_flow_warp_mask_bgra(const uint8_t *fg, const float *backward, const float *forward,
@@ -217,14 +244,14 @@ extern "C" int vm_flow_warp_mask_bgra(const uint8_t *fg, const float *backward, 
     VM_REQUIRE(n >= 0 && h > 0 && w > 0 && h <= 32767 && w <= 32767, "bad size");
     if (n == 0) return VM_OK;
     const int tiles_x = (w + C2_TW - 1) / C2_TW, tiles_y = (h + C2_TH - 1) / C2_TH;
-    const int64_t tiles = (int64_t)n * tiles_x * tiles_y;
-    VM_REQUIRE(tiles < (1ll << 31), "too many tiles for one launch");
+    VM_REQUIRE(tiles_y <= 65535 && n <= 65535, "too many tiles for one launch");
+    const dim3 tiles(tiles_x, tiles_y, n);
     cudaStream_t st = (cudaStream_t)stream;
     if (forward)
-        k_flow_warp_mask_bgra<true><<<(unsigned)tiles, 256, 0, st>>>(
+        k_flow_warp_mask_bgra<true, false><<<tiles, 256, 0, st>>>(
             fg, (const float2 *)backward, (const float2 *)forward, h, w, tiles_x, tiles_y, out_bgr, out_alpha, status);
     else
-        k_flow_warp_mask_bgra<false><<<(unsigned)tiles, 256, 0, st>>>(
+        k_flow_warp_mask_bgra<false, false><<<tiles, 256, 0, st>>>(
             fg, (const float2 *)backward, nullptr, h, w, tiles_x, tiles_y, out_bgr, out_alpha, status);
     return vm_check_launch("vm_flow_warp_mask_bgra");
 }

@@ -365,16 +365,20 @@ template <int TH> struct TileCfg {
     static_assert(CR * NSEG <= TT_THREADS, "coarse tile does not fit one pass");
 };
 
-template <int TH> struct __align__(16) TileSmem {
-    double2 logtab[VM_LOG_N];
+template <int TH> struct __align__(16) CoarseSmem {
+    double2 logtab[VM_LOG_N];                              // P1 only; reused as the bg tile afterwards
     double4 ctrl[TT_MAX_N];                                // {Px, Py, w0/2, w1/2}
     vm_axis_entry rows[TH];
     vm_axis_entry cols[TT_W];
     double2 T[TileCfg<TH>::CR * TileCfg<TH>::CC];          // {row coord, col coord} per coarse point
-    uint2 inter[TileCfg<TH>::IMAX];                        // {B | G<<8 | R<<16, alpha code}
     double aff[6];
     int box[4];                                            // rmin, rmax, cmin, cmax (floors)
     int bad;
+    int pad;
+};
+
+template <int TH> struct __align__(16) TileSmem : CoarseSmem<TH> {
+    uint2 inter[TileCfg<TH>::IMAX];                        // {B | G<<8 | R<<16, alpha code}
 };
 
 // log(x), x > 0 finite (x = 0 gives a finite value, so that 0 * log(0) = 0 as in tps.py:81)
@@ -392,28 +396,18 @@ __device__ __forceinline__ double vm_log_tab_smem(double x, const double2 *__res
     return fma(ed, 0.6931471805599453094, fma(r, q, t.y));
 }
 
-template <bool FLOW, int TH>
-__global__ void __launch_bounds__(TT_THREADS, (TH == 64) ? 2 : 3)
-k_tps_tiled(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd, const float2 *__restrict__ fwd,
-            const uint8_t *__restrict__ bg, int n_bg, const double *__restrict__ ctrl,
-            const double *__restrict__ coef, int N, int nx, int ny, double step_x, double step_y,
-            const vm_axis_entry *__restrict__ rows, const vm_axis_entry *__restrict__ cols,
-            int h, int w, int tiles_x, int tiles_y, float4 *__restrict__ out, int32_t *__restrict__ status) {
+// P0 + P1 of a tile: stage control points / log table / axis entries, evaluate the spline on the
+// tile's coarse sub-grid into S.T and reduce the bounding box of the coarse values.  Returns
+// false (after counting it) when the axis tables are not those of a /2 grid.
+template <int TH>
+__device__ __forceinline__ bool vm_tile_coarse(CoarseSmem<TH> &S, const double *__restrict__ ctrl,
+                                               const double *__restrict__ coef, int N, double step_x, double step_y,
+                                               const vm_axis_entry *__restrict__ rows,
+                                               const vm_axis_entry *__restrict__ cols, int frame, int I0, int J0,
+                                               int th, int tw, int32_t *__restrict__ status, int &kr0, int &kc0,
+                                               int &nkr_out, int &nkc_out) {
     using Cfg = TileCfg<TH>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileSmem<TH> &S = *reinterpret_cast<TileSmem<TH> *>(smem_raw);
     const int tid = threadIdx.x;
-    const int per = tiles_x * tiles_y;
-    const int frame = blockIdx.x / per;
-    const int tl = blockIdx.x - frame * per;
-    const int ty = tl / tiles_x, tx = tl - ty * tiles_x;
-    const int I0 = ty * TH, J0 = tx * TT_W;
-    const int th = min(TH, h - I0), tw = min(TT_W, w - J0);
-    const int64_t fbase = (int64_t)frame * h * w;
-    const uint32_t *fg32 = reinterpret_cast<const uint32_t *>(fg) + fbase;
-    const float2 *bf = FLOW ? bwd + fbase : nullptr;
-    const float2 *ff = (FLOW && fwd) ? fwd + fbase : nullptr;
-
     // ---- P0 ----------------------------------------------------------------------------
     {
         const double *P = ctrl + (int64_t)frame * N * 2;
@@ -426,11 +420,12 @@ k_tps_tiled(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd, cons
         if (tid == 0) { S.box[0] = INT_MAX; S.box[1] = INT_MIN; S.box[2] = INT_MAX; S.box[3] = INT_MIN; S.bad = 0; }
     }
     __syncthreads();
-    const int kr0 = S.rows[0].i0, kc0 = S.cols[0].i0;
+    kr0 = S.rows[0].i0; kc0 = S.cols[0].i0;
     const int nkr = S.rows[th - 1].i1 - kr0 + 1, nkc = S.cols[tw - 1].i1 - kc0 + 1;
+    nkr_out = nkr; nkc_out = nkc;
     if (nkr < 1 || nkc < 1 || nkr > Cfg::CR || nkc > Cfg::CC) {      // axis tables are not those of a /2 grid
         if (status && tid == 0) atomicAdd(status + VM_STATUS_BAD_TABLE, 1);
-        return;
+        return false;
     }
 
     // ---- P1: coarse radial-basis evaluation: thread = run of SEG points in one coarse row ---
@@ -483,6 +478,34 @@ k_tps_tiled(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd, cons
         }
     }
     __syncthreads();
+    return true;
+}
+
+template <bool FLOW, int TH>
+__global__ void __launch_bounds__(TT_THREADS, (TH == 64) ? 2 : 3)
+k_tps_tiled(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd, const float2 *__restrict__ fwd,
+            const uint8_t *__restrict__ bg, int n_bg, const double *__restrict__ ctrl,
+            const double *__restrict__ coef, int N, int nx, int ny, double step_x, double step_y,
+            const vm_axis_entry *__restrict__ rows, const vm_axis_entry *__restrict__ cols,
+            int h, int w, int tiles_x, int tiles_y, float4 *__restrict__ out, int32_t *__restrict__ status) {
+    using Cfg = TileCfg<TH>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem<TH> &S = *reinterpret_cast<TileSmem<TH> *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int per = tiles_x * tiles_y;
+    const int frame = blockIdx.x / per;
+    const int tl = blockIdx.x - frame * per;
+    const int ty = tl / tiles_x, tx = tl - ty * tiles_x;
+    const int I0 = ty * TH, J0 = tx * TT_W;
+    const int th = min(TH, h - I0), tw = min(TT_W, w - J0);
+    const int64_t fbase = (int64_t)frame * h * w;
+    const uint32_t *fg32 = reinterpret_cast<const uint32_t *>(fg) + fbase;
+    const float2 *bf = FLOW ? bwd + fbase : nullptr;
+    const float2 *ff = (FLOW && fwd) ? fwd + fbase : nullptr;
+
+    int kr0, kc0, nkr, nkc;
+    if (!vm_tile_coarse<TH>(S, ctrl, coef, N, step_x, step_y, rows, cols, frame, I0, J0, th, tw, status, kr0, kc0, nkr, nkc))
+        return;
     // source box actually addressed by in-range pixels: rows [rmin, rmax+1], cols [cmin, cmax+1]
     const int rmin = max(S.box[0], 0), rmax = min(S.box[1] + 1, h - 1);
     const int cmin = max(S.box[2], 0), cmax = min(S.box[3] + 1, w - 1);
@@ -697,14 +720,183 @@ k_tps_tiled(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd, cons
     }
 }
 
-// option block (vm_set_option): variant 0 = tiled (default), 1 = per-pixel gather kernels
+// ---------------------------------------------------------------------------------------
+// Split pipeline, stage B: TPS resampling + composite with the source pixels gathered from
+// global memory through L1/L2 (no shared-memory source box, so 4 CTAs per SM).
+//
+//   PACKED = true : src is the (n,h,w) uint2 {bgr, alpha code} intermediate written by stage A
+//                   (k_flow_warp_mask_bgra<.., PACKED>) for the same frames - produced a few
+//                   microseconds earlier, so it is served from the 126 MB L2;
+//   PACKED = false: src is the BGRA clip itself (C3: no flow stage at all).
+// Phases P0/P1 (spline on the tile's coarse sub-grid) are those of the tiled kernel.
+// ---------------------------------------------------------------------------------------
+template <bool PACKED>
+__device__ __forceinline__ uint2 vm_ld_src(const void *__restrict__ src, int idx) {
+    if (PACKED) return __ldg(reinterpret_cast<const uint2 *>(src) + idx);
+    const uint32_t s = __ldg(reinterpret_cast<const uint32_t *>(src) + idx);
+    return make_uint2(s & 0x00FFFFFFu, vm_alpha_code((s >> 24) * 1024u));
+}
+
+template <bool PACKED, int TH>
+__global__ void __launch_bounds__(TT_THREADS, 4)
+k_tps_gather2(const void *__restrict__ src_all, const uint8_t *__restrict__ bg, int n_bg, int frame0,
+              const double *__restrict__ ctrl, const double *__restrict__ coef, int N, double step_x,
+              double step_y, const vm_axis_entry *__restrict__ rows, const vm_axis_entry *__restrict__ cols,
+              int h, int w, float4 *__restrict__ out, int32_t *__restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CoarseSmem<TH> &S = *reinterpret_cast<CoarseSmem<TH> *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int frame = blockIdx.z, I0 = blockIdx.y * TH, J0 = blockIdx.x * TT_W;   // frame: index in this launch
+    const int th = min(TH, h - I0), tw = min(TT_W, w - J0);
+    const int64_t fbase = (int64_t)frame * h * w;
+    const void *src = PACKED ? (const void *)(reinterpret_cast<const uint2 *>(src_all) + fbase)
+                             : (const void *)(reinterpret_cast<const uint32_t *>(src_all) + fbase);
+    int kr0, kc0, nkr, nkc;
+    if (!vm_tile_coarse<TH>(S, ctrl, coef, N, step_x, step_y, rows, cols, frame, I0, J0, th, tw, status, kr0, kc0, nkr, nkc))
+        return;
+    const bool finite = !S.bad;
+
+    // background tile -> (dead) log-table space, asynchronously
+    uint8_t *bgt = reinterpret_cast<uint8_t *>(S.logtab);           // [TH][TT_W * 3]
+    const uint8_t *bgf = bg + (int64_t)((frame0 + frame) % n_bg) * h * w * 3;
+    const bool bg_async = (w & 15) == 0 && tw == TT_W && (reinterpret_cast<uintptr_t>(bg) & 15) == 0;
+    if (bg_async) {
+        for (int c = tid; c < th * (TT_W * 3 / 16); c += TT_THREADS) {
+            const int r = c / (TT_W * 3 / 16), k = c - r * (TT_W * 3 / 16);
+            const uint8_t *g = bgf + ((int64_t)(I0 + r) * w + J0) * 3 + k * 16;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(bgt + r * (TT_W * 3) + k * 16);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g));
+        }
+        asm volatile("cp.async.commit_group;");
+        asm volatile("cp.async.wait_group 0;");
+    } else {
+        for (int c = tid; c < th * tw * 3; c += TT_THREADS) {
+            const int r = c / (tw * 3), k = c - r * (tw * 3);
+            bgt[r * (TT_W * 3) + k] = __ldg(bgf + ((int64_t)(I0 + r) * w + J0) * 3 + k);
+        }
+    }
+    __syncthreads();
+
+    const int jc = tid & (TT_W - 1);
+    int outside = 0;
+    if (jc < tw) {
+        const vm_axis_entry ce = S.cols[jc];
+        const int c0 = ce.i0 - kc0, c1 = ce.i1 - kc0;
+        const double yf = ce.frac, y1 = 1.0 - yf;
+        const int j = J0 + jc;
+        constexpr int RSTEP = TT_THREADS / TT_W;
+        for (int ir0 = tid / TT_W; ir0 < th; ir0 += 2 * RSTEP) {
+            float4 o[2];
+            double t0v[2], t1v[2];
+            uint2 ev[2][4];
+            float wv[2][4];
+            bool fast[2], live[2];
+            unsigned unc = 0;
+#pragma unroll
+            for (int z = 0; z < 2; ++z) {
+                const int ir = ir0 + z * RSTEP;
+                live[z] = ir < th;
+                const vm_axis_entry re = S.rows[min(ir, th - 1)];
+                const int o0 = (re.i0 - kr0) * nkc, o1 = (re.i1 - kr0) * nkc;
+                const double xf = re.frac, x1 = 1.0 - xf;
+                const double2 T00 = S.T[o0 + c0], T01 = S.T[o0 + c1], T10 = S.T[o1 + c0], T11 = S.T[o1 + c1];
+                const double u00 = x1 * y1, u01 = x1 * yf, u10 = xf * y1, u11 = xf * yf;
+                const double t0 = fma(T11.x, u11, fma(T10.x, u10, fma(T01.x, u01, T00.x * u00)));
+                const double t1 = fma(T11.y, u11, fma(T10.y, u10, fma(T01.y, u01, T00.y * u00)));
+                t0v[z] = t0; t1v[z] = t1;
+                const double m0 = t0 + 6755399441055744.0, m1 = t1 + 6755399441055744.0;
+                const double d0 = t0 - (m0 - 6755399441055744.0), d1 = t1 - (m1 - 6755399441055744.0);
+                const int n0 = __double2loint(m0) - (d0 < 0.0 ? 1 : 0);
+                const int n1 = __double2loint(m1) - (d1 < 0.0 ? 1 : 0);
+                // strictly inside the frame with both neighbours (|t| < 2^31 is implied by `finite`)
+                fast[z] = finite && (unsigned)n0 < (unsigned)(h - 1) && (unsigned)n1 < (unsigned)(w - 1);
+                const int q = fast[z] ? n0 * w + n1 : 0, qs = fast[z] ? w : 0;
+                ev[z][0] = vm_ld_src<PACKED>(src, q); ev[z][1] = vm_ld_src<PACKED>(src, q + 1);
+                ev[z][2] = vm_ld_src<PACKED>(src, q + qs); ev[z][3] = vm_ld_src<PACKED>(src, q + qs + 1);
+                const float af = (float)d0 + (d0 < 0.0 ? 1.f : 0.f), bfr = (float)d1 + (d1 < 0.0 ? 1.f : 0.f);
+                const float a0f = 1.f - af, b0f = 1.f - bfr;
+                wv[z][0] = a0f * b0f; wv[z][1] = a0f * bfr; wv[z][2] = af * b0f; wv[z][3] = af * bfr;
+            }
+#pragma unroll
+            for (int z = 0; z < 2; ++z) {
+                const int ir = min(ir0 + z * RSTEP, th - 1);
+                const uint8_t *bp = bgt + ir * (TT_W * 3) + jc * 3;
+                const float bb = vm_u2f(bp[0]), bgc = vm_u2f(bp[1]), br = vm_u2f(bp[2]);
+                float col[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float v = __fmaf_rn(vm_byte2f(ev[z][3].x, c), wv[z][3], __fmaf_rn(vm_byte2f(ev[z][2].x, c), wv[z][2],
+                                    __fmaf_rn(vm_byte2f(ev[z][1].x, c), wv[z][1], vm_byte2f(ev[z][0].x, c) * wv[z][0])));
+                    col[c] = (v + 12582912.f) - 12582912.f;
+                    if (fabsf(v - col[c]) > 0.4995f) unc |= 1u << (z * 4 + c);
+                }
+                float al[4], nl[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) vm_alpha_decode(ev[z][k].y, al[k], nl[k]);
+                const float a2 = __fmaf_rn(al[3], wv[z][3], __fmaf_rn(al[2], wv[z][2], __fmaf_rn(al[1], wv[z][1], al[0] * wv[z][0])));
+                const float na = __fmaf_rn(nl[3], wv[z][3], __fmaf_rn(nl[2], wv[z][2], __fmaf_rn(nl[1], wv[z][1], nl[0] * wv[z][0])));
+                o[z].x = __fmaf_rn(a2, col[0], na * bb);
+                o[z].y = __fmaf_rn(a2, col[1], na * bgc);
+                o[z].z = __fmaf_rn(a2, col[2], na * br);
+                o[z].w = a2;
+                if (!fast[z]) unc |= 8u << (z * 4);
+            }
+            if (unc) {
+                // rare: exact float64 re-evaluation (knife-edge samples, last row/column, outside)
+#pragma unroll
+                for (int z = 0; z < 2; ++z) {
+                    if (!((unc >> (z * 4)) & 15u) || !live[z]) continue;
+                    const int ir = ir0 + z * RSTEP;
+                    const uint8_t *bp = bgt + ir * (TT_W * 3) + jc * 3;
+                    const float bb = vm_u2f(bp[0]), bgc = vm_u2f(bp[1]), br = vm_u2f(bp[2]);
+                    const VmBilin64 s = vm_mapcoord_setup(t0v[z], t1v[z], h, w);
+                    if (!s.inside) {
+                        o[z] = make_float4(bb, bgc, br, 0.f);
+                        outside++;
+                        continue;
+                    }
+                    if (!fast[z]) {                           // t on the last row / column: clamped neighbours
+                        ev[z][0] = vm_ld_src<PACKED>(src, s.i0 * w + s.j0); ev[z][1] = vm_ld_src<PACKED>(src, s.i0 * w + s.j1);
+                        ev[z][2] = vm_ld_src<PACKED>(src, s.i1 * w + s.j0); ev[z][3] = vm_ld_src<PACKED>(src, s.i1 * w + s.j1);
+                    }
+                    float col[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        col[c] = (float)vm_round_half_up_u8(vm_mapcoord_blend(
+                            s, (double)((ev[z][0].x >> (8 * c)) & 255u), (double)((ev[z][1].x >> (8 * c)) & 255u),
+                            (double)((ev[z][2].x >> (8 * c)) & 255u), (double)((ev[z][3].x >> (8 * c)) & 255u)));
+                    float al[4], nl[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) vm_alpha_decode(ev[z][k].y, al[k], nl[k]);
+                    const float w0 = (float)(s.a0 * s.b0), w1 = (float)(s.a0 * s.b1), w2 = (float)(s.a1 * s.b0), w3 = (float)(s.a1 * s.b1);
+                    const float a2 = __fmaf_rn(al[3], w3, __fmaf_rn(al[2], w2, __fmaf_rn(al[1], w1, al[0] * w0)));
+                    const float na = __fmaf_rn(nl[3], w3, __fmaf_rn(nl[2], w2, __fmaf_rn(nl[1], w1, nl[0] * w0)));
+                    o[z] = make_float4(__fmaf_rn(a2, col[0], na * bb), __fmaf_rn(a2, col[1], na * bgc),
+                                       __fmaf_rn(a2, col[2], na * br), a2);
+                }
+            }
+#pragma unroll
+            for (int z = 0; z < 2; ++z)
+                if (live[z]) out[fbase + (I0 + ir0 + z * RSTEP) * w + j] = o[z];
+        }
+    }
+    if (status) {
+        outside = __reduce_add_sync(0xffffffffu, outside);
+        if ((tid & 31) == 0 && outside) atomicAdd(status + VM_STATUS_TPS_OUTSIDE, outside);
+    }
+}
+
+// option block (vm_set_option): variant 0 = split pipeline (default), 1 = per-pixel gather
+// kernels, 2 = single shared-memory tiled kernel
 static int g_opt_variant = 0;
-static int g_opt_tile_h = 64;
+static int g_opt_chunk = 4;                  // frames per stage-A/stage-B launch pair
+static int g_opt_tile_h = 32;
 
 extern "C" int vm_set_option(const char *key, int value) {
     if (!key) return VM_ERR_ARG;
     if (!strcmp(key, "fused_variant")) { g_opt_variant = value; return VM_OK; }
     if (!strcmp(key, "tile_h") && (value == 32 || value == 64)) { g_opt_tile_h = value; return VM_OK; }
+    if (!strcmp(key, "chunk_frames") && value >= 1 && value <= 4096) { g_opt_chunk = value; return VM_OK; }
     vm_set_error("vm_set_option: unknown option %s=%d", key, value);
     return VM_ERR_ARG;
 }
@@ -726,6 +918,28 @@ static int launch_tiled(const uint8_t *fg, const float *backward, const float *f
     return vm_check_launch(what);
 }
 
+int vm_launch_flow_stage(const uint8_t *fg, const float *backward, const float *forward, int n, int h, int w,
+                         void *packed, int32_t *status, cudaStream_t st);          // vm_flow.cu
+
+template <bool PACKED, int TH>
+static int launch_gather2(const void *src, const uint8_t *bg, int n_bg, int frame0, const double *ctrl,
+                          const double *coef, int N, double step_x, double step_y, const vm_axis_entry *rows,
+                          const vm_axis_entry *cols, int n, int h, int w, float *out, int32_t *status,
+                          cudaStream_t st, const char *what) {
+    const dim3 grid((w + TT_W - 1) / TT_W, (h + TH - 1) / TH, n);
+    VM_REQUIRE(grid.y <= 65535 && n <= 65535, "too many tiles for one launch");
+    const size_t smem = sizeof(CoarseSmem<TH>);
+    k_tps_gather2<PACKED, TH><<<grid, TT_THREADS, smem, st>>>(src, bg, n_bg, frame0, ctrl, coef, N, step_x, step_y,
+                                                              rows, cols, h, w, (float4 *)out, status);
+    return vm_check_launch(what);
+}
+
+static int64_t fused_scratch_bytes(int n, int h, int w) {
+    if (g_opt_variant == 0) return (int64_t)(n < g_opt_chunk ? n : g_opt_chunk) * h * w * 8;
+    if (g_opt_variant == 1) return (int64_t)n * 2 * (h / 2) * (w / 2) * (int64_t)sizeof(double);
+    return 0;
+}
+
 static int launch_fused(bool flow, const uint8_t *fg, const float *backward, const float *forward,
                         const uint8_t *bg, int n_bg, const double *ctrl, const double *coef, int N, int nx, int ny,
                         double step_x, double step_y, const vm_axis_entry *rows, const vm_axis_entry *cols, int n,
@@ -733,16 +947,37 @@ static int launch_fused(bool flow, const uint8_t *fg, const float *backward, con
     if (n == 0) return VM_OK;
     int rc = vm_init();
     if (rc != VM_OK) return rc;
+    VM_REQUIRE(h <= 32767 && w <= 32767 && (int64_t)h * w < (1ll << 28), "frame too large");
     cudaStream_t st = (cudaStream_t)stream;
-    if (g_opt_variant == 0 && N <= TT_MAX_N && h >= 2 && w >= 2) {
+    const bool small_n = N <= TT_MAX_N && h >= 2 && w >= 2;
+    if (g_opt_variant == 0 && small_n) {
+        // split pipeline: stage A (flow warp + mask -> packed intermediate, L2 resident) and stage B
+        // (TPS + composite) per chunk of frames; C3 has no stage A.
+        if (!flow)
+            return launch_gather2<false, 32>(fg, bg, n_bg, 0, ctrl, coef, N, step_x, step_y, rows, cols, n, h, w, out,
+                                             status, st, what);
+        VM_REQUIRE(scratch, "scratch workspace (vm_fused_scratch_bytes) required");
+        const int64_t px = (int64_t)h * w;
+        for (int f0 = 0; f0 < n; f0 += g_opt_chunk) {
+            const int m = (n - f0 < g_opt_chunk) ? n - f0 : g_opt_chunk;
+            rc = vm_launch_flow_stage(fg + f0 * px * 4, backward + f0 * px * 2, forward ? forward + f0 * px * 2 : nullptr,
+                                      m, h, w, scratch, status, st);
+            if (rc != VM_OK) return rc;
+            rc = launch_gather2<true, 32>(scratch, bg, n_bg, f0, ctrl + (int64_t)f0 * N * 2, coef + (int64_t)f0 * (N + 3) * 2,
+                                          N, step_x, step_y, rows, cols, m, h, w, out + f0 * px * 4, status, st, what);
+            if (rc != VM_OK) return rc;
+        }
+        return VM_OK;
+    }
+    if (g_opt_variant == 2 && small_n) {
         if (g_opt_tile_h == 64)
             return flow ? launch_tiled<true, 64>(fg, backward, forward, bg, n_bg, ctrl, coef, N, nx, ny, step_x, step_y, rows, cols, n, h, w, out, status, st, what)
                         : launch_tiled<false, 64>(fg, nullptr, nullptr, bg, n_bg, ctrl, coef, N, nx, ny, step_x, step_y, rows, cols, n, h, w, out, status, st, what);
         return flow ? launch_tiled<true, 32>(fg, backward, forward, bg, n_bg, ctrl, coef, N, nx, ny, step_x, step_y, rows, cols, n, h, w, out, status, st, what)
                     : launch_tiled<false, 32>(fg, nullptr, nullptr, bg, n_bg, ctrl, coef, N, nx, ny, step_x, step_y, rows, cols, n, h, w, out, status, st, what);
     }
-    // gather variant: coarse transform through global scratch, then one pixel per thread
-    VM_REQUIRE(scratch, "scratch workspace required for the gather variant");
+    // per-pixel gather variant: coarse transform through global scratch, then one pixel per thread
+    VM_REQUIRE(scratch, "scratch workspace (vm_fused_scratch_bytes) required");
     double *coarse = (double *)scratch;
     rc = vm_tps_coarse(ctrl, coef, n, N, nx, ny, step_x, step_y, 0.0, 0.0, coarse, stream);
     if (rc != VM_OK) return rc;
@@ -756,8 +991,12 @@ static int launch_fused(bool flow, const uint8_t *fg, const float *backward, con
     return vm_check_launch(what);
 }
 
-extern "C" int64_t vm_fused_scratch_bytes(int n, int nx, int ny) {
-    return (int64_t)n * 2 * nx * ny * (int64_t)sizeof(double);
+extern "C" int64_t vm_fused_scratch_bytes(int n, int h, int w) {
+    // enough for every variant selectable with vm_set_option for this clip shape
+    const int64_t a = (int64_t)(n < g_opt_chunk ? n : g_opt_chunk) * h * w * 8;
+    const int64_t b = (int64_t)n * 2 * (h / 2) * (w / 2) * (int64_t)sizeof(double);
+    (void)fused_scratch_bytes;
+    return a > b ? a : b;
 }
 
 extern "C" int vm_tps_composite_bgra(const uint8_t *fg, const uint8_t *bg, int n_bg, const double *ctrl,

@@ -312,12 +312,22 @@ def _tps_args(ctrl, coef, n):
     return ctrl, coef, Np
 
 
+_scratch_cache = {}
+
+
 def _fused_scratch(lib, n, plan, scratch, device):
-    """Workspace of the gather variant (coarse transform in global memory); the default tiled
-    kernel keeps the coarse transform in shared memory and never touches it."""
-    need = lib.vm_fused_scratch_bytes(n, plan.nx, plan.ny)
+    """Workspace of the fused entry points: the packed flow-warped intermediate of the split
+    pipeline (a few frames, L2 resident) or the coarse transform of the gather variant.  One
+    buffer per device is cached; work on one stream at a time per device or pass ``scratch``."""
+    h, w = plan.region[2], plan.region[3]
+    need = lib.vm_fused_scratch_bytes(n, h, w)
     if scratch is None or scratch.numel() * scratch.element_size() < need:
-        scratch = torch.empty(need, dtype=torch.uint8, device=device)
+        key = (device.index if device.index is not None else torch.cuda.current_device())
+        cached = _scratch_cache.get(key)
+        if cached is None or cached.numel() < need:
+            cached = torch.empty(need, dtype=torch.uint8, device=device)
+            _scratch_cache[key] = cached
+        scratch = cached
     return scratch
 
 
@@ -335,7 +345,7 @@ def tps_composite(fg, bg, ctrl, coef, plan=None, out=None, scratch=None, status=
         out = torch.empty((n, h, w, 4), dtype=torch.float32, device=fg.device)
     if status is None:
         status = N.new_status(fg.device)
-    scratch = _fused_scratch(lib, n, plan, scratch, fg.device) if (_variant[0] or Np > 64) else scratch
+    scratch = _fused_scratch(lib, n, plan, scratch, fg.device) if (_variant[0] == 1 or Np > 64) else scratch
     N.check(lib.vm_tps_composite_bgra(N.ptr(fg), N.ptr(bg), bg.shape[0], N.ptr(ctrl), N.ptr(coef), Np, plan.nx,
                                       plan.ny, plan.step_x, plan.step_y, N.ptr(plan.rows), N.ptr(plan.cols),
                                       n, h, w, N.ptr(out), N.ptr(scratch), N.ptr(status), N.stream_ptr()))
@@ -357,7 +367,7 @@ def flow_tps_composite(fg, backward, forward, bg, ctrl, coef, plan=None, out=Non
         out = torch.empty((n, h, w, 4), dtype=torch.float32, device=fg.device)
     if status is None:
         status = N.new_status(fg.device)
-    scratch = _fused_scratch(lib, n, plan, scratch, fg.device) if (_variant[0] or Np > 64) else scratch
+    scratch = _fused_scratch(lib, n, plan, scratch, fg.device)
     N.check(lib.vm_flow_tps_composite_bgra(N.ptr(fg), N.ptr(backward), N.ptr(forward), N.ptr(bg), bg.shape[0],
                                            N.ptr(ctrl), N.ptr(coef), Np, plan.nx, plan.ny, plan.step_x,
                                            plan.step_y, N.ptr(plan.rows), N.ptr(plan.cols), n, h, w, N.ptr(out),
@@ -369,8 +379,9 @@ _variant = [0]
 
 
 def set_fused_variant(v):
-    """0 = shared-memory tiled kernel (default), 1 = per-pixel gather kernel (kept as an
-    independent implementation for differential tests)."""
+    """0 = split pipeline (default: flow stage + TPS stage per L2-sized chunk of frames),
+    1 = per-pixel gather kernels, 2 = single shared-memory tiled kernel.  The non-default
+    variants are kept as independent implementations for differential tests."""
     N.set_option("fused_variant", int(v))
     _variant[0] = int(v)
 
