@@ -271,10 +271,10 @@ def test_augment_golden(vm, golden):
 
 # ------------------------------------------------------------------------- fused C3 / C4
 
-VARIANTS = [(0, 32), (2, 64), (2, 32), (1, 32)]   # (fused_variant, tile_h): split, tiled 64, tiled 32, gather
+VARIANTS = [(3, 32), (0, 32), (2, 64), (2, 32), (1, 32)]   # (fused_variant, tile_h): pipe, split, tiled 64, tiled 32, gather
 
 
-@pytest.fixture(params=VARIANTS, ids=["split", "tiled64", "tiled32", "gather"])
+@pytest.fixture(params=VARIANTS, ids=["pipe", "split", "tiled64", "tiled32", "gather"])
 def variant(request, vm):
     v, th = request.param
     vm.pipeline.set_fused_variant(v)

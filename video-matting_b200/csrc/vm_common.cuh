@@ -8,6 +8,7 @@
 #include "../../include/vm_b200.h"
 
 void vm_set_error(const char *fmt, ...);
+extern int g_vp_lead, g_vp_ring_rows, g_vp_cring_rows, g_vp_blocks, g_vp_roles;   // pipeline tuning (vm_pipe.cu)
 int  vm_check_launch(const char *what);
 
 #define VM_REQUIRE(cond, msg)                                   \
@@ -311,3 +312,35 @@ __device__ __forceinline__ void vm_alpha_decode(uint32_t code, float &a, float &
     a = big ? t : s;
     na = big ? s : t;
 }
+
+// source pixel of the TPS resampling evaluated from the original inputs (exact per-pixel path):
+// FLOW: the flow-warped, consistency-masked pixel; otherwise the BGRA pixel itself.
+struct VmSrcPx { double b, g, r, a; };
+
+template <bool FLOW>
+__device__ __forceinline__ VmSrcPx vm_src_px(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd,
+                                             const float2 *__restrict__ fwd, int H, int W, int qi, int qj,
+                                             int &flags) {
+    VmSrcPx o;
+    if (FLOW) {
+        const float2 fb = __ldg(bwd + (int64_t)qi * W + qj);
+        const VmWarped wv = vm_flow_warp_bgra(fg, H, W, qi, qj, fb);
+        const int m = fwd ? vm_consistency(fwd, H, W, qi, qj, fb, flags) : 0;
+        o.b = (double)(wv.bgr & 255u); o.g = (double)((wv.bgr >> 8) & 255u); o.r = (double)((wv.bgr >> 16) & 255u);
+        o.a = m ? 0.0 : (double)wv.ta / VM_ALPHA_DEN;
+    } else {
+        const uint32_t s = vm_ldg_bgra(fg, (int64_t)qi * W + qj);
+        o.b = (double)(s & 255u); o.g = (double)((s >> 8) & 255u); o.r = (double)((s >> 16) & 255u);
+        o.a = (double)(s >> 24) / 255.0;                       // reader.py:16
+    }
+    return o;
+}
+
+__device__ __forceinline__ vm_axis_entry vm_ld_axis(const vm_axis_entry *p) {
+    const int4 v = __ldg(reinterpret_cast<const int4 *>(p));
+    vm_axis_entry e;
+    e.frac = __hiloint2double(v.y, v.x);
+    e.i0 = v.z; e.i1 = v.w;
+    return e;
+}
+

@@ -136,14 +136,6 @@ __device__ __forceinline__ void vm_tps_fine(const double *__restrict__ coarse, i
     t1 = vm_upsample_exact(__ldg(T1 + o00), __ldg(T1 + o01), __ldg(T1 + o10), __ldg(T1 + o11), re.frac, ce.frac);
 }
 
-__device__ __forceinline__ vm_axis_entry vm_ld_axis(const vm_axis_entry *p) {
-    const int4 v = __ldg(reinterpret_cast<const int4 *>(p));
-    vm_axis_entry e;
-    e.frac = __hiloint2double(v.y, v.x);
-    e.i0 = v.z; e.i1 = v.w;
-    return e;
-}
-
 __global__ void __launch_bounds__(256)
 k_tps_upsample(const double *__restrict__ coarse, int nx, int ny, const vm_axis_entry *__restrict__ rows,
                const vm_axis_entry *__restrict__ cols, int h, int w, double *__restrict__ out) {
@@ -267,27 +259,6 @@ extern "C" int vm_map_coordinates(const void *src, int dtype, int channels, int 
 // consistency-masked frame evaluated on the fly at the 4 integer neighbours (C4): each
 // neighbour is {B,G,R uint8 bit-exact, alpha = TA/261120}.  Output float4 {B,G,R,alpha'}.
 // ---------------------------------------------------------------------------------------
-struct VmSrcPx { double b, g, r, a; };
-
-template <bool FLOW>
-__device__ __forceinline__ VmSrcPx vm_src_px(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd,
-                                             const float2 *__restrict__ fwd, int H, int W, int qi, int qj,
-                                             int &flags) {
-    VmSrcPx o;
-    if (FLOW) {
-        const float2 fb = __ldg(bwd + (int64_t)qi * W + qj);
-        const VmWarped wv = vm_flow_warp_bgra(fg, H, W, qi, qj, fb);
-        const int m = fwd ? vm_consistency(fwd, H, W, qi, qj, fb, flags) : 0;
-        o.b = (double)(wv.bgr & 255u); o.g = (double)((wv.bgr >> 8) & 255u); o.r = (double)((wv.bgr >> 16) & 255u);
-        o.a = m ? 0.0 : (double)wv.ta / VM_ALPHA_DEN;
-    } else {
-        const uint32_t s = vm_ldg_bgra(fg, (int64_t)qi * W + qj);
-        o.b = (double)(s & 255u); o.g = (double)((s >> 8) & 255u); o.r = (double)((s >> 16) & 255u);
-        o.a = (double)(s >> 24) / 255.0;                       // reader.py:16
-    }
-    return o;
-}
-
 template <bool FLOW>
 __global__ void __launch_bounds__(256)
 k_tps_composite(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd, const float2 *__restrict__ fwd,
@@ -897,6 +868,11 @@ extern "C" int vm_set_option(const char *key, int value) {
     if (!strcmp(key, "fused_variant")) { g_opt_variant = value; return VM_OK; }
     if (!strcmp(key, "tile_h") && (value == 32 || value == 64)) { g_opt_tile_h = value; return VM_OK; }
     if (!strcmp(key, "chunk_frames") && value >= 1 && value <= 4096) { g_opt_chunk = value; return VM_OK; }
+    if (!strcmp(key, "pipe_lead") && value >= 1 && value <= 4096) { g_vp_lead = value; return VM_OK; }
+    if (!strcmp(key, "pipe_ring_rows") && value >= 16) { g_vp_ring_rows = value; return VM_OK; }
+    if (!strcmp(key, "pipe_cring_rows") && value >= 16) { g_vp_cring_rows = value; return VM_OK; }
+    if (!strcmp(key, "pipe_blocks") && value >= 0) { g_vp_blocks = value; return VM_OK; }
+    if (!strcmp(key, "pipe_roles") && value >= 1 && value <= 7) { g_vp_roles = value; return VM_OK; }
     vm_set_error("vm_set_option: unknown option %s=%d", key, value);
     return VM_ERR_ARG;
 }
@@ -920,6 +896,11 @@ static int launch_tiled(const uint8_t *fg, const float *backward, const float *f
 
 int vm_launch_flow_stage(const uint8_t *fg, const float *backward, const float *forward, int n, int h, int w,
                          void *packed, int32_t *status, cudaStream_t st);          // vm_flow.cu
+int64_t vm_pipe_scratch_bytes(int n, int h, int w);                                // vm_pipe.cu
+int vm_pipe_launch(int mode, const uint8_t *fg, const float *backward, const float *forward, const uint8_t *bg,
+                   int n_bg, const double *ctrl, const double *coef, int N, int nx, int ny, double step_x,
+                   double step_y, const vm_axis_entry *rows, const vm_axis_entry *cols, int n, int h, int w,
+                   float *out, void *scratch, int32_t *status, cudaStream_t st, const char *what);
 
 template <bool PACKED, int TH>
 static int launch_gather2(const void *src, const uint8_t *bg, int n_bg, int frame0, const double *ctrl,
@@ -950,7 +931,10 @@ static int launch_fused(bool flow, const uint8_t *fg, const float *backward, con
     VM_REQUIRE(h <= 32767 && w <= 32767 && (int64_t)h * w < (1ll << 28), "frame too large");
     cudaStream_t st = (cudaStream_t)stream;
     const bool small_n = N <= TT_MAX_N && h >= 2 && w >= 2;
-    if (g_opt_variant == 0 && small_n) {
+    if (g_opt_variant == 3 && small_n && nx == h / 2 && ny == w / 2)
+        return vm_pipe_launch(flow ? (forward ? 2 : 1) : 0, fg, backward, forward, bg, n_bg, ctrl, coef, N, nx, ny,
+                              step_x, step_y, rows, cols, n, h, w, out, scratch, status, st, what);
+    if ((g_opt_variant == 0 || g_opt_variant == 3) && small_n) {
         // split pipeline: stage A (flow warp + mask -> packed intermediate, L2 resident) and stage B
         // (TPS + composite) per chunk of frames; C3 has no stage A.
         if (!flow)
@@ -996,7 +980,8 @@ extern "C" int64_t vm_fused_scratch_bytes(int n, int h, int w) {
     const int64_t a = (int64_t)(n < g_opt_chunk ? n : g_opt_chunk) * h * w * 8;
     const int64_t b = (int64_t)n * 2 * (h / 2) * (w / 2) * (int64_t)sizeof(double);
     (void)fused_scratch_bytes;
-    return a > b ? a : b;
+    const int64_t c = vm_pipe_scratch_bytes(n, h, w);
+    return (a > b ? a : b) > c ? (a > b ? a : b) : c;
 }
 
 extern "C" int vm_tps_composite_bgra(const uint8_t *fg, const uint8_t *bg, int n_bg, const double *ctrl,

@@ -345,7 +345,7 @@ def tps_composite(fg, bg, ctrl, coef, plan=None, out=None, scratch=None, status=
         out = torch.empty((n, h, w, 4), dtype=torch.float32, device=fg.device)
     if status is None:
         status = N.new_status(fg.device)
-    scratch = _fused_scratch(lib, n, plan, scratch, fg.device) if (_variant[0] == 1 or Np > 64) else scratch
+    scratch = _fused_scratch(lib, n, plan, scratch, fg.device)
     N.check(lib.vm_tps_composite_bgra(N.ptr(fg), N.ptr(bg), bg.shape[0], N.ptr(ctrl), N.ptr(coef), Np, plan.nx,
                                       plan.ny, plan.step_x, plan.step_y, N.ptr(plan.rows), N.ptr(plan.cols),
                                       n, h, w, N.ptr(out), N.ptr(scratch), N.ptr(status), N.stream_ptr()))
