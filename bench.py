@@ -23,6 +23,10 @@ sys.path.insert(0, ROOT)
 
 H, W, CLIP, NCTRL = 1080, 1920, 64, 5
 BYTES_PER_PX = {"c4": 39, "c2": 27}
+# dram__bytes_read.sum + dram__bytes_write.sum of the four kernels of one 64-frame launch, from the ncu
+# --set full capture summarised in profiles/ (None until measured for the current kernels)
+TRAFFIC_PER_LAUNCH = None
+TRAFFIC_SOURCE = "profiles/r01_lean_traffic.txt"
 METRIC = "1080p frames/s (warp+TPS+composite)"
 WORKLOAD = ("C4 1080p: flow warp + fwd/bwd occlusion mask + TPS (25 control points, fresh grid per frame) "
             "+ composite, BGRA uint8 in, float32x4 out, clip of 64 frames per GPU per step")
@@ -160,6 +164,19 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step(False)
+    # per-stage durations of one (untimed) step, CUDA events recorded inside the library on the launch stream
+    import ctypes
+    vm._native.set_option("lean_timing", 1)
+    stage_ms = []
+    for _ in range(3):
+        step(False)
+        torch.cuda.synchronize()
+        buf = (ctypes.c_float * 4)()
+        vm._native.check(lib.vm_lean_stage_ms(ctypes.cast(buf, ctypes.c_void_p)))
+        stage_ms.append(list(buf))
+    vm._native.set_option("lean_timing", 0)
+    stage_ms = [statistics.median(col) for col in zip(*stage_ms)]
+    launches0 = lib.vm_lean_launch_count()
     sampler = ClockSampler(str(torch.cuda.get_device_properties(local).uuid)) if rank == 0 else None
     barrier()
     if sampler:
@@ -170,7 +187,7 @@ def run_ours(args):
         step(True)
     t1.record()
     barrier()
-    clocks = sampler.stop() if sampler else None
+    launches = int(lib.vm_lean_launch_count() - launches0)
     ms = t0.elapsed_time(t1)
     tms = torch.tensor([ms], device=dev)
     if dist is not None:
@@ -192,6 +209,7 @@ def run_ours(args):
         P.flow_tps_composite_host(host[0], host[1], host[2], bg_h, grids, out=out_h)
     barrier()
     e2e_s = time.perf_counter() - w0
+    clocks = sampler.stop() if sampler else None     # sampled over the device-timed steps and the end-to-end steps
     te = torch.tensor([e2e_s], device=dev)
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -208,6 +226,13 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     alg = BYTES_PER_PX["c4"] * H * W * CLIP
     ach = alg / (k_ms / 1e3) / 1e9
+    names = ["k_lean_coarse<25> (TPS on the coarse grid, float64)", "k_lean_boxes<1> (source box per tile)",
+             "k_flow_warp_mask_bgra<1,2> (flow warp + consistency mask)", "k_lean_fine<1,4> (resampling + composite)"]
+    # algorithmic bytes each stage moves per pixel (SURVEY 8d layouts; intermediates are not algorithmic)
+    stage_bpp = [0, 0, 8 + 8 + 4, 3 + 16]
+    stages = [{"kernel": nm, "ms": ms_k, "share_of_step": ms_k / sum(stage_ms),
+               "algorithmic_GBps": (bpp * H * W * CLIP / (ms_k / 1e3) / 1e9) if bpp else None}
+              for nm, ms_k, bpp in zip(names, stage_ms, stage_bpp)]
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -215,16 +240,20 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "height": H, "width": W, "frames_per_step_per_gpu": CLIP,
                    "control_points": NCTRL * NCTRL, "sharding": f"clip-sharded replicas x{world}, no collective",
                    "l2": "inputs+outputs 4.8 GB per step >> 126 MB L2 (no flush needed)"},
-        "roofline": {"bound": "hbm", "kernel": "k_tps_tiled<FLOW=true,TH=64> (vm_flow_tps_composite_bgra)",
-                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        "roofline": {"bound": "hbm",
+                     "kernel": "vm_flow_tps_composite_bgra = k_lean_coarse + k_lean_boxes + k_flow_warp_mask_bgra + "
+                               "k_lean_fine, timed as one unit (39 B/px is defined for the whole pipeline); the "
+                               "dominant kernel is k_lean_fine, see stages",
+                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": TRAFFIC_PER_LAUNCH,
+                     "traffic_source": TRAFFIC_SOURCE,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms,
-                     "step_frac": alg / ((ms_total / args.steps) / 1e3) / 1e9 / peak},
+                     "step_frac": alg / ((ms_total / args.steps) / 1e3) / 1e9 / peak, "stages": stages},
         "e2e": e2e, "e2e_matches_device_path": same,
-        "gpu_launches": args.steps, "clocks": clocks,
+        "gpu_launches": launches, "clocks": clocks,
         "status_words": [int(v) for v in status.cpu()],
     }
     if world == 1:
-        line["cpu_baseline"] = cpu_baseline(O, frames=2)
+        line["cpu_baseline"] = cpu_baseline(O, frames=4)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -261,17 +290,24 @@ def run_reference(args):
     workers = max(1, min(cores, 32))
     ctx = mp.get_context("spawn")
     times = []
+    # bounded sample: every step is `workers` frames (one per process); at most ~150 s of wall clock in total
+    budget_s, t_start = 150.0, time.perf_counter()
+    warm = min(args.warmup, 1)
     with ctx.Pool(workers) as pool:
-        for s in range(args.warmup + args.steps):
+        for s in range(warm + args.steps):
             t = time.perf_counter()
             pool.map(_cpu_frame, [1000 * s + k for k in range(workers)])
-            if s >= args.warmup:
-                times.append(time.perf_counter() - t)
+            dt = time.perf_counter() - t
+            if s >= warm:
+                times.append(dt)
+            if times and time.perf_counter() - t_start + dt > budget_s:
+                break
     total = sum(times)
-    value = workers * args.steps / total
+    steps_run = len(times)
+    value = workers * steps_run / total
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s",
-            "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": steps_run, "steps_requested": args.steps,
+            "warmup": warm, "ms_per_step": 1e3 * total / steps_run, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 in / f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "height": H, "width": W, "frames_per_step": workers},
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": workers, "kind": "port",
@@ -285,7 +321,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

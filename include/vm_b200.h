@@ -174,10 +174,20 @@ int vm_flow_tps_composite_bgra(const uint8_t *fg, const float *backward, const f
                                int n, int h, int w, float *out, void *scratch,
                                int32_t *status, void *stream);
 
-/* Tuning / test switches: "fused_variant" 0 = split pipeline (default), 1 = per-pixel gather
- * kernel, 2 = single shared-memory tiled kernel; "tile_h" 32 or 64 (rows per tile of variant
- * 2); "chunk_frames" frames per stage-A/stage-B pair of variant 0.                          */
+/* Tuning / test switches: "fused_variant" 4 = lean split pipeline (default: flow stage, float64
+ * spline stage, TMA-tiled resampling stage), 0 = first split pipeline, 1 = per-pixel gather
+ * kernel, 2 = single shared-memory tiled kernel, 3 = persistent role-specialised kernel;
+ * "tile_h" 32 or 64 (rows per tile of variant 2); "chunk_frames" frames per stage pair of
+ * variant 0; "lean_chunk" frames per stage round of variant 4; "lean_timing" 1 = record CUDA
+ * events around the stages of variant 4 (read back with vm_lean_stage_ms).                   */
 int vm_set_option(const char *key, int value);
+
+/* Measurement hooks of the default fused path (no reference counterpart; used by bench.py).
+ * vm_lean_stage_ms: durations in ms of {spline, tile boxes, flow stage, resampling+composite}
+ * of the first chunk of the last call made with "lean_timing" = 1 on the current device, after
+ * the stream was synchronised.  vm_lean_launch_count: kernels launched so far by that path.  */
+int       vm_lean_stage_ms(float *out4);
+long long vm_lean_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -24,6 +24,9 @@ if os.environ.get("VM_VARIANT"):
 for key in ("pipe_lead", "pipe_ring_rows", "pipe_cring_rows", "pipe_blocks", "pipe_roles", "chunk_frames"):
     if os.environ.get("VM_" + key.upper()):
         vm._native.set_option(key, int(os.environ["VM_" + key.upper()]))
+for kv in filter(None, os.environ.get("VM_OPTS", "").split(",")):
+    k, v = kv.split("=")
+    vm._native.set_option(k, int(v))
 if os.environ.get("VM_TILE_H"):
     vm._native.set_option("tile_h", int(os.environ["VM_TILE_H"]))
 dev = torch.device("cuda", 0)

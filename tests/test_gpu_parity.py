@@ -271,16 +271,16 @@ def test_augment_golden(vm, golden):
 
 # ------------------------------------------------------------------------- fused C3 / C4
 
-VARIANTS = [(3, 32), (0, 32), (2, 64), (2, 32), (1, 32)]   # (fused_variant, tile_h): pipe, split, tiled 64, tiled 32, gather
+VARIANTS = [(4, 32), (3, 32), (0, 32), (2, 64), (2, 32), (1, 32)]   # (fused_variant, tile_h): lean, pipe, split, tiled 64, tiled 32, gather
 
 
-@pytest.fixture(params=VARIANTS, ids=["pipe", "split", "tiled64", "tiled32", "gather"])
+@pytest.fixture(params=VARIANTS, ids=["lean", "pipe", "split", "tiled64", "tiled32", "gather"])
 def variant(request, vm):
     v, th = request.param
     vm.pipeline.set_fused_variant(v)
     vm._native.set_option("tile_h", th)
     yield request.param
-    vm.pipeline.set_fused_variant(0)
+    vm.pipeline.set_fused_variant(4)
     vm._native.set_option("tile_h", 32)
 
 
@@ -337,7 +337,7 @@ def test_fused_degenerate_grid_takes_gather_path(vm):
     try:
         out, st = P.flow_tps_composite(dev(frame[None]), dev(fb[None]), dev(ff[None]), dev(bg[None]), ctrl, coef)
     finally:
-        P.set_fused_variant(0)
+        P.set_fused_variant(4)
     rc, ra = O.pipeline_c4(frame, fb, ff, (grid, dgrid), bg)
     got = out[0].cpu().numpy()
     assert close(got[..., 3], ra, 1e-6)

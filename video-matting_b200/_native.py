@@ -40,6 +40,8 @@ SIGNATURES = {
     "vm_tps_composite_bgra": [_P, _P, _I, _P, _P, _I, _I, _I, _D, _D, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "vm_flow_tps_composite_bgra": [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _D, _D, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "vm_set_option": [_c.c_char_p, _I],
+    "vm_lean_stage_ms": [_P],
+    "vm_lean_launch_count": [],
 }
 
 _lib = None
@@ -73,6 +75,7 @@ def load(build_if_missing=True):
         fn.restype = _c.c_int
     lib.vm_last_error_string.restype = _c.c_char_p
     lib.vm_fused_scratch_bytes.restype = _c.c_int64
+    lib.vm_lean_launch_count.restype = _c.c_longlong
     _lib = lib
     return lib
 

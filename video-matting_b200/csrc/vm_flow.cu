@@ -157,10 +157,16 @@ __device__ __forceinline__ float vm_alpha_f32(uint32_t ta) {
     return (ta > nta) ? 1.f - s : s;
 }
 
-// PACKED = false: out_bgr (n,h,w,3) uint8 + out_alpha (n,h,w) float32 (the C2 result);
-// PACKED = true : out_bgr is a (n,h,w) uint2 array {B|G<<8|R<<16, alpha code} - the stage-A
-// intermediate of the split C4 pipeline (see vm_tps.cu), out_alpha unused.
-template <bool HAS_FWD, bool PACKED>
+// PACKED = 0: out_bgr (n,h,w,3) uint8 + out_alpha (n,h,w) float32 (the C2 result);
+// PACKED = 1: out_bgr is a (n,h,w) uint2 array {B|G<<8|R<<16, alpha code} - the stage-A
+//             intermediate of the split C4 pipeline (see vm_tps.cu), out_alpha unused;
+// PACKED = 2: same, with the raw alpha numerator {B|G<<8|R<<16, TA} (TA = 0 where masked) -
+//             the intermediate of the lean pipeline (vm_lean.cu), alpha = TA / 261120.
+template <int PACKED> __device__ __forceinline__ uint32_t vm_pack_alpha(const VmFlowPx &px) {
+    return px.masked ? 0u : (PACKED == 2 ? px.ta : vm_alpha_code(px.ta));
+}
+
+template <bool HAS_FWD, int PACKED>
 __global__ void __launch_bounds__(256, 6)
 k_flow_warp_mask_bgra(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd,
                       const float2 *__restrict__ fwd, int h, int w, int tiles_x, int tiles_y,
@@ -178,8 +184,8 @@ k_flow_warp_mask_bgra(const uint8_t *__restrict__ fg, const float2 *__restrict__
     const float fi = (float)i, fj = (float)j;
     int flags = 0;
     if (j + 3 < w && (w & 3) == 0) {
-        const float4 f01 = __ldg(reinterpret_cast<const float4 *>(bf + p));
-        const float4 f23 = __ldg(reinterpret_cast<const float4 *>(bf + p + 2));
+        const float4 f01 = __ldcs(reinterpret_cast<const float4 *>(bf + p));      // streamed once: evict first
+        const float4 f23 = __ldcs(reinterpret_cast<const float4 *>(bf + p + 2));
         const float2 fl[4] = {{f01.x, f01.y}, {f01.z, f01.w}, {f23.x, f23.y}, {f23.z, f23.w}};
         VmFlowPx px[4];
 #pragma unroll
@@ -187,10 +193,8 @@ k_flow_warp_mask_bgra(const uint8_t *__restrict__ fg, const float2 *__restrict__
             px[k] = vm_flow_px<HAS_FWD>(fg32, ff, h, w, i, j + k, fi, fj + (float)k, fl[k], flags);
         if (PACKED) {
             uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<uint2 *>(out_bgr) + fbase + p);
-            op[0] = make_uint4(px[0].bgr, px[0].masked ? 0u : vm_alpha_code(px[0].ta),
-                               px[1].bgr, px[1].masked ? 0u : vm_alpha_code(px[1].ta));
-            op[1] = make_uint4(px[2].bgr, px[2].masked ? 0u : vm_alpha_code(px[2].ta),
-                               px[3].bgr, px[3].masked ? 0u : vm_alpha_code(px[3].ta));
+            op[0] = make_uint4(px[0].bgr, vm_pack_alpha<PACKED>(px[0]), px[1].bgr, vm_pack_alpha<PACKED>(px[1]));
+            op[1] = make_uint4(px[2].bgr, vm_pack_alpha<PACKED>(px[2]), px[3].bgr, vm_pack_alpha<PACKED>(px[3]));
             goto done;
         }
         float al[4];
@@ -208,7 +212,7 @@ k_flow_warp_mask_bgra(const uint8_t *__restrict__ fg, const float2 *__restrict__
             const float2 f = __ldg(bf + p + k);
             const VmFlowPx px = vm_flow_px<HAS_FWD>(fg32, ff, h, w, i, j + k, fi, fj + (float)k, f, flags);
             if (PACKED) {
-                reinterpret_cast<uint2 *>(out_bgr)[fbase + p + k] = make_uint2(px.bgr, px.masked ? 0u : vm_alpha_code(px.ta));
+                reinterpret_cast<uint2 *>(out_bgr)[fbase + p + k] = make_uint2(px.bgr, vm_pack_alpha<PACKED>(px));
                 continue;
             }
             uint8_t *ob = out_bgr + (fbase + p + k) * 3;
@@ -223,17 +227,17 @@ done:
     }
 }
 
-// stage A of the split C4 pipeline: (n,h,w) uint2 {bgr, alpha code}
+// stage A of the split C4 pipelines: (n,h,w) uint2 {bgr, alpha code} or, raw_ta, {bgr, TA}
 int vm_launch_flow_stage(const uint8_t *fg, const float *backward, const float *forward, int n, int h, int w,
-                         void *packed, int32_t *status, cudaStream_t st) {
+                         void *packed, int32_t *status, cudaStream_t st, bool raw_ta) {
     const int tiles_x = (w + C2_TW - 1) / C2_TW, tiles_y = (h + C2_TH - 1) / C2_TH;
     const dim3 tiles(tiles_x, tiles_y, n);
-    if (forward)
-        k_flow_warp_mask_bgra<true, true><<<tiles, 256, 0, st>>>(fg, (const float2 *)backward, (const float2 *)forward, h, w,
-                                                                 tiles_x, tiles_y, (uint8_t *)packed, nullptr, status);
-    else
-        k_flow_warp_mask_bgra<false, true><<<tiles, 256, 0, st>>>(fg, (const float2 *)backward, nullptr, h, w, tiles_x,
-                                                                  tiles_y, (uint8_t *)packed, nullptr, status);
+    const float2 *b2 = (const float2 *)backward, *f2 = (const float2 *)forward;
+    uint8_t *o = (uint8_t *)packed;
+    if (forward && raw_ta) k_flow_warp_mask_bgra<true, 2><<<tiles, 256, 0, st>>>(fg, b2, f2, h, w, tiles_x, tiles_y, o, nullptr, status);
+    else if (forward)      k_flow_warp_mask_bgra<true, 1><<<tiles, 256, 0, st>>>(fg, b2, f2, h, w, tiles_x, tiles_y, o, nullptr, status);
+    else if (raw_ta)       k_flow_warp_mask_bgra<false, 2><<<tiles, 256, 0, st>>>(fg, b2, nullptr, h, w, tiles_x, tiles_y, o, nullptr, status);
+    else                   k_flow_warp_mask_bgra<false, 1><<<tiles, 256, 0, st>>>(fg, b2, nullptr, h, w, tiles_x, tiles_y, o, nullptr, status);
     return vm_check_launch("vm_flow_stage");
 }
 
@@ -248,10 +252,10 @@ extern "C" int vm_flow_warp_mask_bgra(const uint8_t *fg, const float *backward, 
     const dim3 tiles(tiles_x, tiles_y, n);
     cudaStream_t st = (cudaStream_t)stream;
     if (forward)
-        k_flow_warp_mask_bgra<true, false><<<tiles, 256, 0, st>>>(
+        k_flow_warp_mask_bgra<true, 0><<<tiles, 256, 0, st>>>(
             fg, (const float2 *)backward, (const float2 *)forward, h, w, tiles_x, tiles_y, out_bgr, out_alpha, status);
     else
-        k_flow_warp_mask_bgra<false, false><<<tiles, 256, 0, st>>>(
+        k_flow_warp_mask_bgra<false, 0><<<tiles, 256, 0, st>>>(
             fg, (const float2 *)backward, nullptr, h, w, tiles_x, tiles_y, out_bgr, out_alpha, status);
     return vm_check_launch("vm_flow_warp_mask_bgra");
 }

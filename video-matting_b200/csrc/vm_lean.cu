@@ -1,0 +1,948 @@
+// Lean split pipeline for the fused C3 / C4 entry points (fused_variant 4, the default).
+//
+// Per chunk of frames (sized so that the two intermediates stay in the 126 MB L2):
+//
+//   stage A   k_flow_warp_mask_bgra<.., 2> (vm_flow.cu)   flow warp + consistency mask
+//             -> packed (n,h,w) uint2 {B|G<<8|R<<16, TA}, alpha = TA / 261120     [C4 only]
+//   stage B1  k_lean_coarse   thin-plate spline on the coarse grid (tps.py:101-123), float64,
+//             -> T (n,nx,ny) double2 {row coordinate, column coordinate}
+//   stage B2  k_lean_fine     bilinear up-sampling of T (tps.py:55-74), map_coordinates
+//             (tps.py:34) on the packed intermediate / the BGRA frame, composite (reader.py:72-79)
+//             -> out (n,h,w) float4 {B, G, R, alpha'}
+//
+// B1 is bound by the float64 pipe: 9 DP instructions per (coarse point, control point) - the
+// log comes from a 31-octave x 256-entry {1/c, log c} table staged in shared memory by a bulk
+// async copy (TMA, 127 KB per persistent CTA) plus a degree-3 minimax polynomial.  B2 is bound
+// by instruction issue: coordinates are the only float64 work (6 DP per pixel thanks to
+// rolling column-interpolated coarse rows); weights, colour blending and alpha are integer
+// fixed point (2^-30 weights), with an exact float64 re-evaluation of the rare samples whose
+// rounding the fixed-point value cannot decide.
+#include "vm_common.cuh"
+#include <math.h>
+#include <string.h>
+#include <mutex>
+
+int vm_launch_flow_stage(const uint8_t *fg, const float *backward, const float *forward, int n, int h, int w,
+                         void *packed, int32_t *status, cudaStream_t st, bool raw_ta);     // vm_flow.cu
+
+int g_vl_chunk = 64;         // frames per A/B1/B2 round
+int g_vl_overlap = 0;        // run B1 on a side stream next to stage A
+int g_vl_rb = 0;             // coarse rows per B1 unit (0 = pick on the host)
+int g_vl_fine_rows = 8;      // fine rows per B2 thread
+int g_vl_timing = 0;         // 1: bracket the stages of the first chunk of every call with CUDA events (vm_lean_stage_ms)
+static cudaEvent_t g_vl_tev[64][5];
+static bool g_vl_tev_ok[64];
+static long long g_vl_launches = 0;   // kernels launched by this library's lean path (bench.py "gpu_launches")
+int g_vl_box_cap = 0;        // source-box entries per B2 tile (0: as many as the occupancy target allows)
+int g_vl_minb = 4;           // B2 occupancy target (CTAs of 256 threads per SM: 2, 3 or 4)
+
+// ---------------------------------------------------------------------------------------
+// log table: value x = 2^e * m, e in [VL_EMIN, VL_EMAX), m in [1 + k/2^B, 1 + (k+1)/2^B), B = VL_BITS;
+// entry (e,k) = {RN(1/c_k) * 2^-e, e ln2 - log(RN(1/c_k))}, c_k = 1 + (k + 1/2)/2^B.
+// t = fma(x, entry.x, -1) has |t| <= 2^-(VL_BITS+1);  log x = entry.y + t * q(t).
+// ---------------------------------------------------------------------------------------
+#define VL_EMIN (-6)
+#define VL_EMAX 25
+#define VL_BITS 5
+#define VL_TAB_N ((VL_EMAX - VL_EMIN) << VL_BITS)
+#define VL_TAB_BYTES (VL_TAB_N * 16)
+#define VL_HI_MIN ((1023 + VL_EMIN) << 20)
+#define VL_HI_MAX ((1023 + VL_EMAX) << 20)
+
+// minimax fit of log1p(t)/t on |t| <= 2^-6 (max error of t*q(t): 1.03e-15 absolute).  32 entries per
+// octave keep the table index of neighbouring coarse columns within one entry of each other for every
+// control point further than ~190 px away, so a quarter-warp reads consecutive entries: no bank conflicts.
+#define VL_Q5 (-0.1667124531815725708429)
+#define VL_Q4 0.2000523271261866307
+#define VL_Q3 (-0.2499999958078498099121)
+#define VL_Q2 0.3333333285423420934598
+#define VL_Q1 (-0.5000000000000568604014)
+#define VL_Q0 1.000000000000064982787
+
+__device__ double2 g_vl_tab[VL_TAB_N];
+
+static std::mutex g_vl_mu;
+static bool g_vl_done[64];
+static cudaStream_t g_vl_side[64];
+static cudaEvent_t g_vl_ev_fork[64], g_vl_ev_ready[64][2], g_vl_ev_free[64][2];
+
+static int vl_init(int *dev_out) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        vm_set_error("vm_lean: cudaGetDevice failed");
+        return VM_ERR_CUDA;
+    }
+    *dev_out = dev;
+    std::lock_guard<std::mutex> lk(g_vl_mu);
+    if (g_vl_done[dev]) return VM_OK;
+    static double2 tab[VL_TAB_N];
+    for (int e = VL_EMIN; e < VL_EMAX; ++e)
+        for (int k = 0; k < (1 << VL_BITS); ++k) {
+            const long double c = 1.0L + ((long double)k + 0.5L) / (long double)(1 << VL_BITS);
+            const double inv = (double)(1.0L / c);
+            double2 &t = tab[((e - VL_EMIN) << VL_BITS) + k];
+            t.x = ldexp(inv, -e);
+            t.y = (double)((long double)e * 0.693147180559945309417232121458L - logl((long double)inv));
+        }
+    cudaError_t err = cudaMemcpyToSymbol(g_vl_tab, tab, sizeof(tab));
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&g_vl_side[dev], cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&g_vl_ev_fork[dev], cudaEventDisableTiming);
+    for (int k = 0; k < 2 && err == cudaSuccess; ++k) {
+        err = cudaEventCreateWithFlags(&g_vl_ev_ready[dev][k], cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&g_vl_ev_free[dev][k], cudaEventDisableTiming);
+    }
+    if (err != cudaSuccess) {
+        vm_set_error("vm_lean: init: %s", cudaGetErrorString(err));
+        return VM_ERR_CUDA;
+    }
+    g_vl_done[dev] = true;
+    return VM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// stage B1
+// ---------------------------------------------------------------------------------------
+#define VL_B1_WARPS 16
+#define VL_B1_THREADS (VL_B1_WARPS * 32)
+#define VL_B1_WARPS_HI 24
+#define VL_B1_THREADS_HI (VL_B1_WARPS_HI * 32)
+#define VL_MAX_N 64
+#define VL_RG 4                                    // coarse rows evaluated together
+
+struct __align__(16) VlWarpSmem {
+    double2 p[VL_MAX_N];                           // control point {x (row axis), y (column axis)}
+    double2 wv[VL_MAX_N];                          // {w0 / 2, w1 / 2}
+    double4 dx2[VL_MAX_N];                         // (x_r - Px)^2 for the VL_RG rows of the group
+    double aff[8];
+};
+
+struct __align__(16) VlCoarseSmem {
+    double2 tab[VL_TAB_N];
+    VlWarpSmem w[VL_B1_WARPS_HI];
+    unsigned long long bar;
+};
+
+__device__ __forceinline__ uint32_t vl_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// r2 * log(r2) through the shared-memory table; r2 must lie in [2^VL_EMIN, 2^VL_EMAX)
+__device__ __forceinline__ double vl_u_fast(double r2, uint32_t tab_adj) {
+    const uint32_t addr = tab_adj + (((uint32_t)__double2hiint(r2) >> (20 - VL_BITS)) << 4);
+    double ex, ey;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ex), "=d"(ey) : "r"(addr));
+    const double t = fma(r2, ex, -1.0);
+    double q = fma(t, VL_Q5, VL_Q4);
+    q = fma(t, q, VL_Q3);
+    q = fma(t, q, VL_Q2);
+    q = fma(t, q, VL_Q1);
+    q = fma(t, q, VL_Q0);
+    return r2 * fma(t, q, ey);
+}
+
+// any r2 >= 0 (tps.py:78-82: U = 0 for r < 1e-100)
+__device__ __noinline__ double vl_u_any(double r2, uint32_t tab_adj) {
+    const int hi = __double2hiint(r2);
+    if (hi >= VL_HI_MIN && hi < VL_HI_MAX) return vl_u_fast(r2, tab_adj);
+    if (r2 >= 1e-200) return r2 * log(r2);
+    return (r2 == r2) ? 0.0 : r2;
+}
+
+// N > 0: number of control points known at compile time; 0: run-time count.
+// DYR: (y - Py)^2 of every control point held in registers (16 warps per SM at 128 registers);
+// otherwise it is recomputed per row group and the kernel runs 24 warps per SM.
+template <int N, bool DYR>
+__global__ void __launch_bounds__(DYR ? VL_B1_THREADS : VL_B1_THREADS_HI, 1)
+k_lean_coarse(const double *__restrict__ ctrl, const double *__restrict__ coef, int n_rt, int n_frames, int nx, int ny,
+              double step_x, double step_y, int rb, int nbands, int ncb, double2 *__restrict__ T,
+              unsigned int *__restrict__ next_unit) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    VlCoarseSmem &S = *reinterpret_cast<VlCoarseSmem *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NC = N > 0 ? N : n_rt;
+
+    // log table -> shared memory with one bulk async copy per 16 KB piece, all on one mbarrier
+    const uint32_t bar = vl_smem_u32(&S.bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)VL_TAB_BYTES) : "memory");
+        constexpr int PIECE = VL_TAB_BYTES / 8;
+        static_assert(VL_TAB_BYTES % PIECE == 0 && PIECE % 16 == 0, "bulk copy pieces");
+        for (int o = 0; o < VL_TAB_BYTES; o += PIECE)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(vl_smem_u32(reinterpret_cast<unsigned char *>(S.tab) + o)),
+                           "l"(reinterpret_cast<const unsigned char *>(g_vl_tab) + o), "r"((uint32_t)PIECE), "r"(bar)
+                         : "memory");
+    }
+
+    VlWarpSmem &Ws = S.w[warp];
+    const uint32_t tab_adj = vl_smem_u32(S.tab) - (uint32_t)(((1023 + VL_EMIN) << VL_BITS) << 4);
+    const int units_per_frame = nbands * ncb;
+    const int units = n_frames * units_per_frame;
+    int cur_frame = -1;
+    bool tab_ready = false;
+
+    // dynamic unit queue: unit costs differ (table conflicts near control points, generic-path units)
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = (int)atomicAdd(next_unit, 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= units) break;
+        const int frame = u / units_per_frame;
+        const int rem = u - frame * units_per_frame;
+        const int band = rem / ncb, cb = rem - band * ncb;
+        const int k0 = band * rb, kend = min(k0 + rb, nx) - 1;        // rows of the unit
+        const int l0 = cb * 32, lend = min(l0 + 32, ny) - 1;
+        const int l = min(l0 + lane, ny - 1);
+        const double y = (double)l * step_y;
+
+        if (frame != cur_frame) {                                     // warp-uniform
+            __syncwarp();
+            const double *P = ctrl + (int64_t)frame * NC * 2;
+            const double *C = coef + (int64_t)frame * (NC + 3) * 2;
+            for (int a = lane; a < NC; a += 32) {
+                Ws.p[a] = make_double2(P[2 * a], P[2 * a + 1]);
+                Ws.wv[a] = make_double2(0.5 * C[2 * a], 0.5 * C[2 * a + 1]);
+            }
+            if (lane < 6) Ws.aff[lane] = C[(NC + lane % 3) * 2 + lane / 3];
+            cur_frame = frame;
+            __syncwarp();
+        }
+
+        // can every (point, control) pair of the unit use the table?  lane a checks control a
+        bool bad = false;
+        {
+            const double xlo = (double)k0 * step_x, xhi = (double)kend * step_x;
+            const double ylo = (double)l0 * step_y, yhi = (double)lend * step_y;
+            for (int a = lane; a < NC; a += 32) {
+                const double2 p = Ws.p[a];
+                const double kn = fmin(fmax(rint(p.x / step_x), (double)k0), (double)kend);
+                const double ln = fmin(fmax(rint(p.y / step_y), (double)l0), (double)lend);
+                const double dxm = kn * step_x - p.x, dym = ln * step_y - p.y;
+                const double dxM = fmax(fabs(xlo - p.x), fabs(xhi - p.x)), dyM = fmax(fabs(ylo - p.y), fabs(yhi - p.y));
+                const double dmin2 = dxm * dxm + dym * dym, dmax2 = dxM * dxM + dyM * dyM;
+                if (!(dmin2 >= 0.015626) || !(dmax2 < 33550000.0)) bad = true;      // 2^-6 (1 + 6e-5), 2^25 (1 - 1e-4)
+            }
+        }
+        const bool slow = __any_sync(0xffffffffu, bad) || (N == 0);
+
+        if (!tab_ready) {                                             // first unit: wait for the table
+            uint32_t ok = 0;
+            while (!ok)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(ok) : "r"(bar) : "memory");
+            tab_ready = true;
+        }
+
+        if (!slow) {
+            // ---- fast path: dy^2 per control in registers, VL_RG rows per step ----------------
+            constexpr int NF = N > 0 ? N : 1;
+            double dy2[DYR ? NF : 1];
+            if (DYR) {
+#pragma unroll
+                for (int a = 0; a < NF; ++a) {
+                    const double dy = y - Ws.p[a].y;
+                    dy2[a] = dy * dy;
+                }
+            }
+            for (int kg = k0; kg <= kend; kg += VL_RG) {
+                __syncwarp();
+                for (int a = lane; a < NF; a += 32) {
+                    const double px = Ws.p[a].x;
+                    double d[VL_RG];
+#pragma unroll
+                    for (int r = 0; r < VL_RG; ++r) {
+                        const double dx = (double)min(kg + r, kend) * step_x - px;
+                        d[r] = dx * dx;
+                    }
+                    Ws.dx2[a] = make_double4(d[0], d[1], d[2], d[3]);
+                }
+                __syncwarp();
+                double s0[VL_RG], s1[VL_RG];
+#pragma unroll
+                for (int r = 0; r < VL_RG; ++r) { s0[r] = 0.0; s1[r] = 0.0; }
+#pragma unroll
+                for (int a = 0; a < NF; ++a) {
+                    const double2 wv = Ws.wv[a];
+                    const double4 dx2 = Ws.dx2[a];
+                    const double dd[VL_RG] = {dx2.x, dx2.y, dx2.z, dx2.w};
+                    double dy2a;
+                    if (DYR) dy2a = dy2[a];
+                    else { const double dy = y - Ws.p[a].y; dy2a = dy * dy; }
+#pragma unroll
+                    for (int r = 0; r < VL_RG; ++r) {
+                        const double U = vl_u_fast(dd[r] + dy2a, tab_adj);
+                        s0[r] = fma(wv.x, U, s0[r]);
+                        s1[r] = fma(wv.y, U, s1[r]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < VL_RG; ++r) {
+                    const int k = kg + r;
+                    if (k <= kend && l0 + lane < ny) {
+                        const double x = (double)k * step_x;
+                        const double v0 = ((Ws.aff[0] + Ws.aff[1] * x) + Ws.aff[2] * y) + s0[r];
+                        const double v1 = ((Ws.aff[3] + Ws.aff[4] * x) + Ws.aff[5] * y) + s1[r];
+                        T[((int64_t)frame * nx + k) * ny + l] = make_double2(v0, v1);
+                    }
+                }
+            }
+        } else {
+            // ---- generic path: any control count, any distance -------------------------------
+            for (int k = k0; k <= kend; ++k) {
+                const double x = (double)k * step_x;
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll 1
+                for (int a = 0; a < NC; ++a) {
+                    const double2 p = Ws.p[a], wv = Ws.wv[a];
+                    const double dx = x - p.x, dy = y - p.y;
+                    const double U = vl_u_any(dx * dx + dy * dy, tab_adj);   // same roundings as the fast path's dx2 + dy2
+                    s0 = fma(wv.x, U, s0);
+                    s1 = fma(wv.y, U, s1);
+                }
+                if (l0 + lane < ny) {
+                    const double v0 = ((Ws.aff[0] + Ws.aff[1] * x) + Ws.aff[2] * y) + s0;
+                    const double v1 = ((Ws.aff[3] + Ws.aff[4] * x) + Ws.aff[5] * y) + s1;
+                    T[((int64_t)frame * nx + k) * ny + l] = make_double2(v0, v1);
+                }
+            }
+        }
+    }
+    if (!tab_ready && tid == 0) {                                      // never leave a bulk copy in flight
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(bar) : "memory");
+    }
+    __syncthreads();
+}
+
+// rows per unit: minimise (waves of units over the persistent warps) x (rows + set-up cost)
+int g_vl_b1_warps = VL_B1_WARPS;
+int g_vl_b1_dyr = 1;         // 1: dy^2 in registers / <= 16 warps per SM; 0: recomputed / <= 24 warps per SM
+
+static int vl_pick_rb(int n, int nx, int ny, int ctas) {
+    if (g_vl_rb > 0) return (g_vl_rb + VL_RG - 1) / VL_RG * VL_RG;
+    const int ncb = (ny + 31) / 32;
+    const int64_t warps = (int64_t)ctas * g_vl_b1_warps;
+    int best = VL_RG;
+    double best_cost = 1e300;
+    for (int rb = VL_RG; rb <= 32; rb += VL_RG) {
+        const int64_t units = (int64_t)n * ((nx + rb - 1) / rb) * ncb;
+        const double cost = (double)((units + warps - 1) / warps) * (rb + 1.0);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = rb; }
+    }
+    return best;
+}
+
+static int vl_sm_count() {
+    static int sms[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (!sms[dev]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        sms[dev] = v;
+    }
+    return sms[dev];
+}
+
+static int vl_launch_coarse(const double *ctrl, const double *coef, int N, int n, int nx, int ny, double step_x,
+                            double step_y, double2 *T, unsigned int *counter, cudaStream_t st) {
+    if (cudaMemsetAsync(counter, 0, sizeof(unsigned int), st) != cudaSuccess) {
+        vm_set_error("vm_lean: cudaMemsetAsync failed");
+        return VM_ERR_CUDA;
+    }
+    const int ctas = vl_sm_count();
+    const int warps_cta = g_vl_b1_dyr ? (g_vl_b1_warps < VL_B1_WARPS ? g_vl_b1_warps : VL_B1_WARPS) : g_vl_b1_warps;
+    const int rb = vl_pick_rb(n, nx, ny, ctas);
+    const int nbands = (nx + rb - 1) / rb, ncb = (ny + 31) / 32;
+    const size_t smem = sizeof(VlCoarseSmem);
+#define VL_LAUNCH(NN, DY)                                                                                           \
+    do {                                                                                                          \
+        static bool attr_set[64];                                                                                 \
+        int dev = 0;                                                                                              \
+        cudaGetDevice(&dev);                                                                                      \
+        if (!attr_set[dev & 63]) {                                                                                \
+            cudaError_t e = cudaFuncSetAttribute(k_lean_coarse<NN, DY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) { vm_set_error("vm_lean: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VM_ERR_CUDA; } \
+            attr_set[dev & 63] = true;                                                                            \
+        }                                                                                                         \
+        k_lean_coarse<NN, DY><<<ctas, warps_cta * 32, smem, st>>>(ctrl, coef, N, n, nx, ny, step_x, step_y, rb, nbands, ncb, T, counter); \
+    } while (0)
+    if (g_vl_b1_dyr) {
+        switch (N) {
+        case 16: VL_LAUNCH(16, true); break;
+        case 25: VL_LAUNCH(25, true); break;
+        default: VL_LAUNCH(0, true); break;
+        }
+    } else {
+        switch (N) {
+        case 16: VL_LAUNCH(16, false); break;
+        case 25: VL_LAUNCH(25, false); break;
+        default: VL_LAUNCH(0, false); break;
+        }
+    }
+#undef VL_LAUNCH
+    return vm_check_launch("vm_lean coarse stage");
+}
+
+// ---------------------------------------------------------------------------------------
+// stage B2
+//
+// CTA = VL_FW columns x (VL_FS * rpt) rows, thread = one column of one strip of rpt rows.
+//   P0  axis entries of the tile -> registers / shared memory
+//   P1  bulk async copies (TMA): the coarse transform window of the tile and its background rows
+//   P2  bounding box of the window (= bounding box of every fine coordinate: the fine transform
+//       is a convex combination of coarse values) and the column-interpolated coarse rows Cs
+//   P3  bulk async copies: the source rows of the box (packed stage-A pixels or BGRA)
+//   P4  per pixel: row interpolation of Cs (float64), fixed-point weights, integer blend of the
+//       four taps read from shared memory, composite, one 16-byte streaming store
+// Tiles whose box does not fit (strongly stretched grids) gather the taps from global memory;
+// plans whose axis tables are not monotone windows take everything from global memory.
+// ---------------------------------------------------------------------------------------
+#define VL_FW 64                                   // columns per CTA
+#define VL_FS 4                                    // row strips per CTA
+#define VL_FROWS_MAX 32                            // fine rows per CTA (VL_FS * rpt)
+#define VL_TC (VL_FW / 2 + 4)                      // coarse columns staged per CTA (36)
+#define VL_TR (VL_FROWS_MAX / 2 + 4)               // coarse rows staged per CTA (20)
+#define VL_BOX_MAX 5632                            // source-box entries staged per CTA (8 B each)
+#define VL_MAGIC 1572864.0                         // 1.5 * 2^20: ulp = 2^-32, exponent field 0x413
+#define VL_MAGIC_HI 0x41380000
+
+struct __align__(16) VlFineSmem {
+    double2 Cs[VL_TR * VL_FW];                     // coarse rows interpolated at the tile's fine columns
+    unsigned char bgt[VL_FROWS_MAX * VL_FW * 3];
+    vm_axis_entry rows[VL_FROWS_MAX];
+    unsigned long long bar[2];
+    uint2 box[1];                                  // box_cap entries (dynamic): source rows [rmin, rmin + bh) x [cmin, cmin + bw)
+};
+static inline size_t vl_fine_smem_bytes(int box_cap) { return sizeof(VlFineSmem) + (size_t)(box_cap - 1) * sizeof(uint2); }
+
+// per-tile record written by k_lean_boxes: source box of the tile (bw = 0: does not fit / not usable)
+struct __align__(16) VlTileBox { int rmin, bh, cmin, bw; };
+
+struct VlC { double x, y; };                       // column-interpolated coarse row {row coord, column coord}
+
+template <int SRC> struct VlSrc;
+template <> struct VlSrc<0> {                      // BGRA frame: alpha = A / 255
+    typedef uint32_t elem;
+    static constexpr double DEN = 255.0;
+    static __device__ __forceinline__ uint2 ld(const elem *p) { const uint32_t s = __ldg(p); return make_uint2(s, s >> 24); }
+    static __device__ __forceinline__ uint2 lds(const elem *p) { const uint32_t s = *p; return make_uint2(s, s >> 24); }
+};
+template <> struct VlSrc<1> {                      // packed {bgr, TA}: alpha = TA / 261120
+    typedef uint2 elem;
+    static constexpr double DEN = VM_ALPHA_DEN;
+    static __device__ __forceinline__ uint2 ld(const elem *p) { return __ldg(p); }
+    static __device__ __forceinline__ uint2 lds(const elem *p) { return *p; }
+};
+
+// exact per-pixel evaluation (frame borders, samples outside the source, undecidable roundings):
+// scipy's float64 arithmetic on the fast path's coordinates.  `mask` bit c set =
+// recompute colour c; bit 3 = the fast geometry did not apply: recompute everything.
+// o.w / na = the fast path's alpha', 1 - alpha'.
+template <int SRC>
+__device__ __noinline__ float4 vl_exact_px(const typename VlSrc<SRC>::elem *__restrict__ src, double t0, double t1,
+                                           int h, int w, const uint8_t *__restrict__ bp, float4 o, float na,
+                                           unsigned mask, int *outside) {
+    const float bgv[3] = {(float)__ldg(bp), (float)__ldg(bp + 1), (float)__ldg(bp + 2)};
+    const VmBilin64 s = vm_mapcoord_setup(t0, t1, h, w);
+    if (!s.inside) {
+        (*outside)++;
+        return make_float4(bgv[0], bgv[1], bgv[2], 0.f);
+    }
+    const uint2 e0 = VlSrc<SRC>::ld(src + ((int64_t)s.i0 * w + s.j0)), e1 = VlSrc<SRC>::ld(src + ((int64_t)s.i0 * w + s.j1));
+    const uint2 e2 = VlSrc<SRC>::ld(src + ((int64_t)s.i1 * w + s.j0)), e3 = VlSrc<SRC>::ld(src + ((int64_t)s.i1 * w + s.j1));
+    float a2 = o.w;
+    if (mask & 8u) {
+        const double a64 = vm_mapcoord_blend(s, (double)e0.y / VlSrc<SRC>::DEN, (double)e1.y / VlSrc<SRC>::DEN,
+                                             (double)e2.y / VlSrc<SRC>::DEN, (double)e3.y / VlSrc<SRC>::DEN);
+        a2 = (float)a64;
+        na = (float)(1.0 - a64);
+        mask = 15u;
+    }
+    float res[3] = {o.x, o.y, o.z};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (mask & (1u << c)) {
+            const float col = (float)vm_round_half_up_u8(vm_mapcoord_blend(
+                s, (double)((e0.x >> (8 * c)) & 255u), (double)((e1.x >> (8 * c)) & 255u),
+                (double)((e2.x >> (8 * c)) & 255u), (double)((e3.x >> (8 * c)) & 255u)));
+            res[c] = __fmaf_rn(a2, col, na * bgv[c]);
+        }
+    }
+    return make_float4(res[0], res[1], res[2], a2);
+}
+
+// column interpolation of one coarse row (tps.py:68,73 with the column weights applied first)
+__device__ __forceinline__ VlC vl_col_lerp(double2 a, double2 b, double y1, double yf) {
+    VlC c;
+    c.x = fma(b.x, yf, a.x * y1);
+    c.y = fma(b.y, yf, a.y * y1);
+    return c;
+}
+
+// fixed-point blend + composite of one pixel; returns the mask of what the exact path must redo
+template <int SRC>
+__device__ __forceinline__ unsigned vl_blend(const uint2 (&e)[4], uint32_t fa, uint32_t fb, bool fast, float b0, float b1,
+                                             float b2, float4 &o, float &na_out) {
+    constexpr float SCALE = (float)(1.0 / (VlSrc<SRC>::DEN * 1073741824.0));
+    constexpr uint32_t DEN_U = (uint32_t)VlSrc<SRC>::DEN;
+    // 2^-30 fixed-point weights (floor: each is at most one unit below the true product)
+    const uint32_t A1 = fa >> 1, A0 = 0x80000000u - A1, B1 = fb >> 1, B0 = 0x80000000u - B1;
+    const uint32_t W00 = __umulhi(A0, B0), W01 = __umulhi(A0, B1), W10 = __umulhi(A1, B0), W11 = __umulhi(A1, B1);
+    const uint32_t w0 = W00 >> 6, w1 = W01 >> 6, w2 = W10 >> 6, w3 = W11 >> 6;     // 2^-24
+    unsigned unc = fast ? 0u : 8u;
+    float col[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const uint32_t s0 = c == 0 ? (e[0].x & 255u) : __byte_perm(e[0].x, 0, 0x4440 + c);
+        const uint32_t s1 = c == 0 ? (e[1].x & 255u) : __byte_perm(e[1].x, 0, 0x4440 + c);
+        const uint32_t s2 = c == 0 ? (e[2].x & 255u) : __byte_perm(e[2].x, 0, 0x4440 + c);
+        const uint32_t s3 = c == 0 ? (e[3].x & 255u) : __byte_perm(e[3].x, 0, 0x4440 + c);
+        // value * 2^24 + 1/2 + window: the true value lies in [v, v + 1040] units (floored weights),
+        // +-1 unit for the rounding of the fraction itself
+        const uint32_t v = s0 * w0 + s1 * w1 + s2 * w2 + s3 * w3 + (8388608u + 1100u);
+        col[c] = (float)(v >> 24);
+        if ((v & 0x00FFFFFFu) < 1108u) unc |= 1u << c;
+    }
+    const unsigned long long a2f = (unsigned long long)e[0].y * W00 + (unsigned long long)e[1].y * W01 +
+                                   (unsigned long long)e[2].y * W10 + (unsigned long long)e[3].y * W11;
+    const uint32_t ws = W00 + W01 + W10 + W11;
+    const unsigned long long naf = (unsigned long long)DEN_U * ws - a2f;
+    const float a2 = (float)a2f * SCALE, na = (float)naf * SCALE;
+    o.x = __fmaf_rn(a2, col[0], na * b0);
+    o.y = __fmaf_rn(a2, col[1], na * b1);
+    o.z = __fmaf_rn(a2, col[2], na * b2);
+    o.w = a2;
+    na_out = na;
+    return unc;
+}
+
+// floor + 2^-32 fraction of both coordinates; true when all four taps are strictly inside the
+// frame and away from the t = 0 edge (the exact path decides there)
+__device__ __forceinline__ bool vl_geometry(double t0, double t1, int h, int w, int &n0, int &n1, uint32_t &fa, uint32_t &fb) {
+    const double m0 = t0 + VL_MAGIC, m1 = t1 + VL_MAGIC;
+    n0 = __double2hiint(m0) - VL_MAGIC_HI; n1 = __double2hiint(m1) - VL_MAGIC_HI;
+    fa = (uint32_t)__double2loint(m0); fb = (uint32_t)__double2loint(m1);
+    return (unsigned)(n0 - 1) < (unsigned)(h - 2) && (unsigned)(n1 - 1) < (unsigned)(w - 2);
+}
+
+// ---- P4, tile path: Cs in shared memory; taps from the staged box (BOX) or from global memory ----
+template <int SRC, bool BOX, bool BGSM>
+__device__ __forceinline__ void vl_strip_tile(const typename VlSrc<SRC>::elem *__restrict__ src,
+                                              const typename VlSrc<SRC>::elem *__restrict__ box, int rmin, int cmin, int bw,
+                                              const double2 *__restrict__ Csj, int kr0, const vm_axis_entry *__restrict__ rp,
+                                              const unsigned char *__restrict__ bgl, const uint8_t *__restrict__ bgp,
+                                              float4 *__restrict__ op, int nrows, int h, int w, int *outside) {
+    typedef typename VlSrc<SRC>::elem elem;
+    const int w3 = w * 3;
+    constexpr int pitch = VL_FW * 3;
+#pragma unroll 2
+    for (int i = 0; i < nrows; ++i) {
+        const vm_axis_entry re = rp[i];
+        const double2 c0 = Csj[(re.i0 - kr0) * VL_FW], c1 = Csj[(re.i1 - kr0) * VL_FW];
+        const double xf = re.frac, x1 = 1.0 - xf;
+        const double t0 = fma(c1.x, xf, c0.x * x1), t1 = fma(c1.y, xf, c0.y * x1);
+        int n0, n1;
+        uint32_t fa, fb;
+        const bool fast = vl_geometry(t0, t1, h, w, n0, n1, fa, fb);
+        uint2 e[4];
+        if (BOX) {
+            const int q = fast ? (n0 - rmin) * bw + (n1 - cmin) : 0;
+            const elem *g0 = box + q, *g1 = g0 + (fast ? bw : 0);
+            e[0] = VlSrc<SRC>::lds(g0); e[1] = VlSrc<SRC>::lds(g0 + 1); e[2] = VlSrc<SRC>::lds(g1); e[3] = VlSrc<SRC>::lds(g1 + 1);
+        } else {
+            const int q = fast ? n0 * w + n1 : 0;
+            const elem *g0 = src + q, *g1 = g0 + (fast ? w : 0);
+            e[0] = VlSrc<SRC>::ld(g0); e[1] = VlSrc<SRC>::ld(g0 + 1); e[2] = VlSrc<SRC>::ld(g1); e[3] = VlSrc<SRC>::ld(g1 + 1);
+        }
+        float b0, b1, b2;
+        if (BGSM) { b0 = (float)bgl[0]; b1 = (float)bgl[1]; b2 = (float)bgl[2]; }
+        else { b0 = (float)__ldcs(bgp); b1 = (float)__ldcs(bgp + 1); b2 = (float)__ldcs(bgp + 2); }
+        float4 o;
+        float na;
+        const unsigned unc = vl_blend<SRC>(e, fa, fb, fast, b0, b1, b2, o, na);
+        if (unc) o = vl_exact_px<SRC>(src, t0, t1, h, w, bgp, o, na, unc, outside);
+        __stcs(op, o);                                                 // streamed once: evict first
+        bgl += pitch; bgp += w3; op += w;
+    }
+}
+
+// ---- P4, generic path: rolling column-interpolated rows straight from global memory ----------
+template <int SRC>
+__device__ __noinline__ void vl_strip_generic(const typename VlSrc<SRC>::elem *__restrict__ src,
+                                              const double2 *__restrict__ Ta, const double2 *__restrict__ Tb, int ny,
+                                              const vm_axis_entry *__restrict__ rp, double yf,
+                                              const uint8_t *__restrict__ bgp, float4 *__restrict__ op, int nrows,
+                                              int h, int w, int *outside) {
+    typedef typename VlSrc<SRC>::elem elem;
+    const double y1 = 1.0 - yf;
+    const int w3 = w * 3;
+    int k0 = -1, k1 = -1;
+    VlC C0 = {0.0, 0.0}, C1 = {0.0, 0.0};
+    for (int i = 0; i < nrows; ++i) {
+        const vm_axis_entry re = vm_ld_axis(rp + i);
+        if (re.i0 != k0) {
+            if (re.i0 == k1) C0 = C1; else C0 = vl_col_lerp(__ldg(Ta + re.i0 * ny), __ldg(Tb + re.i0 * ny), y1, yf);
+            k0 = re.i0;
+        }
+        if (re.i1 != k1) {
+            if (re.i1 == k0) C1 = C0; else C1 = vl_col_lerp(__ldg(Ta + re.i1 * ny), __ldg(Tb + re.i1 * ny), y1, yf);
+            k1 = re.i1;
+        }
+        const double xf = re.frac, x1 = 1.0 - xf;
+        const double t0 = fma(C1.x, xf, C0.x * x1), t1 = fma(C1.y, xf, C0.y * x1);
+        int n0, n1;
+        uint32_t fa, fb;
+        const bool fast = vl_geometry(t0, t1, h, w, n0, n1, fa, fb);
+        const int q = fast ? n0 * w + n1 : 0;
+        const elem *g0 = src + q, *g1 = g0 + (fast ? w : 0);
+        uint2 e[4];
+        e[0] = VlSrc<SRC>::ld(g0); e[1] = VlSrc<SRC>::ld(g0 + 1); e[2] = VlSrc<SRC>::ld(g1); e[3] = VlSrc<SRC>::ld(g1 + 1);
+        const float b0 = (float)__ldcs(bgp), b1 = (float)__ldcs(bgp + 1), b2 = (float)__ldcs(bgp + 2);
+        float4 o;
+        float na;
+        const unsigned unc = vl_blend<SRC>(e, fa, fb, fast, b0, b1, b2, o, na);
+        if (unc) o = vl_exact_px<SRC>(src, t0, t1, h, w, bgp, o, na, unc, outside);
+        __stcs(op, o);
+        bgp += w3; op += w;
+    }
+}
+
+// one warp polls the mbarrier (phase 0), the CTA barrier releases everybody else without spinning
+__device__ __forceinline__ void vl_cta_wait(uint32_t bar, bool poll) {
+    if (poll) {
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(bar) : "memory");
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void vl_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Source box of every B2 tile: bounding box of the coarse transform window the tile interpolates
+// in (the fine transform is a convex combination of those values), aligned for 16-byte bulk copies.
+// One warp per tile; runs right behind B1 on the same stream.
+template <int SRC>
+__global__ void __launch_bounds__(128)
+k_lean_boxes(const double2 *__restrict__ T, int nx, int ny, const vm_axis_entry *__restrict__ rows,
+             const vm_axis_entry *__restrict__ cols, int h, int w, int rpt, int tiles_x, int tiles_y, int n_tiles,
+             int box_cap, VlTileBox *__restrict__ boxes) {
+    constexpr int EPV = 16 / (int)sizeof(typename VlSrc<SRC>::elem);
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (t >= n_tiles) return;
+    const int per = tiles_x * tiles_y;
+    const int frame = t / per, tl = t - frame * per;
+    const int ty = tl / tiles_x, tx = tl - ty * tiles_x;
+    const int I0 = ty * (VL_FS * rpt), J0 = tx * VL_FW;
+    const int th = min(VL_FS * rpt, h - I0), tw = min(VL_FW, w - J0);
+    const vm_axis_entry r0 = vm_ld_axis(rows + I0), r1 = vm_ld_axis(rows + I0 + th - 1);
+    const vm_axis_entry c0 = vm_ld_axis(cols + J0), c1 = vm_ld_axis(cols + J0 + tw - 1);
+    const int kr0 = r0.i0, kr1 = max(r1.i1, r1.i0), kc0 = c0.i0, kc1 = max(c1.i1, c1.i0);
+    const int nkr = kr1 - kr0 + 1, nkc = kc1 - kc0 + 1;
+    VlTileBox rec = {0, 0, 0, 0};
+    if (nkr >= 1 && nkc >= 1 && nkr <= 4096 && nkc <= 4096 && kr0 >= 0 && kr1 < nx && kc0 >= 0 && kc1 < ny) {
+        const double2 *Tf = T + (int64_t)frame * nx * ny + (int64_t)kr0 * ny + kc0;
+        int rlo = INT_MAX, rhi = INT_MIN, clo = INT_MAX, chi = INT_MIN, bad = 0;
+        for (int r = 0; r < nkr; ++r)
+            for (int c = lane; c < nkc; c += 32) {
+                const double2 v = __ldg(Tf + (int64_t)r * ny + c);
+                if (!(fabs(v.x) < 1.0e9) || !(fabs(v.y) < 1.0e9)) bad = 1;
+                else {
+                    const int f0 = __double2int_rd(v.x), f1 = __double2int_rd(v.y);
+                    rlo = min(rlo, f0); rhi = max(rhi, f0); clo = min(clo, f1); chi = max(chi, f1);
+                }
+            }
+        rlo = __reduce_min_sync(0xffffffffu, rlo); rhi = __reduce_max_sync(0xffffffffu, rhi);
+        clo = __reduce_min_sync(0xffffffffu, clo); chi = __reduce_max_sync(0xffffffffu, chi);
+        bad = __reduce_max_sync(0xffffffffu, bad);
+        // rows [rmin, rmax] x columns [cmin, cmin + bw) hold every tap of every in-frame fast pixel
+        const int rmin = max(rlo, 0), rmax = min(rhi + 1, h - 1);
+        int cmin = max(clo, 0) & ~(EPV - 1);
+        const int cmax = min(chi + 1, w - 1);
+        const int bh = rmax - rmin + 1;
+        const int bw = (cmax - cmin + 1 + EPV - 1) & ~(EPV - 1);
+        if (cmin + bw > w) cmin = w - bw;
+        if (!bad && bh >= 1 && bw >= EPV && cmin >= 0 && (w & (EPV - 1)) == 0 && bh * bw <= box_cap) {
+            rec.rmin = rmin; rec.bh = bh; rec.cmin = cmin; rec.bw = bw;
+        }
+    }
+    if (lane == 0) boxes[t] = rec;
+}
+
+template <int SRC, int MINB>
+__global__ void __launch_bounds__(VL_FW * VL_FS, MINB)
+k_lean_fine(const void *__restrict__ src_all, const uint8_t *__restrict__ bg, int n_bg, int frame0,
+            const double2 *__restrict__ T, int nx, int ny, const vm_axis_entry *__restrict__ rows,
+            const vm_axis_entry *__restrict__ cols, int h, int w, int rpt, const VlTileBox *__restrict__ boxes,
+            float4 *__restrict__ out, int32_t *__restrict__ status) {
+    typedef typename VlSrc<SRC>::elem elem;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    VlFineSmem &S = *reinterpret_cast<VlFineSmem *>(smem_raw);
+    const int tid = threadIdx.y * VL_FW + threadIdx.x;
+    const int J0 = blockIdx.x * VL_FW, I0 = blockIdx.y * (VL_FS * rpt);
+    const int tw = min(VL_FW, w - J0), th = min(VL_FS * rpt, h - I0);
+    const int frame = blockIdx.z;
+    const int jc = min((int)threadIdx.x, tw - 1), j = J0 + jc;
+    const uint32_t bar0 = vl_smem_u32(&S.bar[0]);
+    const int64_t fbase = (int64_t)frame * h * w;
+    const elem *src = reinterpret_cast<const elem *>(src_all) + fbase;
+    int bgi = frame0 + frame;
+    if (bgi >= n_bg) bgi %= n_bg;
+    const uint8_t *bgf = bg + (int64_t)bgi * h * w * 3;
+    const double2 *Tf = T + (int64_t)frame * nx * ny;
+
+    // ---- P0: axis entries, tile record, barrier ---------------------------------------------
+    const vm_axis_entry ce = vm_ld_axis(cols + j);
+    const VlTileBox rec = boxes[((int64_t)frame * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x];
+    vm_axis_entry myrow = {0.0, 0, 0};
+    if (tid < th) { myrow = vm_ld_axis(rows + I0 + tid); S.rows[tid] = myrow; }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const int kr0 = S.rows[0].i0, kr1 = max(S.rows[th - 1].i1, S.rows[th - 1].i0);
+    const int nkr = kr1 - kr0 + 1;
+    // every (i0, i1) of the tile's rows must lie inside the window that Cs covers
+    const bool row_ok = tid >= th || (myrow.i0 >= kr0 && myrow.i0 <= kr1 && myrow.i1 >= kr0 && myrow.i1 <= kr1);
+    // ... and every (i0, i1) of its columns inside the window k_lean_boxes scanned
+    const vm_axis_entry cf = vm_ld_axis(cols + J0), cl = vm_ld_axis(cols + J0 + tw - 1);
+    const int kc0 = cf.i0, kc1 = max(cl.i1, cl.i0);
+    const bool win_ok = nkr >= 1 && nkr <= VL_TR && kr0 >= 0 && kr1 < nx && kc0 >= 0 && kc1 < ny &&
+                        ce.i0 >= kc0 && ce.i0 <= kc1 && ce.i1 >= kc0 && ce.i1 <= kc1;
+    const bool all_staged = __syncthreads_and(row_ok && win_ok);
+
+    const int strip0 = threadIdx.y * rpt;                               // first row of the strip inside the CTA
+    const int nrows = min(rpt, th - strip0);
+    const int64_t p0 = (int64_t)(I0 + strip0) * w + j;
+    const uint8_t *bgp = bgf + p0 * 3;
+    float4 *op = out + fbase + p0;
+    int outside = 0;
+    const bool active = (int)threadIdx.x < tw && nrows > 0;
+
+    if (!all_staged) {                                                  // generic axis tables: everything from global memory
+        if (active) vl_strip_generic<SRC>(src, Tf + ce.i0, Tf + ce.i1, ny, rows + I0 + strip0, ce.frac, bgp, op, nrows, h, w, &outside);
+        if (status && outside) atomicAdd(status + VM_STATUS_TPS_OUTSIDE, outside);
+        return;
+    }
+
+    // ---- P1: bulk async copies (TMA): background rows + source box, all on one mbarrier -------
+    const bool bg_sm = tw == VL_FW && (w & 15) == 0 && (reinterpret_cast<uintptr_t>(bg) & 15) == 0;
+    const bool boxed = rec.bw > 0 && (reinterpret_cast<uintptr_t>(src_all) & 15) == 0;
+    elem *boxp = reinterpret_cast<elem *>(S.box);
+    if (tid == 0 && (bg_sm || boxed)) {
+        const uint32_t bytes = (bg_sm ? (uint32_t)(th * VL_FW * 3) : 0u) + (boxed ? (uint32_t)(rec.bh * rec.bw * (int)sizeof(elem)) : 0u);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0), "r"(bytes) : "memory");
+        if (boxed)
+            for (int r = 0; r < rec.bh; ++r)
+                vl_bulk_g2s(vl_smem_u32(boxp + r * rec.bw), src + (int64_t)(rec.rmin + r) * w + rec.cmin,
+                            (uint32_t)(rec.bw * (int)sizeof(elem)), bar0);
+        if (bg_sm)
+            for (int r = 0; r < th; ++r)
+                vl_bulk_g2s(vl_smem_u32(S.bgt + r * (VL_FW * 3)), bgf + ((int64_t)(I0 + r) * w + J0) * 3, VL_FW * 3, bar0);
+    }
+
+    // ---- P2: column-interpolated coarse rows; thread (jc, strip) takes rows strip, strip + VL_FS, ...
+    {
+        const double yf = ce.frac, y1 = 1.0 - yf;
+        const double2 *Ta = Tf + (int64_t)kr0 * ny + ce.i0, *Tb = Tf + (int64_t)kr0 * ny + ce.i1;
+        constexpr int KMAX = (VL_TR + VL_FS - 1) / VL_FS;
+        double2 ta[KMAX], tb[KMAX];
+#pragma unroll
+        for (int u = 0; u < KMAX; ++u) {
+            const int k = min((int)threadIdx.y + u * VL_FS, nkr - 1);
+            ta[u] = __ldg(Ta + k * ny); tb[u] = __ldg(Tb + k * ny);
+        }
+#pragma unroll
+        for (int u = 0; u < KMAX; ++u) {
+            const int k = threadIdx.y + u * VL_FS;
+            if (k < nkr) {
+                const VlC c = vl_col_lerp(ta[u], tb[u], y1, yf);
+                S.Cs[k * VL_FW + threadIdx.x] = make_double2(c.x, c.y);
+            }
+        }
+    }
+    vl_cta_wait(bar0, tid < 32 && (bg_sm || boxed));
+
+    const unsigned char *bgl = S.bgt + (strip0 * VL_FW + (int)threadIdx.x) * 3;
+    const double2 *Csj = S.Cs + threadIdx.x;
+
+    // ---- P3: per-pixel resampling + composite ------------------------------------------------
+    if (!boxed && status && tid == 0) atomicAdd(status + VM_STATUS_SLOW_TILES, 1);
+    if (active) {
+        const vm_axis_entry *rp = S.rows + strip0;
+        if (boxed && bg_sm) vl_strip_tile<SRC, true, true>(src, boxp, rec.rmin, rec.cmin, rec.bw, Csj, kr0, rp, bgl, bgp, op, nrows, h, w, &outside);
+        else if (boxed)     vl_strip_tile<SRC, true, false>(src, boxp, rec.rmin, rec.cmin, rec.bw, Csj, kr0, rp, bgl, bgp, op, nrows, h, w, &outside);
+        else                vl_strip_tile<SRC, false, false>(src, boxp, 0, 0, 0, Csj, kr0, rp, bgl, bgp, op, nrows, h, w, &outside);
+    }
+    if (status && outside) atomicAdd(status + VM_STATUS_TPS_OUTSIDE, outside);
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static inline int64_t vl_align(int64_t v) { return (v + 255) & ~(int64_t)255; }
+
+int64_t vm_lean_scratch_bytes(int n, int h, int w) {
+    const int m = n < g_vl_chunk ? n : g_vl_chunk;
+    const int64_t tiles = (int64_t)m * ((w + VL_FW - 1) / VL_FW) * ((h + 3) / 4);     // >= tiles for any rows-per-thread setting
+    return 512 + vl_align((int64_t)m * h * w * 8) +
+           (g_vl_overlap ? 2 : 1) * (vl_align((int64_t)m * (h / 2 + 1) * (w / 2 + 1) * 16) + vl_align(tiles * 16));
+}
+
+int vm_lean_set_option(const char *key, int value) {
+    if (!strcmp(key, "lean_chunk") && value >= 1 && value <= 4096) { g_vl_chunk = value; return VM_OK; }
+    if (!strcmp(key, "lean_overlap") && value >= 0 && value <= 1) { g_vl_overlap = value; return VM_OK; }
+    if (!strcmp(key, "lean_rb") && value >= 0 && value <= 64) { g_vl_rb = value; return VM_OK; }
+    if (!strcmp(key, "lean_b1_warps") && value >= 1 && value <= VL_B1_WARPS_HI) { g_vl_b1_warps = value; return VM_OK; }
+    if (!strcmp(key, "lean_b1_dyr") && value >= 0 && value <= 1) { g_vl_b1_dyr = value; return VM_OK; }
+    if (!strcmp(key, "lean_timing") && value >= 0 && value <= 1) { g_vl_timing = value; return VM_OK; }
+    if (!strcmp(key, "lean_box_cap") && value >= 0 && value <= 16384) { g_vl_box_cap = value; return VM_OK; }
+    if (!strcmp(key, "lean_minb") && value >= 2 && value <= 4) { g_vl_minb = value; return VM_OK; }
+    if (!strcmp(key, "lean_fine_rows") && value >= 1 && value <= 256) { g_vl_fine_rows = value; return VM_OK; }
+    return VM_ERR_ARG;
+}
+
+// mode 0: C3 (no flow stage), 1: flow warp only, 2: flow warp + consistency mask
+int vm_lean_launch(int mode, const uint8_t *fg, const float *backward, const float *forward, const uint8_t *bg,
+                   int n_bg, const double *ctrl, const double *coef, int N, int nx, int ny, double step_x,
+                   double step_y, const vm_axis_entry *rows, const vm_axis_entry *cols, int n, int h, int w,
+                   float *out, void *scratch, int32_t *status, cudaStream_t st, const char *what) {
+    int dev = 0;
+    int rc = vl_init(&dev);
+    if (rc != VM_OK) return rc;
+    VM_REQUIRE(scratch, "scratch workspace (vm_fused_scratch_bytes) required");
+    VM_REQUIRE(N >= 1 && N <= VL_MAX_N, "control point count out of range");
+    VM_REQUIRE(nx <= h / 2 + 1 && ny <= w / 2 + 1, "coarse grid larger than the scratch layout");
+    const int64_t px = (int64_t)h * w;
+    const int chunk = g_vl_chunk;
+    unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+    unsigned int *counters = reinterpret_cast<unsigned int *>(base);     // one B1 unit counter per chunk parity
+    base += 256;
+    void *packed = base;
+    const int mc = n < chunk ? n : chunk;
+    const int64_t t_bytes = vl_align((int64_t)mc * (h / 2 + 1) * (w / 2 + 1) * 16);
+    const int rpt = g_vl_fine_rows < VL_FROWS_MAX / VL_FS ? g_vl_fine_rows : VL_FROWS_MAX / VL_FS;
+    const int64_t box_bytes = vl_align((int64_t)mc * ((w + VL_FW - 1) / VL_FW) * ((h + 3) / 4) * 16);
+    // two {T, boxes} sets: the spline stage of chunk c+1 runs on the side stream while chunk c is
+    // flow-warped and resampled on the caller's stream (it uses the float64 / shared-memory pipes the
+    // other two stages leave idle)
+    unsigned char *tb0 = base + vl_align((int64_t)mc * px * 8);
+    double2 *Tset[2] = {reinterpret_cast<double2 *>(tb0), reinterpret_cast<double2 *>(tb0 + t_bytes + box_bytes)};
+    VlTileBox *Bset[2] = {reinterpret_cast<VlTileBox *>(tb0 + t_bytes), reinterpret_cast<VlTileBox *>(tb0 + 2 * t_bytes + box_bytes)};
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    const bool overlap = g_vl_overlap && cap == cudaStreamCaptureStatusNone;
+    if (!g_vl_overlap) { Tset[1] = Tset[0]; Bset[1] = Bset[0]; }       // one set: the scratch only holds one
+    cudaStream_t side = overlap ? g_vl_side[dev] : st;
+    if (overlap) {                                                      // the side stream starts behind the caller's work
+        cudaEventRecord(g_vl_ev_fork[dev], st);
+        cudaStreamWaitEvent(side, g_vl_ev_fork[dev], 0);
+    }
+    const bool timing = g_vl_timing && !overlap && cap == cudaStreamCaptureStatusNone;
+    if (timing && !g_vl_tev_ok[dev]) {
+        for (int k = 0; k < 5; ++k)
+            if (cudaEventCreate(&g_vl_tev[dev][k]) != cudaSuccess) { vm_set_error("vm_lean: cudaEventCreate failed"); return VM_ERR_CUDA; }
+        g_vl_tev_ok[dev] = true;
+    }
+    const int n_chunks = (n + chunk - 1) / chunk;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int f0 = c * chunk;
+        const int m = (n - f0 < chunk) ? n - f0 : chunk;
+        const int par = c & 1;
+        double2 *T = Tset[par];
+        VlTileBox *boxes = Bset[par];
+        const dim3 block(VL_FW, VL_FS), grid((w + VL_FW - 1) / VL_FW, (h + VL_FS * rpt - 1) / (VL_FS * rpt), m);
+        VM_REQUIRE(grid.y <= 65535 && m <= 65535, "too many tiles for one launch");
+        // shared memory per CTA: 227 KB per SM (1 KB reserved per CTA) split over the occupancy target
+        int box_cap = g_vl_box_cap;
+        if (box_cap <= 0) {
+            const int64_t per_cta = (227 * 1024) / g_vl_minb - 1024 - (int64_t)sizeof(VlFineSmem);
+            box_cap = (int)(per_cta / 8) & ~63;
+            if (box_cap > 8192) box_cap = 8192;
+        }
+        const size_t fine_smem = vl_fine_smem_bytes(box_cap);
+        // ---- side stream: spline on the coarse grid + tile boxes of chunk c ---------------------
+        if (overlap && c >= 2) cudaStreamWaitEvent(side, g_vl_ev_free[dev][par], 0);     // set `par` consumed by chunk c-2
+        const bool tev = timing && c == 0;
+        if (tev) cudaEventRecord(g_vl_tev[dev][0], st);
+        rc = vl_launch_coarse(ctrl + (int64_t)f0 * N * 2, coef + (int64_t)f0 * (N + 3) * 2, N, m, nx, ny, step_x, step_y, T,
+                              counters + par * 32, side);
+        if (rc != VM_OK) return rc;
+        if (tev) cudaEventRecord(g_vl_tev[dev][1], st);
+        {
+            const int n_tiles = (int)(grid.x * grid.y * m);
+            if (mode != 0) k_lean_boxes<1><<<(n_tiles + 3) / 4, 128, 0, side>>>(T, nx, ny, rows, cols, h, w, rpt, grid.x, grid.y, n_tiles, box_cap, boxes);
+            else           k_lean_boxes<0><<<(n_tiles + 3) / 4, 128, 0, side>>>(T, nx, ny, rows, cols, h, w, rpt, grid.x, grid.y, n_tiles, box_cap, boxes);
+            rc = vm_check_launch("vm_lean box stage");
+            if (rc != VM_OK) return rc;
+        }
+        if (overlap) cudaEventRecord(g_vl_ev_ready[dev][par], side);
+        if (tev) cudaEventRecord(g_vl_tev[dev][2], st);
+        g_vl_launches += 2 + (mode != 0 ? 1 : 0) + 1;
+        // ---- caller's stream: flow stage, then resampling + composite ------------------------------
+        if (mode != 0) {
+            rc = vm_launch_flow_stage(fg + f0 * px * 4, backward + f0 * px * 2, (mode == 2 && forward) ? forward + f0 * px * 2 : nullptr,
+                                      m, h, w, packed, status, st, true);
+            if (rc != VM_OK) return rc;
+        }
+        if (overlap) cudaStreamWaitEvent(st, g_vl_ev_ready[dev][par], 0);
+        if (tev) cudaEventRecord(g_vl_tev[dev][3], st);
+        float4 *o4 = reinterpret_cast<float4 *>(out) + f0 * px;
+#define VL_FINE(S, MB)                                                                                              \
+    do {                                                                                                            \
+        static size_t attr_set[64];                                                                                 \
+        if (attr_set[dev & 63] < fine_smem) {                                                                       \
+            cudaError_t e = cudaFuncSetAttribute(k_lean_fine<S, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fine_smem); \
+            if (e != cudaSuccess) { vm_set_error("vm_lean: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VM_ERR_CUDA; } \
+            attr_set[dev & 63] = fine_smem;                                                                         \
+        }                                                                                                           \
+        k_lean_fine<S, MB><<<grid, block, fine_smem, st>>>(S ? (const void *)packed : (const void *)(fg + f0 * px * 4), \
+                                                                    bg, n_bg, f0, T, nx, ny, rows, cols, h, w, rpt, boxes, o4, status); \
+    } while (0)
+        if (mode != 0) { if (g_vl_minb == 4) VL_FINE(1, 4); else if (g_vl_minb == 3) VL_FINE(1, 3); else VL_FINE(1, 2); }
+        else           { if (g_vl_minb == 4) VL_FINE(0, 4); else if (g_vl_minb == 3) VL_FINE(0, 3); else VL_FINE(0, 2); }
+#undef VL_FINE
+        rc = vm_check_launch(what);
+        if (rc != VM_OK) return rc;
+        if (tev) cudaEventRecord(g_vl_tev[dev][4], st);
+        if (overlap) cudaEventRecord(g_vl_ev_free[dev][par], st);
+    }
+    return VM_OK;
+}
+
+// Durations (ms) of the four stages of the first chunk of the last timed call on the current device:
+// {spline (k_lean_coarse), tile boxes (k_lean_boxes), flow stage (k_flow_warp_mask_bgra), resampling +
+// composite (k_lean_fine)}.  Requires vm_set_option("lean_timing", 1) before the call and a synchronised
+// stream.  Returns VM_OK, or VM_ERR_ARG when no timed call has completed.
+extern "C" int vm_lean_stage_ms(float *out4) {
+    int dev = 0;
+    if (!out4 || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !g_vl_tev_ok[dev]) {
+        vm_set_error("vm_lean_stage_ms: no timed call on this device");
+        return VM_ERR_ARG;
+    }
+    for (int k = 0; k < 4; ++k)
+        if (cudaEventElapsedTime(out4 + k, g_vl_tev[dev][k], g_vl_tev[dev][k + 1]) != cudaSuccess) {
+            cudaGetLastError();
+            vm_set_error("vm_lean_stage_ms: events not complete");
+            return VM_ERR_ARG;
+        }
+    return VM_OK;
+}
+
+// number of kernels the lean path has launched in this process (all devices)
+extern "C" long long vm_lean_launch_count(void) { return g_vl_launches; }

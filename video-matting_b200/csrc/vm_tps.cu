@@ -6,6 +6,8 @@
 #include <string.h>
 #include <mutex>
 
+int vm_lean_set_option(const char *key, int value);                                // vm_lean.cu
+
 // ---------------------------------------------------------------------------------------
 // float64 log for the radial basis U(r) = r^2 log r = 0.5 * r2 * log(r2).
 //
@@ -857,9 +859,11 @@ k_tps_gather2(const void *__restrict__ src_all, const uint8_t *__restrict__ bg, 
     }
 }
 
-// option block (vm_set_option): variant 0 = split pipeline (default), 1 = per-pixel gather
-// kernels, 2 = single shared-memory tiled kernel
-static int g_opt_variant = 0;
+// option block (vm_set_option): variant 4 = lean split pipeline (default, vm_lean.cu), 0 = first split
+// pipeline, 1 = per-pixel gather kernels, 2 = single shared-memory tiled kernel, 3 = persistent
+// role-specialised pipeline (vm_pipe.cu).  The non-default ones are kept as independent
+// implementations for differential tests.
+static int g_opt_variant = 4;
 static int g_opt_chunk = 4;                  // frames per stage-A/stage-B launch pair
 static int g_opt_tile_h = 32;
 
@@ -873,6 +877,7 @@ extern "C" int vm_set_option(const char *key, int value) {
     if (!strcmp(key, "pipe_cring_rows") && value >= 16) { g_vp_cring_rows = value; return VM_OK; }
     if (!strcmp(key, "pipe_blocks") && value >= 0) { g_vp_blocks = value; return VM_OK; }
     if (!strcmp(key, "pipe_roles") && value >= 1 && value <= 7) { g_vp_roles = value; return VM_OK; }
+    if (!strncmp(key, "lean_", 5) && vm_lean_set_option(key, value) == VM_OK) return VM_OK;
     vm_set_error("vm_set_option: unknown option %s=%d", key, value);
     return VM_ERR_ARG;
 }
@@ -895,7 +900,12 @@ static int launch_tiled(const uint8_t *fg, const float *backward, const float *f
 }
 
 int vm_launch_flow_stage(const uint8_t *fg, const float *backward, const float *forward, int n, int h, int w,
-                         void *packed, int32_t *status, cudaStream_t st);          // vm_flow.cu
+                         void *packed, int32_t *status, cudaStream_t st, bool raw_ta); // vm_flow.cu
+int64_t vm_lean_scratch_bytes(int n, int h, int w);                                // vm_lean.cu
+int vm_lean_launch(int mode, const uint8_t *fg, const float *backward, const float *forward, const uint8_t *bg,
+                   int n_bg, const double *ctrl, const double *coef, int N, int nx, int ny, double step_x,
+                   double step_y, const vm_axis_entry *rows, const vm_axis_entry *cols, int n, int h, int w,
+                   float *out, void *scratch, int32_t *status, cudaStream_t st, const char *what);
 int64_t vm_pipe_scratch_bytes(int n, int h, int w);                                // vm_pipe.cu
 int vm_pipe_launch(int mode, const uint8_t *fg, const float *backward, const float *forward, const uint8_t *bg,
                    int n_bg, const double *ctrl, const double *coef, int N, int nx, int ny, double step_x,
@@ -931,10 +941,13 @@ static int launch_fused(bool flow, const uint8_t *fg, const float *backward, con
     VM_REQUIRE(h <= 32767 && w <= 32767 && (int64_t)h * w < (1ll << 28), "frame too large");
     cudaStream_t st = (cudaStream_t)stream;
     const bool small_n = N <= TT_MAX_N && h >= 2 && w >= 2;
+    if (g_opt_variant == 4 && small_n && nx <= h / 2 + 1 && ny <= w / 2 + 1)
+        return vm_lean_launch(flow ? (forward ? 2 : 1) : 0, fg, backward, forward, bg, n_bg, ctrl, coef, N, nx, ny,
+                              step_x, step_y, rows, cols, n, h, w, out, scratch, status, st, what);
     if (g_opt_variant == 3 && small_n && nx == h / 2 && ny == w / 2)
         return vm_pipe_launch(flow ? (forward ? 2 : 1) : 0, fg, backward, forward, bg, n_bg, ctrl, coef, N, nx, ny,
                               step_x, step_y, rows, cols, n, h, w, out, scratch, status, st, what);
-    if ((g_opt_variant == 0 || g_opt_variant == 3) && small_n) {
+    if ((g_opt_variant == 0 || g_opt_variant == 3 || g_opt_variant == 4) && small_n) {
         // split pipeline: stage A (flow warp + mask -> packed intermediate, L2 resident) and stage B
         // (TPS + composite) per chunk of frames; C3 has no stage A.
         if (!flow)
@@ -945,7 +958,7 @@ static int launch_fused(bool flow, const uint8_t *fg, const float *backward, con
         for (int f0 = 0; f0 < n; f0 += g_opt_chunk) {
             const int m = (n - f0 < g_opt_chunk) ? n - f0 : g_opt_chunk;
             rc = vm_launch_flow_stage(fg + f0 * px * 4, backward + f0 * px * 2, forward ? forward + f0 * px * 2 : nullptr,
-                                      m, h, w, scratch, status, st);
+                                      m, h, w, scratch, status, st, false);
             if (rc != VM_OK) return rc;
             rc = launch_gather2<true, 32>(scratch, bg, n_bg, f0, ctrl + (int64_t)f0 * N * 2, coef + (int64_t)f0 * (N + 3) * 2,
                                           N, step_x, step_y, rows, cols, m, h, w, out + f0 * px * 4, status, st, what);
@@ -980,8 +993,10 @@ extern "C" int64_t vm_fused_scratch_bytes(int n, int h, int w) {
     const int64_t a = (int64_t)(n < g_opt_chunk ? n : g_opt_chunk) * h * w * 8;
     const int64_t b = (int64_t)n * 2 * (h / 2) * (w / 2) * (int64_t)sizeof(double);
     (void)fused_scratch_bytes;
-    const int64_t c = vm_pipe_scratch_bytes(n, h, w);
-    return (a > b ? a : b) > c ? (a > b ? a : b) : c;
+    const int64_t c = vm_pipe_scratch_bytes(n, h, w), d = vm_lean_scratch_bytes(n, h, w);
+    int64_t m = a > b ? a : b;
+    m = m > c ? m : c;
+    return m > d ? m : d;
 }
 
 extern "C" int vm_tps_composite_bgra(const uint8_t *fg, const uint8_t *bg, int n_bg, const double *ctrl,

@@ -375,13 +375,14 @@ def flow_tps_composite(fg, backward, forward, bg, ctrl, coef, plan=None, out=Non
     return out, status
 
 
-_variant = [0]
+_variant = [4]
 
 
 def set_fused_variant(v):
-    """0 = split pipeline (default: flow stage + TPS stage per L2-sized chunk of frames),
-    1 = per-pixel gather kernels, 2 = single shared-memory tiled kernel.  The non-default
-    variants are kept as independent implementations for differential tests."""
+    """4 = lean split pipeline (default: flow stage, float64 spline stage, TMA-tiled resampling
+    stage - csrc/vm_lean.cu), 0 = first split pipeline, 1 = per-pixel gather kernels, 2 = single
+    shared-memory tiled kernel, 3 = persistent role-specialised kernel.  The non-default variants
+    are kept as independent implementations for differential tests."""
     N.set_option("fused_variant", int(v))
     _variant[0] = int(v)
 
