@@ -148,7 +148,8 @@ extern "C" int vm_composite(const void *fg, int fg_dtype, const void *bg, int bg
 // 4-byte aligned because the thread's first pixel index is a multiple of 4).
 // ---------------------------------------------------------------------------------------
 #define C2_TW 128
-#define C2_TH 8
+#define C2_TH 8                    /* rows in flight per CTA (one per warp) */
+#define C2_ROWS 40                 /* rows per CTA: each warp walks C2_ROWS / C2_TH of them */
 
 // alpha = ta / 261120 as float32 with <= 1.2e-7 relative error and exact 0 / 1 end points
 __device__ __forceinline__ float vm_alpha_f32(uint32_t ta) {
@@ -167,60 +168,73 @@ template <int PACKED> __device__ __forceinline__ uint32_t vm_pack_alpha(const Vm
 }
 
 template <bool HAS_FWD, int PACKED>
-__global__ void __launch_bounds__(256, 6)
+__global__ void __launch_bounds__(256, 5)
 k_flow_warp_mask_bgra(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd,
                       const float2 *__restrict__ fwd, int h, int w, int tiles_x, int tiles_y,
                       uint8_t *__restrict__ out_bgr, float *__restrict__ out_alpha,
                       int32_t *__restrict__ status) {
+    // CTA = 128 columns x C2_ROWS rows; warp k walks rows k, k + 8, ...: the two 16-byte flow
+    // loads of the next row are in flight while the current row's taps are gathered and blended
     const int frame = blockIdx.z, ty = blockIdx.y, tx = blockIdx.x;     // 3-D grid: no integer division
-    const int i = ty * C2_TH + (threadIdx.x >> 5);
+    const int ibeg = ty * C2_ROWS + (threadIdx.x >> 5), iend = min((ty + 1) * C2_ROWS, h);
     const int j = tx * C2_TW + (threadIdx.x & 31) * 4;
-    if (i >= h || j >= w) return;
+    if (ibeg >= iend || j >= w) return;
     const int64_t fbase = (int64_t)frame * h * w;
     const uint32_t *fg32 = reinterpret_cast<const uint32_t *>(fg) + fbase;
     const float2 *bf = bwd + fbase;
     const float2 *ff = HAS_FWD ? fwd + fbase : nullptr;
-    const int p = i * w + j;
-    const float fi = (float)i, fj = (float)j;
+    const float fj = (float)j;
     int flags = 0;
     if (j + 3 < w && (w & 3) == 0) {
-        const float4 f01 = __ldcs(reinterpret_cast<const float4 *>(bf + p));      // streamed once: evict first
-        const float4 f23 = __ldcs(reinterpret_cast<const float4 *>(bf + p + 2));
-        const float2 fl[4] = {{f01.x, f01.y}, {f01.z, f01.w}, {f23.x, f23.y}, {f23.z, f23.w}};
-        VmFlowPx px[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            px[k] = vm_flow_px<HAS_FWD>(fg32, ff, h, w, i, j + k, fi, fj + (float)k, fl[k], flags);
-        if (PACKED) {
-            uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<uint2 *>(out_bgr) + fbase + p);
-            op[0] = make_uint4(px[0].bgr, vm_pack_alpha<PACKED>(px[0]), px[1].bgr, vm_pack_alpha<PACKED>(px[1]));
-            op[1] = make_uint4(px[2].bgr, vm_pack_alpha<PACKED>(px[2]), px[3].bgr, vm_pack_alpha<PACKED>(px[3]));
-            goto done;
-        }
-        float al[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) al[k] = px[k].masked ? 0.f : vm_alpha_f32(px[k].ta);
-        // 12 bytes of BGR: b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3
-        const uint32_t c0 = px[0].bgr, c1 = px[1].bgr, c2 = px[2].bgr, c3 = px[3].bgr;
-        uint32_t *ob = reinterpret_cast<uint32_t *>(out_bgr + (fbase + p) * 3);
-        ob[0] = c0 | (c1 << 24);
-        ob[1] = (c1 >> 8) | (c2 << 16);
-        ob[2] = (c2 >> 16) | (c3 << 8);
-        *reinterpret_cast<float4 *>(out_alpha + fbase + p) = make_float4(al[0], al[1], al[2], al[3]);
-    } else {
-        for (int k = 0; k < 4 && j + k < w; ++k) {
-            const float2 f = __ldg(bf + p + k);
-            const VmFlowPx px = vm_flow_px<HAS_FWD>(fg32, ff, h, w, i, j + k, fi, fj + (float)k, f, flags);
-            if (PACKED) {
-                reinterpret_cast<uint2 *>(out_bgr)[fbase + p + k] = make_uint2(px.bgr, vm_pack_alpha<PACKED>(px));
-                continue;
+        float4 n01 = __ldcs(reinterpret_cast<const float4 *>(bf + ibeg * w + j));       // streamed once: evict first
+        float4 n23 = __ldcs(reinterpret_cast<const float4 *>(bf + ibeg * w + j + 2));
+        for (int i = ibeg; i < iend; i += C2_TH) {
+            const float4 f01 = n01, f23 = n23;
+            if (i + C2_TH < iend) {
+                n01 = __ldcs(reinterpret_cast<const float4 *>(bf + (i + C2_TH) * w + j));
+                n23 = __ldcs(reinterpret_cast<const float4 *>(bf + (i + C2_TH) * w + j + 2));
             }
-            uint8_t *ob = out_bgr + (fbase + p + k) * 3;
-            ob[0] = (uint8_t)px.bgr; ob[1] = (uint8_t)(px.bgr >> 8); ob[2] = (uint8_t)(px.bgr >> 16);
-            out_alpha[fbase + p + k] = px.masked ? 0.f : vm_alpha_f32(px.ta);
+            const int p = i * w + j;
+            const float fi = (float)i;
+            const float2 fl[4] = {{f01.x, f01.y}, {f01.z, f01.w}, {f23.x, f23.y}, {f23.z, f23.w}};
+            VmFlowPx px[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                px[k] = vm_flow_px<HAS_FWD>(fg32, ff, h, w, i, j + k, fi, fj + (float)k, fl[k], flags);
+            if (PACKED) {
+                uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<uint2 *>(out_bgr) + fbase + p);
+                op[0] = make_uint4(px[0].bgr, vm_pack_alpha<PACKED>(px[0]), px[1].bgr, vm_pack_alpha<PACKED>(px[1]));
+                op[1] = make_uint4(px[2].bgr, vm_pack_alpha<PACKED>(px[2]), px[3].bgr, vm_pack_alpha<PACKED>(px[3]));
+            } else {
+                float al[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) al[k] = px[k].masked ? 0.f : vm_alpha_f32(px[k].ta);
+                // 12 bytes of BGR: b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3
+                const uint32_t c0 = px[0].bgr, c1 = px[1].bgr, c2 = px[2].bgr, c3 = px[3].bgr;
+                uint32_t *ob = reinterpret_cast<uint32_t *>(out_bgr + (fbase + p) * 3);
+                __stcs(ob, c0 | (c1 << 24));
+                __stcs(ob + 1, (c1 >> 8) | (c2 << 16));
+                __stcs(ob + 2, (c2 >> 16) | (c3 << 8));
+                __stcs(reinterpret_cast<float4 *>(out_alpha + fbase + p), make_float4(al[0], al[1], al[2], al[3]));
+            }
+        }
+    } else {
+        for (int i = ibeg; i < iend; i += C2_TH) {
+            const int p = i * w + j;
+            const float fi = (float)i;
+            for (int k = 0; k < 4 && j + k < w; ++k) {
+                const float2 f = __ldg(bf + p + k);
+                const VmFlowPx px = vm_flow_px<HAS_FWD>(fg32, ff, h, w, i, j + k, fi, fj + (float)k, f, flags);
+                if (PACKED) {
+                    reinterpret_cast<uint2 *>(out_bgr)[fbase + p + k] = make_uint2(px.bgr, vm_pack_alpha<PACKED>(px));
+                    continue;
+                }
+                uint8_t *ob = out_bgr + (fbase + p + k) * 3;
+                ob[0] = (uint8_t)px.bgr; ob[1] = (uint8_t)(px.bgr >> 8); ob[2] = (uint8_t)(px.bgr >> 16);
+                out_alpha[fbase + p + k] = px.masked ? 0.f : vm_alpha_f32(px.ta);
+            }
         }
     }
-done:
     if (HAS_FWD && flags && status) {
         if (flags & 1) atomicAdd(status + VM_STATUS_INDEX_ERR, 1);
         if (flags & 2) atomicAdd(status + VM_STATUS_NAN_ERR, 1);
@@ -230,7 +244,7 @@ done:
 // stage A of the split C4 pipelines: (n,h,w) uint2 {bgr, alpha code} or, raw_ta, {bgr, TA}
 int vm_launch_flow_stage(const uint8_t *fg, const float *backward, const float *forward, int n, int h, int w,
                          void *packed, int32_t *status, cudaStream_t st, bool raw_ta) {
-    const int tiles_x = (w + C2_TW - 1) / C2_TW, tiles_y = (h + C2_TH - 1) / C2_TH;
+    const int tiles_x = (w + C2_TW - 1) / C2_TW, tiles_y = (h + C2_ROWS - 1) / C2_ROWS;
     const dim3 tiles(tiles_x, tiles_y, n);
     const float2 *b2 = (const float2 *)backward, *f2 = (const float2 *)forward;
     uint8_t *o = (uint8_t *)packed;
@@ -247,7 +261,7 @@ extern "C" int vm_flow_warp_mask_bgra(const uint8_t *fg, const float *backward, 
     VM_REQUIRE(fg && backward && out_bgr && out_alpha, "null pointer");
     VM_REQUIRE(n >= 0 && h > 0 && w > 0 && h <= 32767 && w <= 32767, "bad size");
     if (n == 0) return VM_OK;
-    const int tiles_x = (w + C2_TW - 1) / C2_TW, tiles_y = (h + C2_TH - 1) / C2_TH;
+    const int tiles_x = (w + C2_TW - 1) / C2_TW, tiles_y = (h + C2_ROWS - 1) / C2_ROWS;
     VM_REQUIRE(tiles_y <= 65535 && n <= 65535, "too many tiles for one launch");
     const dim3 tiles(tiles_x, tiles_y, n);
     cudaStream_t st = (cudaStream_t)stream;

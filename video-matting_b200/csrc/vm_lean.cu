@@ -497,7 +497,8 @@ __device__ __forceinline__ unsigned vl_blend(const uint2 (&e)[4], uint32_t fa, u
     const uint32_t A1 = fa >> 1, A0 = 0x80000000u - A1, B1 = fb >> 1, B0 = 0x80000000u - B1;
     const uint32_t W00 = __umulhi(A0, B0), W01 = __umulhi(A0, B1), W10 = __umulhi(A1, B0), W11 = __umulhi(A1, B1);
     const uint32_t w0 = W00 >> 6, w1 = W01 >> 6, w2 = W10 >> 6, w3 = W11 >> 6;     // 2^-24
-    unsigned unc = fast ? 0u : 8u;
+    bool knife = false;
+    uint32_t vv[3];
     float col[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -509,7 +510,8 @@ __device__ __forceinline__ unsigned vl_blend(const uint2 (&e)[4], uint32_t fa, u
         // +-1 unit for the rounding of the fraction itself
         const uint32_t v = s0 * w0 + s1 * w1 + s2 * w2 + s3 * w3 + (8388608u + 1100u);
         col[c] = (float)(v >> 24);
-        if ((v & 0x00FFFFFFu) < 1108u) unc |= 1u << c;
+        vv[c] = v;
+        knife |= (v & 0x00FFFFFFu) < 1108u;
     }
     const unsigned long long a2f = (unsigned long long)e[0].y * W00 + (unsigned long long)e[1].y * W01 +
                                    (unsigned long long)e[2].y * W10 + (unsigned long long)e[3].y * W11;
@@ -521,6 +523,11 @@ __device__ __forceinline__ unsigned vl_blend(const uint2 (&e)[4], uint32_t fa, u
     o.z = __fmaf_rn(a2, col[2], na * b2);
     o.w = a2;
     na_out = na;
+    if (fast && !knife) return 0u;
+    unsigned unc = fast ? 0u : 8u;                                     // rare: which colours need the exact evaluation
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        if ((vv[c] & 0x00FFFFFFu) < 1108u) unc |= 1u << c;
     return unc;
 }
 
@@ -744,16 +751,23 @@ k_lean_fine(const void *__restrict__ src_all, const uint8_t *__restrict__ bg, in
     const bool bg_sm = tw == VL_FW && (w & 15) == 0 && (reinterpret_cast<uintptr_t>(bg) & 15) == 0;
     const bool boxed = rec.bw > 0 && (reinterpret_cast<uintptr_t>(src_all) & 15) == 0;
     elem *boxp = reinterpret_cast<elem *>(S.box);
-    if (tid == 0 && (bg_sm || boxed)) {
-        const uint32_t bytes = (bg_sm ? (uint32_t)(th * VL_FW * 3) : 0u) + (boxed ? (uint32_t)(rec.bh * rec.bw * (int)sizeof(elem)) : 0u);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0), "r"(bytes) : "memory");
-        if (boxed)
-            for (int r = 0; r < rec.bh; ++r)
-                vl_bulk_g2s(vl_smem_u32(boxp + r * rec.bw), src + (int64_t)(rec.rmin + r) * w + rec.cmin,
-                            (uint32_t)(rec.bw * (int)sizeof(elem)), bar0);
-        if (bg_sm)
-            for (int r = 0; r < th; ++r)
-                vl_bulk_g2s(vl_smem_u32(S.bgt + r * (VL_FW * 3)), bgf + ((int64_t)(I0 + r) * w + J0) * 3, VL_FW * 3, bar0);
+    if (tid < 32 && (bg_sm || boxed)) {                                 // warp 0: one lane per row, 32 copies per instruction
+        if (tid == 0) {
+            const uint32_t bytes = (bg_sm ? (uint32_t)(th * VL_FW * 3) : 0u) + (boxed ? (uint32_t)(rec.bh * rec.bw * (int)sizeof(elem)) : 0u);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0), "r"(bytes) : "memory");
+        }
+        __syncwarp();
+        if (boxed) {
+            const uint32_t row_bytes = (uint32_t)(rec.bw * (int)sizeof(elem));
+            const elem *g = src + (int64_t)rec.rmin * w + rec.cmin;
+            for (int r = tid; r < rec.bh; r += 32)
+                vl_bulk_g2s(vl_smem_u32(boxp + r * rec.bw), g + (int64_t)r * w, row_bytes, bar0);
+        }
+        if (bg_sm) {
+            const uint8_t *g = bgf + ((int64_t)I0 * w + J0) * 3;
+            for (int r = tid; r < th; r += 32)
+                vl_bulk_g2s(vl_smem_u32(S.bgt + r * (VL_FW * 3)), g + (int64_t)r * w * 3, VL_FW * 3, bar0);
+        }
     }
 
     // ---- P2: column-interpolated coarse rows; thread (jc, strip) takes rows strip, strip + VL_FS, ...
