@@ -25,7 +25,7 @@ H, W, CLIP, NCTRL = 1080, 1920, 64, 5
 BYTES_PER_PX = {"c4": 39, "c2": 27}
 # dram__bytes_read.sum + dram__bytes_write.sum of the four kernels of one 64-frame launch, from the ncu
 # --set full capture summarised in profiles/ (None until measured for the current kernels)
-TRAFFIC_PER_LAUNCH = None
+TRAFFIC_PER_LAUNCH = 8758900480
 TRAFFIC_SOURCE = "profiles/r01_lean_traffic.txt"
 METRIC = "1080p frames/s (warp+TPS+composite)"
 WORKLOAD = ("C4 1080p: flow warp + fwd/bwd occlusion mask + TPS (25 control points, fresh grid per frame) "

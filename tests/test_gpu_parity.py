@@ -393,3 +393,132 @@ def test_1080p_properties(vm):
     assert close(got[..., 3], ra, 1e-6)
     flips = np.count_nonzero(~np.isclose(got[..., :3], rc, rtol=RTOL, atol=1e-5))
     assert flips <= 3, f"{flips} composite samples differ beyond tolerance at 1080p"
+
+
+# ------------------------------------------------------------------ lean pipeline (default variant)
+
+def _lean_case(h, w, n, n_ctrl, seed=300, stretch=1.0):
+    frames = np.stack([O.synth_frame(seed + k, h, w) for k in range(n)])
+    flows = [O.synth_flows(seed + k, h, w) for k in range(n)]
+    grids = []
+    for k in range(n):
+        g, d = O.synth_grids(seed + k, h, w, n_ctrl)
+        grids.append((g, g + (d - g) * stretch))
+    bgs = np.stack([O.synth_background(k, h, w) for k in range(n)])
+    return frames, np.stack([f[0] for f in flows]), np.stack([f[1] for f in flows]), grids, bgs
+
+
+def test_lean_partition_independent(vm):
+    """The result must not depend on how the work is cut: frames per stage round, coarse rows per
+    spline unit, resampling occupancy target, and whether a tile's source box is staged in shared
+    memory (box capacity 64 entries forces every tile onto the global-gather path)."""
+    h, w, n = 200, 333 + 3, 5                       # w % 4 == 0 so that the box path is eligible
+    P, Nt = vm.pipeline, vm._native
+    frames, fb, ff, grids, bgs = _lean_case(h, w, n, 5)
+    ctrl, coef = P.solve_grids(grids)
+    args = (dev(frames), dev(fb), dev(ff), dev(bgs), ctrl, coef)
+    base, st0 = P.flow_tps_composite(*args)
+    base3, _ = P.tps_composite(args[0], args[3], ctrl, coef)
+    assert int(st0[4]) < 4, "most tiles of a mild grid must take the shared-memory box path"
+    defaults = {"lean_chunk": 64, "lean_rb": 0, "lean_minb": 4, "lean_box_cap": 0, "lean_fine_rows": 8}
+    try:
+        for key, values in (("lean_chunk", (1, 2, 3)), ("lean_rb", (4, 16, 32)), ("lean_minb", (2, 3)),
+                            ("lean_box_cap", (64,)), ("lean_fine_rows", (3, 5))):
+            for v in values:
+                Nt.set_option(key, v)
+                out, st = P.flow_tps_composite(*args)
+                out3, _ = P.tps_composite(args[0], args[3], ctrl, coef)
+                assert torch.equal(out, base) and torch.equal(out3, base3), f"{key}={v} changes the result"
+                if key == "lean_box_cap":
+                    assert int(st[4]) > 0, "box capacity 64 must push tiles onto the gather path"
+            Nt.set_option(key, defaults[key])
+    finally:
+        for key, v in defaults.items():
+            Nt.set_option(key, v)
+
+
+@pytest.mark.parametrize("n_ctrl", [3, 4, 6, 8])
+def test_lean_control_point_counts_vs_oracle(vm, n_ctrl):
+    """N = 16 and 25 use the unrolled spline kernels, every other count the run-time one (N <= 64)."""
+    h, w, n = 96, 128, 2
+    P = vm.pipeline
+    frames, fb, ff, grids, bgs = _lean_case(h, w, n, n_ctrl, seed=410)
+    ctrl, coef = P.solve_grids(grids)
+    out, _ = P.flow_tps_composite(dev(frames), dev(fb), dev(ff), dev(bgs), ctrl, coef)
+    out = out.cpu().numpy()
+    for k in range(n):
+        rc, ra = O.pipeline_c4(frames[k], fb[k], ff[k], grids[k], bgs[k])
+        assert close(out[k][..., 3], ra, 1e-6)
+        assert np.count_nonzero(~np.isclose(out[k][..., :3], rc, rtol=RTOL, atol=1e-5)) <= 1
+
+
+def test_lean_stretched_grid_vs_oracle(vm):
+    """30 % displacements: many tiles' source boxes exceed shared memory (gather path) and control points
+    come close to coarse grid points (generic spline path); both must still match the oracle."""
+    h, w = 256, 320
+    P = vm.pipeline
+    frames, fb, ff, grids, bgs = _lean_case(h, w, 1, 5, seed=77, stretch=6.0)
+    ctrl, coef = P.solve_grids(grids)
+    out, st = P.flow_tps_composite(dev(frames), dev(fb), dev(ff), dev(bgs), ctrl, coef)
+    rc, ra = O.pipeline_c4(frames[0], fb[0], ff[0], grids[0], bgs[0])
+    got = out[0].cpu().numpy()
+    assert close(got[..., 3], ra, 1e-6)
+    assert np.count_nonzero(~np.isclose(got[..., :3], rc, rtol=RTOL, atol=1e-5)) <= 1
+    assert int(st[5]) == 0
+
+
+def test_lean_control_point_on_grid_point(vm):
+    """A control point that coincides with a coarse grid point (r = 0: U = 0, tps.py:78-82) and one a hair
+    away from it (r^2 below the log table) take the generic spline path of their unit."""
+    h, w = 128, 160
+    P = vm.pipeline
+    frames, fb, ff, grids, bgs = _lean_case(h, w, 1, 4, seed=55)
+    g, d = grids[0]
+    d = d.copy()
+    sx, sy = h / float(h // 2 - 1), w / float(w // 2 - 1)          # coarse grid steps (tps.py:47)
+    d[5] = (20 * sx, 31 * sy)                                       # exactly on coarse point (20, 31)
+    d[6] = (33 * sx + 1e-3, 40 * sy - 2e-3)                         # 2e-3 px away from coarse point (33, 40)
+    grids = [(g, d)]
+    ctrl, coef = P.solve_grids(grids)
+    out, _ = P.flow_tps_composite(dev(frames), dev(fb), dev(ff), dev(bgs), ctrl, coef)
+    rc, ra = O.pipeline_c4(frames[0], fb[0], ff[0], grids[0], bgs[0])
+    got = out[0].cpu().numpy()
+    assert close(got[..., 3], ra, 1e-6)
+    assert np.count_nonzero(~np.isclose(got[..., :3], rc, rtol=RTOL, atol=1e-5)) <= 1
+
+
+def test_lean_stage_timing_and_launch_count(vm):
+    import ctypes
+    h, w, n = 128, 192, 3
+    P, Nt = vm.pipeline, vm._native
+    lib = Nt.load()
+    frames, fb, ff, grids, bgs = _lean_case(h, w, n, 5)
+    ctrl, coef = P.solve_grids(grids)
+    before = lib.vm_lean_launch_count()
+    Nt.set_option("lean_timing", 1)
+    try:
+        P.flow_tps_composite(dev(frames), dev(fb), dev(ff), dev(bgs), ctrl, coef)
+        torch.cuda.synchronize()
+        buf = (ctypes.c_float * 4)()
+        Nt.check(lib.vm_lean_stage_ms(ctypes.cast(buf, ctypes.c_void_p)))
+    finally:
+        Nt.set_option("lean_timing", 0)
+    assert all(0.0 < v < 1000.0 for v in buf)
+    assert lib.vm_lean_launch_count() - before == 4          # spline, boxes, flow stage, resampling
+
+
+def test_4k_identity_property(vm):
+    """4K (config 4 size): zero flow + undeformed grid through the fused C4 path == plain composite."""
+    h, w = 2160, 3840
+    P = vm.pipeline
+    frame = O.synth_frame(990, h, w)
+    bg = O.synth_background(4, h, w)
+    grid, _ = O.synth_grids(0, h, w, 5)
+    ctrl, coef = P.solve_grids([(grid, grid)])
+    zero = torch.zeros((1, h, w, 2), dtype=torch.float32, device="cuda")
+    out, _ = P.flow_tps_composite(dev(frame[None]), zero, zero, dev(bg[None]), ctrl, coef)
+    ref = O.create_composite_image(frame[..., :3], bg, frame[..., 3] / 255.)
+    inner = (slice(2, -2), slice(2, -2))
+    o = out[0].cpu().numpy()
+    assert close(o[inner][..., :3], ref[inner], 1e-5)
+    assert close(o[inner][..., 3], (frame[..., 3] / 255.)[inner], 1e-6)

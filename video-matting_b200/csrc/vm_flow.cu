@@ -241,12 +241,70 @@ k_flow_warp_mask_bgra(const uint8_t *__restrict__ fg, const float2 *__restrict__
     }
 }
 
+// Packed-output variant used by the C4 pipelines: thread = one column x 4 consecutive rows, so
+// every tap load of a warp covers 32 neighbouring pixels (one or two cache lines instead of four) and
+// vertically adjacent taps of the same thread reuse L1 lines.  CTA = 32 columns x C2P_ROWS rows;
+// warp k owns rows 4k .. 4k+3 of every 32-row group.
+#define C2P_ROWS 96
+template <bool HAS_FWD, int PACKED>
+__global__ void __launch_bounds__(256, 5)
+k_flow_stage_packed(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd, const float2 *__restrict__ fwd,
+                    int h, int w, uint2 *__restrict__ out, int32_t *__restrict__ status) {
+    const int frame = blockIdx.z;
+    const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int rbeg = blockIdx.y * C2P_ROWS + (threadIdx.x >> 5) * 4, rend = min((blockIdx.y + 1) * C2P_ROWS, h);
+    if (j >= w || rbeg >= rend) return;
+    const int64_t fbase = (int64_t)frame * h * w;
+    const uint32_t *fg32 = reinterpret_cast<const uint32_t *>(fg) + fbase;
+    const float2 *bf = bwd + fbase;
+    const float2 *ff = HAS_FWD ? fwd + fbase : nullptr;
+    uint2 *op = out + fbase;
+    const float fj = (float)j;
+    int flags = 0;
+    float2 nx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) nx[k] = __ldcs(bf + min(rbeg + k, h - 1) * w + j);          // streamed once: evict first
+    for (int i = rbeg; i < rend; i += 32) {
+        float2 fl[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) fl[k] = nx[k];
+        if (i + 32 < rend) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) nx[k] = __ldcs(bf + min(i + 32 + k, h - 1) * w + j);
+        }
+        VmFlowPx px[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ii = min(i + k, h - 1);
+            px[k] = vm_flow_px<HAS_FWD>(fg32, ff, h, w, ii, j, (float)ii, fj, fl[k], flags);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i + k < rend) op[(i + k) * w + j] = make_uint2(px[k].bgr, vm_pack_alpha<PACKED>(px[k]));
+    }
+    if (HAS_FWD && flags && status) {
+        if (flags & 1) atomicAdd(status + VM_STATUS_INDEX_ERR, 1);
+        if (flags & 2) atomicAdd(status + VM_STATUS_NAN_ERR, 1);
+    }
+}
+
 // stage A of the split C4 pipelines: (n,h,w) uint2 {bgr, alpha code} or, raw_ta, {bgr, TA}
+int g_vm_flow_stage_layout = 0;      // 1: column x 4 rows per thread (k_flow_stage_packed); 0: 4 columns per thread
+
 int vm_launch_flow_stage(const uint8_t *fg, const float *backward, const float *forward, int n, int h, int w,
                          void *packed, int32_t *status, cudaStream_t st, bool raw_ta) {
+    const float2 *b2 = (const float2 *)backward, *f2 = (const float2 *)forward;
+    if (g_vm_flow_stage_layout == 1) {
+        const dim3 grid((w + 31) / 32, (h + C2P_ROWS - 1) / C2P_ROWS, n);
+        uint2 *o = (uint2 *)packed;
+        if (forward && raw_ta) k_flow_stage_packed<true, 2><<<grid, 256, 0, st>>>(fg, b2, f2, h, w, o, status);
+        else if (forward)      k_flow_stage_packed<true, 1><<<grid, 256, 0, st>>>(fg, b2, f2, h, w, o, status);
+        else if (raw_ta)       k_flow_stage_packed<false, 2><<<grid, 256, 0, st>>>(fg, b2, nullptr, h, w, o, status);
+        else                   k_flow_stage_packed<false, 1><<<grid, 256, 0, st>>>(fg, b2, nullptr, h, w, o, status);
+        return vm_check_launch("vm_flow_stage");
+    }
     const int tiles_x = (w + C2_TW - 1) / C2_TW, tiles_y = (h + C2_ROWS - 1) / C2_ROWS;
     const dim3 tiles(tiles_x, tiles_y, n);
-    const float2 *b2 = (const float2 *)backward, *f2 = (const float2 *)forward;
     uint8_t *o = (uint8_t *)packed;
     if (forward && raw_ta) k_flow_warp_mask_bgra<true, 2><<<tiles, 256, 0, st>>>(fg, b2, f2, h, w, tiles_x, tiles_y, o, nullptr, status);
     else if (forward)      k_flow_warp_mask_bgra<true, 1><<<tiles, 256, 0, st>>>(fg, b2, f2, h, w, tiles_x, tiles_y, o, nullptr, status);

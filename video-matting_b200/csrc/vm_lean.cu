@@ -575,7 +575,11 @@ __device__ __forceinline__ void vl_strip_tile(const typename VlSrc<SRC>::elem *_
         float4 o;
         float na;
         const unsigned unc = vl_blend<SRC>(e, fa, fb, fast, b0, b1, b2, o, na);
-        if (unc) o = vl_exact_px<SRC>(src, t0, t1, h, w, bgp, o, na, unc, outside);
+        if (unc) {
+            // t in [n, n + 1]: anything with n <= -2 or n >= size is outside [0, size - 1] (map_coordinates -> 0)
+            if (n0 <= -2 || n0 >= h || n1 <= -2 || n1 >= w) { o = make_float4(b0, b1, b2, 0.f); ++*outside; }
+            else o = vl_exact_px<SRC>(src, t0, t1, h, w, bgp, o, na, unc, outside);
+        }
         __stcs(op, o);                                                 // streamed once: evict first
         bgl += pitch; bgp += w3; op += w;
     }

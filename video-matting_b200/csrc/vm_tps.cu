@@ -7,6 +7,7 @@
 #include <mutex>
 
 int vm_lean_set_option(const char *key, int value);                                // vm_lean.cu
+extern int g_vm_flow_stage_layout;                                                 // vm_flow.cu
 
 // ---------------------------------------------------------------------------------------
 // float64 log for the radial basis U(r) = r^2 log r = 0.5 * r2 * log(r2).
@@ -878,6 +879,7 @@ extern "C" int vm_set_option(const char *key, int value) {
     if (!strcmp(key, "pipe_blocks") && value >= 0) { g_vp_blocks = value; return VM_OK; }
     if (!strcmp(key, "pipe_roles") && value >= 1 && value <= 7) { g_vp_roles = value; return VM_OK; }
     if (!strncmp(key, "lean_", 5) && vm_lean_set_option(key, value) == VM_OK) return VM_OK;
+    if (!strcmp(key, "flow_stage_layout") && (value == 0 || value == 1)) { g_vm_flow_stage_layout = value; return VM_OK; }
     vm_set_error("vm_set_option: unknown option %s=%d", key, value);
     return VM_ERR_ARG;
 }
