@@ -33,6 +33,7 @@ int g_vl_timing = 0;         // 1: bracket the stages of the first chunk of ever
 static cudaEvent_t g_vl_tev[64][5];
 static bool g_vl_tev_ok[64];
 static long long g_vl_launches = 0;   // kernels launched by this library's lean path (bench.py "gpu_launches")
+int g_vl_sub = 0;            // frames per flow-stage / resampling sub-round inside a round (0: the whole round)
 int g_vl_box_cap = 0;        // source-box entries per B2 tile (0: as many as the occupancy target allows)
 int g_vl_minb = 4;           // B2 occupancy target (CTAs of 256 threads per SM: 2, 3 or 4)
 
@@ -829,6 +830,7 @@ int vm_lean_set_option(const char *key, int value) {
     if (!strcmp(key, "lean_b1_warps") && value >= 1 && value <= VL_B1_WARPS_HI) { g_vl_b1_warps = value; return VM_OK; }
     if (!strcmp(key, "lean_b1_dyr") && value >= 0 && value <= 1) { g_vl_b1_dyr = value; return VM_OK; }
     if (!strcmp(key, "lean_timing") && value >= 0 && value <= 1) { g_vl_timing = value; return VM_OK; }
+    if (!strcmp(key, "lean_sub") && value >= 0 && value <= 4096) { g_vl_sub = value; return VM_OK; }
     if (!strcmp(key, "lean_box_cap") && value >= 0 && value <= 16384) { g_vl_box_cap = value; return VM_OK; }
     if (!strcmp(key, "lean_minb") && value >= 2 && value <= 4) { g_vl_minb = value; return VM_OK; }
     if (!strcmp(key, "lean_fine_rows") && value >= 1 && value <= 256) { g_vl_fine_rows = value; return VM_OK; }
@@ -911,16 +913,26 @@ int vm_lean_launch(int mode, const uint8_t *fg, const float *backward, const flo
         }
         if (overlap) cudaEventRecord(g_vl_ev_ready[dev][par], side);
         if (tev) cudaEventRecord(g_vl_tev[dev][2], st);
-        g_vl_launches += 2 + (mode != 0 ? 1 : 0) + 1;
-        // ---- caller's stream: flow stage, then resampling + composite ------------------------------
-        if (mode != 0) {
-            rc = vm_launch_flow_stage(fg + f0 * px * 4, backward + f0 * px * 2, (mode == 2 && forward) ? forward + f0 * px * 2 : nullptr,
-                                      m, h, w, packed, status, st, true);
-            if (rc != VM_OK) return rc;
-        }
+        g_vl_launches += 2;
+        // ---- caller's stream: flow stage, then resampling + composite, in sub-rounds of `lean_sub` frames
+        // (0 = the whole round): small sub-rounds keep the packed intermediate in L2 between the two kernels
         if (overlap) cudaStreamWaitEvent(st, g_vl_ev_ready[dev][par], 0);
-        if (tev) cudaEventRecord(g_vl_tev[dev][3], st);
-        float4 *o4 = reinterpret_cast<float4 *>(out) + f0 * px;
+        const int sub = (g_vl_sub > 0 && g_vl_sub < m && !tev) ? g_vl_sub : m;
+        const int64_t tiles_per_frame = (int64_t)grid.x * grid.y;
+        for (int fs = 0; fs < m; fs += sub) {
+            const int ms = (m - fs < sub) ? m - fs : sub;
+            const int ff0 = f0 + fs;
+            if (mode != 0) {
+                rc = vm_launch_flow_stage(fg + ff0 * px * 4, backward + ff0 * px * 2, (mode == 2 && forward) ? forward + ff0 * px * 2 : nullptr,
+                                          ms, h, w, packed, status, st, true);
+                if (rc != VM_OK) return rc;
+                g_vl_launches += 1;
+            }
+            if (tev) cudaEventRecord(g_vl_tev[dev][3], st);
+            const dim3 sgrid(grid.x, grid.y, ms);
+            const double2 *Ts = T + (int64_t)fs * nx * ny;
+            const VlTileBox *bs = boxes + fs * tiles_per_frame;
+            float4 *o4 = reinterpret_cast<float4 *>(out) + ff0 * px;
 #define VL_FINE(S, MB)                                                                                              \
     do {                                                                                                            \
         static size_t attr_set[64];                                                                                 \
@@ -929,12 +941,16 @@ int vm_lean_launch(int mode, const uint8_t *fg, const float *backward, const flo
             if (e != cudaSuccess) { vm_set_error("vm_lean: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VM_ERR_CUDA; } \
             attr_set[dev & 63] = fine_smem;                                                                         \
         }                                                                                                           \
-        k_lean_fine<S, MB><<<grid, block, fine_smem, st>>>(S ? (const void *)packed : (const void *)(fg + f0 * px * 4), \
-                                                                    bg, n_bg, f0, T, nx, ny, rows, cols, h, w, rpt, boxes, o4, status); \
+        k_lean_fine<S, MB><<<sgrid, block, fine_smem, st>>>(S ? (const void *)packed : (const void *)(fg + ff0 * px * 4), \
+                                                            bg, n_bg, ff0, Ts, nx, ny, rows, cols, h, w, rpt, bs, o4, status); \
     } while (0)
-        if (mode != 0) { if (g_vl_minb == 4) VL_FINE(1, 4); else if (g_vl_minb == 3) VL_FINE(1, 3); else VL_FINE(1, 2); }
-        else           { if (g_vl_minb == 4) VL_FINE(0, 4); else if (g_vl_minb == 3) VL_FINE(0, 3); else VL_FINE(0, 2); }
+            if (mode != 0) { if (g_vl_minb == 4) VL_FINE(1, 4); else if (g_vl_minb == 3) VL_FINE(1, 3); else VL_FINE(1, 2); }
+            else           { if (g_vl_minb == 4) VL_FINE(0, 4); else if (g_vl_minb == 3) VL_FINE(0, 3); else VL_FINE(0, 2); }
 #undef VL_FINE
+            g_vl_launches += 1;
+            rc = vm_check_launch(what);
+            if (rc != VM_OK) return rc;
+        }
         rc = vm_check_launch(what);
         if (rc != VM_OK) return rc;
         if (tev) cudaEventRecord(g_vl_tev[dev][4], st);
