@@ -1,0 +1,64 @@
+"""Device-resident throughput of the BASELINE.json configs 2-4 (one GPU): frames/s, algorithmic GB/s and
+fraction of the measured HBM peak.  python scripts/bench_configs.py [iters] > profiles/rNN_configs.json"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import torch
+import __graft_entry__ as ge
+import bench
+import vm_oracle as O
+
+iters = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+vm = ge.load_package()
+P = vm.pipeline
+dev = torch.device("cuda", 0)
+peak, peak_src = bench.measured_peak()
+
+
+def timed(fn):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def case(name, which, h, w, n, n_ctrl, bpp):
+    fg, fb, ff, bg = bench.make_clip(torch, 77, n, h, w, dev)
+    st = vm._native.new_status(dev)
+    if which == "c2":
+        ob = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+        oa = torch.empty((n, h, w), dtype=torch.float32, device=dev)
+        ms = timed(lambda: P.flow_warp_mask(fg, fb, ff, out_bgr=ob, out_alpha=oa, status=st))
+    else:
+        grids = [O.synth_grids(5000 + k, h, w, n_ctrl) for k in range(n)]
+        ctrl, coef = P.solve_grids(grids, dev)
+        out = torch.empty((n, h, w, 4), dtype=torch.float32, device=dev)
+        if which == "c3":
+            ms = timed(lambda: P.tps_composite(fg, bg, ctrl, coef, out=out, status=st))
+        else:
+            ms = timed(lambda: P.flow_tps_composite(fg, fb, ff, bg, ctrl, coef, out=out, status=st))
+    gbs = bpp * h * w * n / (ms / 1e3) / 1e9
+    rec = {"config": name, "height": h, "width": w, "frames_per_launch": n, "control_points": n_ctrl * n_ctrl if which != "c2" else None,
+           "ms_per_launch": ms, "frames_per_s": n / (ms / 1e3), "algorithmic_bytes_per_px": bpp, "algorithmic_GBps": gbs,
+           "frac_of_hbm_peak": gbs / peak, "working_set_MB": bpp * h * w * n / 1e6}
+    print(json.dumps(rec), flush=True)
+    del fg, fb, ff, bg
+    torch.cuda.empty_cache()
+
+
+print(json.dumps({"peak_GBps": peak, "peak_source": peak_src, "iters": iters, "gpu": torch.cuda.get_device_name(0)}))
+case("C2 flow warp + fwd/bwd mask, 1080p x 64", "c2", 1080, 1920, 64, 0, 27)
+case("C3 TPS (16 control points) + composite, 512x512 x 256", "c3", 512, 512, 256, 4, 23)
+case("C3 TPS (25 control points) + composite, 1080p x 64", "c3", 1080, 1920, 64, 5, 23)
+case("C4 flow warp + mask + TPS + composite, 1080p x 64 (headline)", "c4", 1080, 1920, 64, 5, 39)
+case("C4 flow warp + mask + TPS + composite, 4K x 16", "c4", 2160, 3840, 16, 5, 39)

@@ -411,7 +411,7 @@ class HostClipRunner:
     copies to be asynchronous; pageable NumPy arrays work but serialise.
     """
 
-    def __init__(self, h, w, chunk=8, device=None):
+    def __init__(self, h, w, chunk=4, device=None):
         N.require_cuda()
         self.h, self.w, self.chunk = h, w, chunk
         self.device = torch.device(device if device is not None else "cuda")
@@ -440,11 +440,7 @@ class HostClipRunner:
         a list of n (grid, deformed grid) pairs, ``out`` a host (n,H,W,4) float32 buffer."""
         fg, backward, forward, bg, out = map(self._as_tensor, (fg, backward, forward, bg, out))
         n = fg.shape[0]
-        ctrl_all = np.stack([np.asarray(d, dtype=np.float64) for (_, d) in grids])
-        coef_all = np.stack([tps_solve(d, g) for (g, d) in grids])
-        ctrl_d = torch.from_numpy(ctrl_all).to(self.device, non_blocking=True)
-        coef_d = torch.from_numpy(coef_all).to(self.device, non_blocking=True)
-        self.h2d_bytes = ctrl_all.nbytes + coef_all.nbytes
+        self.h2d_bytes = 0
         self.d2h_bytes = 0
         cur = torch.cuda.current_stream(self.device)
         for s in (self.s_in, self.s_run, self.s_out):
@@ -460,13 +456,18 @@ class HostClipRunner:
                     slot[key][:m].copy_(src[lo:hi], non_blocking=True)
                     self.h2d_bytes += src[lo:hi].numel() * src.element_size()
                 slot["loaded"].record(self.s_in)
+            # host TPS solve of this chunk (reference tps.py:113-119) while its frames are on the wire
+            ctrl_h = np.stack([np.asarray(d, dtype=np.float64) for (_, d) in grids[lo:hi]])
+            coef_h = np.stack([tps_solve(d, g) for (g, d) in grids[lo:hi]])
+            self.h2d_bytes += ctrl_h.nbytes + coef_h.nbytes
             with torch.cuda.stream(self.s_run):
+                ctrl_d = torch.from_numpy(ctrl_h).to(self.device, non_blocking=True)
+                coef_d = torch.from_numpy(coef_h).to(self.device, non_blocking=True)
                 self.s_run.wait_event(slot["loaded"])
                 if ci >= 2:
                     self.s_run.wait_event(slot["drained"])        # output of chunk ci-2 copied out
                 flow_tps_composite(slot["fg"][:m], slot["fb"][:m], slot["ff"][:m], slot["bg"][:m],
-                                   ctrl_d[lo:hi], coef_d[lo:hi], plan=self.plan, out=slot["out"][:m],
-                                   status=self.status)
+                                   ctrl_d, coef_d, plan=self.plan, out=slot["out"][:m], status=self.status)
                 slot["computed"].record(self.s_run)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(slot["computed"])
@@ -481,7 +482,7 @@ class HostClipRunner:
 _runners = {}
 
 
-def flow_tps_composite_host(fg, backward, forward, bg, grids, out=None, chunk=8):
+def flow_tps_composite_host(fg, backward, forward, bg, grids, out=None, chunk=4):
     """NumPy/host-tensor front end of the C4 pipeline (H2D, kernels, D2H inside).  Returns the
     host (n,H,W,4) float32 result; synchronises before returning."""
     n, h, w = fg.shape[:3]
