@@ -10,9 +10,9 @@
 //             (tps.py:34) on the packed intermediate / the BGRA frame, composite (reader.py:72-79)
 //             -> out (n,h,w) float4 {B, G, R, alpha'}
 //
-// B1 is bound by the float64 pipe: 9 DP instructions per (coarse point, control point) - the
-// log comes from a 31-octave x 256-entry {1/c, log c} table staged in shared memory by a bulk
-// async copy (TMA, 127 KB per persistent CTA) plus a degree-3 minimax polynomial.  B2 is bound
+// B1 is bound by the float64 pipe: 10 DP instructions per (coarse point, control point) - the
+// log comes from a 31-octave x 64-entry {1/c, log c} table staged in shared memory by a bulk
+// async copy (TMA, 32 KB per persistent CTA) plus a degree-4 minimax polynomial.  B2 is bound
 // by instruction issue: coordinates are the only float64 work (6 DP per pixel thanks to
 // rolling column-interpolated coarse rows); weights, colour blending and alpha are integer
 // fixed point (2^-30 weights), with an exact float64 re-evaluation of the rare samples whose
@@ -44,21 +44,22 @@ int g_vl_minb = 4;           // B2 occupancy target (CTAs of 256 threads per SM:
 // ---------------------------------------------------------------------------------------
 #define VL_EMIN (-6)
 #define VL_EMAX 25
-#define VL_BITS 5
+#define VL_BITS 6
 #define VL_TAB_N ((VL_EMAX - VL_EMIN) << VL_BITS)
 #define VL_TAB_BYTES (VL_TAB_N * 16)
 #define VL_HI_MIN ((1023 + VL_EMIN) << 20)
 #define VL_HI_MAX ((1023 + VL_EMAX) << 20)
 
-// minimax fit of log1p(t)/t on |t| <= 2^-6 (max error of t*q(t): 1.03e-15 absolute).  32 entries per
+// minimax fit of log1p(t)/t on |t| <= 2^-7 (max error of t*q(t): 2.4e-15 absolute).  64 entries per
 // octave keep the table index of neighbouring coarse columns within one entry of each other for every
-// control point further than ~190 px away, so a quarter-warp reads consecutive entries: no bank conflicts.
-#define VL_Q5 (-0.1667124531815725708429)
-#define VL_Q4 0.2000523271261866307
-#define VL_Q3 (-0.2499999958078498099121)
-#define VL_Q2 0.3333333285423420934598
-#define VL_Q1 (-0.5000000000000568604014)
-#define VL_Q0 1.000000000000064982787
+// control point further than ~370 px away, so a quarter-warp reads consecutive entries: few bank
+// conflicts.  Measured alternatives: 256 entries + degree 3 (9 DP, bound by shared-memory bank conflicts),
+// 32 entries + degree 5 (11 DP, 5 % slower than this one).
+#define VL_Q4 0.2000108996732607315039
+#define VL_Q3 (-0.2500127162639107632768)
+#define VL_Q2 0.3333333331670152271109
+#define VL_Q1 (-0.4999999998059626206361)
+#define VL_Q0 1.0
 
 __device__ double2 g_vl_tab[VL_TAB_N];
 
@@ -131,8 +132,7 @@ __device__ __forceinline__ double vl_u_fast(double r2, uint32_t tab_adj) {
     double ex, ey;
     asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ex), "=d"(ey) : "r"(addr));
     const double t = fma(r2, ex, -1.0);
-    double q = fma(t, VL_Q5, VL_Q4);
-    q = fma(t, q, VL_Q3);
+    double q = fma(t, VL_Q4, VL_Q3);
     q = fma(t, q, VL_Q2);
     q = fma(t, q, VL_Q1);
     q = fma(t, q, VL_Q0);
@@ -627,15 +627,22 @@ __device__ __noinline__ void vl_strip_generic(const typename VlSrc<SRC>::elem *_
     }
 }
 
-// one warp polls the mbarrier (phase 0), the CTA barrier releases everybody else without spinning
-__device__ __forceinline__ void vl_cta_wait(uint32_t bar, bool poll) {
+// one warp polls the mbarrier (phase 0), the CTA barrier releases everybody else without spinning;
+// every thread then observes the completed phase itself (one try_wait that succeeds at once), which is
+// what orders the async-proxy writes of the bulk copies before its own shared-memory reads
+__device__ __forceinline__ void vl_cta_wait(uint32_t bar, bool poll, bool used) {
+    uint32_t ok = 0;
     if (poll) {
-        uint32_t ok = 0;
         while (!ok)
             asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
                          : "=r"(ok) : "r"(bar) : "memory");
     }
     __syncthreads();
+    if (used && !poll) {
+        while (!ok)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(bar) : "memory");
+    }
 }
 
 __device__ __forceinline__ void vl_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
@@ -795,7 +802,7 @@ k_lean_fine(const void *__restrict__ src_all, const uint8_t *__restrict__ bg, in
             }
         }
     }
-    vl_cta_wait(bar0, tid < 32 && (bg_sm || boxed));
+    vl_cta_wait(bar0, tid < 32 && (bg_sm || boxed), bg_sm || boxed);
 
     const unsigned char *bgl = S.bgt + (strip0 * VL_FW + (int)threadIdx.x) * 3;
     const double2 *Csj = S.Cs + threadIdx.x;
