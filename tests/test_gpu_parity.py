@@ -522,3 +522,73 @@ def test_4k_identity_property(vm):
     o = out[0].cpu().numpy()
     assert close(o[inner][..., :3], ref[inner], 1e-5)
     assert close(o[inner][..., 3], (frame[..., 3] / 255.)[inner], 1e-6)
+
+
+# ------------------------------------------------------------------------------- edge cases
+
+def test_fused_empty_clip(vm):
+    """n = 0 frames: every fused entry point returns an empty result and launches nothing."""
+    h, w = 32, 48
+    P = vm.pipeline
+    e = lambda *s, dt=torch.uint8: torch.empty(s, dtype=dt, device="cuda")
+    bgr, alpha, _ = P.flow_warp_mask(e(0, h, w, 4), e(0, h, w, 2, dt=torch.float32), e(0, h, w, 2, dt=torch.float32))
+    assert bgr.shape == (0, h, w, 3) and alpha.shape == (0, h, w)
+    ctrl, coef = e(0, 25, 2, dt=torch.float64), e(0, 28, 2, dt=torch.float64)
+    out, _ = P.flow_tps_composite(e(0, h, w, 4), e(0, h, w, 2, dt=torch.float32), e(0, h, w, 2, dt=torch.float32),
+                                  e(1, h, w, 3), ctrl, coef)
+    out3, _ = P.tps_composite(e(0, h, w, 4), e(1, h, w, 3), ctrl, coef)
+    assert out.shape == (0, h, w, 4) and out3.shape == (0, h, w, 4)
+    torch.cuda.synchronize()
+
+
+def test_fused_wild_flows(vm):
+    """Flows of sigma 50 / 500 px (most taps outside the frame, wrapped / clamped mask look-ups) through the
+    fused C2 and C4 paths against the oracle; then NaN / Inf / 3e9 components: cv2.remap reads 0 there, and
+    correct_alpha would raise on the NaN / Inf ones - those pixels are counted in the status block."""
+    h, w, n = 72, 100, 2
+    P = vm.pipeline
+    rng = np.random.default_rng(5)
+    frames, _, _, grids, bgs = _lean_case(h, w, n, 5, seed=610)
+    for sigma in (50.0, 500.0):
+        fb = rng.normal(0, sigma, (n, h, w, 2)).astype(np.float32)
+        ff = rng.normal(0, sigma, (n, h, w, 2)).astype(np.float32)
+        ok = True
+        try:
+            refs = [O.pipeline_c4(frames[k], fb[k], ff[k], grids[k], bgs[k]) for k in range(n)]
+        except IndexError:
+            ok = False                                     # a look-up below -H / -W: the reference raises
+        ctrl, coef = P.solve_grids(grids)
+        bgr, alpha, st2 = P.flow_warp_mask(dev(frames), dev(fb), dev(ff))
+        out, st4 = P.flow_tps_composite(dev(frames), dev(fb), dev(ff), dev(bgs), ctrl, coef)
+        assert (int(st2[0]) == 0) == ok and (int(st4[0]) == 0) == ok
+        if ok:
+            for k in range(n):
+                rb, ra = O.pipeline_c2(frames[k], fb[k], ff[k])
+                assert np.array_equal(bgr[k].cpu().numpy(), rb) and close(alpha[k].cpu().numpy(), ra, 1e-6)
+                got = out[k].cpu().numpy()
+                assert close(got[..., 3], refs[k][1], 1e-6)
+                assert np.count_nonzero(~np.isclose(got[..., :3], refs[k][0], rtol=RTOL, atol=1e-5)) <= 1
+    fb = rng.normal(0, 3, (n, h, w, 2)).astype(np.float32)
+    ff = (-fb).copy()
+    fb[0, 5, 7, 0] = np.nan; fb[0, 9, 11, 1] = np.inf; fb[1, 20, 30, 0] = -np.inf; fb[1, 40, 50, 1] = 3e9
+    bgr, alpha, st = P.flow_warp_mask(dev(frames), dev(fb), dev(ff))
+    assert int(st[1]) == 3 and int(st[0]) == 0, "3 NaN/Inf pixels (the reference raises ValueError); +3e9 only clamps"
+    for (k, i, j) in ((0, 5, 7), (0, 9, 11), (1, 20, 30), (1, 40, 50)):
+        assert bgr[k, i, j].sum().item() == 0 and alpha[k, i, j].item() == 0.0      # cv2.remap: NaN / Inf / huge -> 0
+    clean = np.ones((n, h, w), bool)
+    for (k, i, j) in ((0, 5, 7), (0, 9, 11), (1, 20, 30), (1, 40, 50)):
+        clean[k, i, j] = False
+    # the same through the C4 pipeline: counted, and the output stays finite
+    ctrl, coef = P.solve_grids(grids)
+    out, st4 = P.flow_tps_composite(dev(frames), dev(fb), dev(ff), dev(bgs), ctrl, coef)
+    assert int(st4[1]) == 3 and int(st4[0]) == 0 and bool(torch.isfinite(out).all())
+    # NaN in the forward flow where a pixel looks it up, and a look-up below -H: ValueError / IndexError
+    fb2 = np.zeros((1, h, w, 2), np.float32); ff2 = np.zeros((1, h, w, 2), np.float32)
+    ff2[0, 10, 10, 0] = np.nan
+    fb2[0, 30, 30, 1] = -(h + 40.0)
+    _, _, st = P.flow_warp_mask(dev(frames[:1]), dev(fb2), dev(ff2))
+    assert int(st[1]) == 1 and int(st[0]) == 1
+    fb_ok = np.where(np.isfinite(fb) & (np.abs(fb) < 1e9), fb, 0).astype(np.float32)
+    for k in range(n):
+        rb, ra = O.pipeline_c2(frames[k], fb_ok[k], ff[k])
+        assert np.array_equal(bgr[k].cpu().numpy()[clean[k]], rb[clean[k]])

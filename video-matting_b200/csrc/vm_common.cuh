@@ -244,7 +244,8 @@ __device__ __forceinline__ VmFlowPx vm_flow_px(const uint32_t *__restrict__ fg32
                                                int &flags) {
     VmFlowPx o;
     const float mx = __fadd_rn(fj, fb.x), my = __fadd_rn(fi, fb.y);
-    if (fmaxf(fabsf(mx), fabsf(my)) < 60000.f) {                 // false for NaN
+    // fmaxf() returns the non-NaN operand, so each component is tested on its own: false for NaN
+    if ((fabsf(mx) < 60000.f) & (fabsf(my) < 60000.f)) {
         const int SX = vm_fix5_fast(mx), SY = vm_fix5_fast(my);
         const int ix = SX >> 5, iy = SY >> 5, fx = SX & 31, fy = SY & 31;
         uint32_t s00, s01, s10, s11;
@@ -277,7 +278,7 @@ __device__ __forceinline__ VmFlowPx vm_flow_px(const uint32_t *__restrict__ fg32
             if ((unsigned)j0 < (unsigned)W && (unsigned)i0 < (unsigned)H) {
                 const float2 ff = __ldg(fwd + (i0 * W + j0));
                 const float c = __fadd_rn(ff.x, (float)j0), d = __fadd_rn(ff.y, (float)i0);
-                if (fmaxf(fabsf(c), fabsf(d)) < 3.0e38f) {
+                if ((fabsf(c) < 3.0e38f) & (fabsf(d) < 3.0e38f)) {              // finite, and false for NaN
                     // min(trunc(c), W-1) - j, in float: exact for |.| < 2^24, monotone beyond
                     const float dj = __fadd_rn(fminf(truncf(c), (float)(W - 1)), -fj);
                     const float di = __fadd_rn(fminf(truncf(d), (float)(H - 1)), -fi);

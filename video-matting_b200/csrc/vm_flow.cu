@@ -316,6 +316,7 @@ int vm_launch_flow_stage(const uint8_t *fg, const float *backward, const float *
 extern "C" int vm_flow_warp_mask_bgra(const uint8_t *fg, const float *backward, const float *forward,
                                       int n, int h, int w, uint8_t *out_bgr, float *out_alpha,
                                       int32_t *status, void *stream) {
+    if (n == 0) return VM_OK;                                          // empty clip
     VM_REQUIRE(fg && backward && out_bgr && out_alpha, "null pointer");
     VM_REQUIRE(n >= 0 && h > 0 && w > 0 && h <= 32767 && w <= 32767, "bad size");
     if (n == 0) return VM_OK;

@@ -193,7 +193,7 @@ template <bool MASK>
 __device__ __forceinline__ void vp_flow_issue(const uint32_t *__restrict__ fg32, const float2 *__restrict__ fwd,
                                               int H, int W, float fi, float fj, float2 fb, VpTaps &t) {
     const float mx = __fadd_rn(fj, fb.x), my = __fadd_rn(fi, fb.y);
-    bool ok = fmaxf(fabsf(mx), fabsf(my)) < 60000.f;              // false for NaN
+    bool ok = (fabsf(mx) < 60000.f) & (fabsf(my) < 60000.f);      // each component on its own: false for NaN
     const int SX = vm_fix5_fast(mx), SY = vm_fix5_fast(my);
     const int ix = SX >> 5, iy = SY >> 5;
     t.fxy = (uint32_t)(SX & 31) | ((uint32_t)(SY & 31) << 8);
@@ -228,7 +228,7 @@ __device__ __forceinline__ float4 vp_flow_finish(const VpTaps &t, const uint32_t
     int masked = 0;
     if (MASK) {
         const float c = __fadd_rn(t.ff.x, t.cj0), d = __fadd_rn(t.ff.y, t.ci0);
-        ok = ok && fmaxf(fabsf(c), fabsf(d)) < 3.0e38f;
+        ok = ok && (fabsf(c) < 3.0e38f) && (fabsf(d) < 3.0e38f);
         // min(trunc(c), W-1) - j in float: exact for |.| < 2^24, monotone beyond (flow.py:47-48)
         const float dj = __fadd_rn(fminf(truncf(c), (float)(W - 1)), -fj);
         const float di = __fadd_rn(fminf(truncf(d), (float)(H - 1)), -fi);

@@ -1005,6 +1005,7 @@ extern "C" int vm_tps_composite_bgra(const uint8_t *fg, const uint8_t *bg, int n
                                      const double *coef, int N, int nx, int ny, double step_x, double step_y,
                                      const vm_axis_entry *rows, const vm_axis_entry *cols, int n, int h, int w,
                                      float *out, void *scratch, int32_t *status, void *stream) {
+    if (n == 0) return VM_OK;                                          // empty clip: nothing to read, nothing to launch
     VM_REQUIRE(fg && bg && ctrl && coef && rows && cols && out, "null pointer");
     VM_REQUIRE(n >= 0 && n < 65536 && h > 0 && w > 0 && n_bg >= 1 && nx >= 1 && ny >= 1 && N >= 1 && N <= VM_TPS_MAX_N, "bad size");
     return launch_fused(false, fg, nullptr, nullptr, bg, n_bg, ctrl, coef, N, nx, ny, step_x, step_y, rows, cols,
@@ -1016,6 +1017,7 @@ extern "C" int vm_flow_tps_composite_bgra(const uint8_t *fg, const float *backwa
                                           int N, int nx, int ny, double step_x, double step_y,
                                           const vm_axis_entry *rows, const vm_axis_entry *cols, int n, int h,
                                           int w, float *out, void *scratch, int32_t *status, void *stream) {
+    if (n == 0) return VM_OK;
     VM_REQUIRE(fg && backward && bg && ctrl && coef && rows && cols && out, "null pointer");
     VM_REQUIRE(n >= 0 && n < 65536 && h > 0 && w > 0 && n_bg >= 1 && nx >= 1 && ny >= 1 && N >= 1 && N <= VM_TPS_MAX_N, "bad size");
     return launch_fused(true, fg, backward, forward, bg, n_bg, ctrl, coef, N, nx, ny, step_x, step_y, rows, cols,

@@ -320,7 +320,7 @@ def _fused_scratch(lib, n, plan, scratch, device):
     pipeline (a few frames, L2 resident) or the coarse transform of the gather variant.  One
     buffer per device is cached; work on one stream at a time per device or pass ``scratch``."""
     h, w = plan.region[2], plan.region[3]
-    need = lib.vm_fused_scratch_bytes(n, h, w)
+    need = max(int(lib.vm_fused_scratch_bytes(n, h, w)), 256)
     if scratch is None or scratch.numel() * scratch.element_size() < need:
         key = (device.index if device.index is not None else torch.cuda.current_device())
         cached = _scratch_cache.get(key)
