@@ -420,10 +420,11 @@ def test_lean_partition_independent(vm):
     base, st0 = P.flow_tps_composite(*args)
     base3, _ = P.tps_composite(args[0], args[3], ctrl, coef)
     assert int(st0[4]) < 4, "most tiles of a mild grid must take the shared-memory box path"
-    defaults = {"lean_chunk": 64, "lean_rb": 0, "lean_minb": 4, "lean_box_cap": 0, "lean_fine_rows": 8}
+    defaults = {"lean_chunk": 64, "lean_rb": 0, "lean_minb": 4, "lean_box_cap": 0, "lean_fine_rows": 8, "lean_persist": 0,
+                "lean_sub": 0}
     try:
-        for key, values in (("lean_chunk", (1, 2, 3)), ("lean_rb", (4, 16, 32)), ("lean_minb", (2, 3)),
-                            ("lean_box_cap", (64,)), ("lean_fine_rows", (3, 5))):
+        for key, values in (("lean_chunk", (1, 2, 3)), ("lean_rb", (4, 16, 32)), ("lean_box_cap", (64,)), ("lean_sub", (2,)),
+                            ("lean_minb", (2, 3)), ("lean_fine_rows", (3, 5)), ("lean_persist", (1,)), ("lean_box_cap", (64,))):
             for v in values:
                 Nt.set_option(key, v)
                 out, st = P.flow_tps_composite(*args)
@@ -431,7 +432,8 @@ def test_lean_partition_independent(vm):
                 assert torch.equal(out, base) and torch.equal(out3, base3), f"{key}={v} changes the result"
                 if key == "lean_box_cap":
                     assert int(st[4]) > 0, "box capacity 64 must push tiles onto the gather path"
-            Nt.set_option(key, defaults[key])
+            if key != "lean_persist":                      # the per-tile kernel stays selected for its own options
+                Nt.set_option(key, defaults[key])
     finally:
         for key, v in defaults.items():
             Nt.set_option(key, v)

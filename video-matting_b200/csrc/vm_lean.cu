@@ -33,6 +33,7 @@ int g_vl_timing = 0;         // 1: bracket the stages of the first chunk of ever
 static cudaEvent_t g_vl_tev[64][5];
 static bool g_vl_tev_ok[64];
 static long long g_vl_launches = 0;   // kernels launched by this library's lean path (bench.py "gpu_launches")
+int g_vl_persist = 0;        // 1: persistent double-buffered resampling kernel (k_lean_fine_p); 0: one CTA per tile (k_lean_fine)
 int g_vl_sub = 0;            // frames per flow-stage / resampling sub-round inside a round (0: the whole round)
 int g_vl_box_cap = 0;        // source-box entries per B2 tile (0: as many as the occupancy target allows)
 int g_vl_minb = 4;           // B2 occupancy target (CTAs of 256 threads per SM: 2, 3 or 4)
@@ -87,7 +88,11 @@ static int vl_init(int *dev_out) {
             t.y = (double)((long double)e * 0.693147180559945309417232121458L - logl((long double)inv));
         }
     cudaError_t err = cudaMemcpyToSymbol(g_vl_tab, tab, sizeof(tab));
-    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&g_vl_side[dev], cudaStreamNonBlocking);
+    if (err == cudaSuccess) {                      // side stream at the highest priority: its persistent CTAs must get their
+        int lo = 0, hi = 0;                        // slice of every SM as soon as CTAs of the caller's stream retire
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        err = cudaStreamCreateWithPriority(&g_vl_side[dev], cudaStreamNonBlocking, hi);
+    }
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&g_vl_ev_fork[dev], cudaEventDisableTiming);
     for (int k = 0; k < 2 && err == cudaSuccess; ++k) {
         err = cudaEventCreateWithFlags(&g_vl_ev_ready[dev][k], cudaEventDisableTiming);
@@ -120,9 +125,11 @@ struct __align__(16) VlWarpSmem {
 
 struct __align__(16) VlCoarseSmem {
     double2 tab[VL_TAB_N];
-    VlWarpSmem w[VL_B1_WARPS_HI];
     unsigned long long bar;
+    unsigned long long pad;
+    VlWarpSmem w[1];                               // one slice per launched warp (dynamic shared memory)
 };
+static inline size_t vl_coarse_smem_bytes(int warps) { return sizeof(VlCoarseSmem) + (size_t)(warps - 1) * sizeof(VlWarpSmem); }
 
 __device__ __forceinline__ uint32_t vl_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -362,7 +369,7 @@ static int vl_launch_coarse(const double *ctrl, const double *coef, int N, int n
     const int warps_cta = g_vl_b1_dyr ? (g_vl_b1_warps < VL_B1_WARPS ? g_vl_b1_warps : VL_B1_WARPS) : g_vl_b1_warps;
     const int rb = vl_pick_rb(n, nx, ny, ctas);
     const int nbands = (nx + rb - 1) / rb, ncb = (ny + 31) / 32;
-    const size_t smem = sizeof(VlCoarseSmem);
+    const size_t smem = vl_coarse_smem_bytes(VL_B1_WARPS_HI);             // attribute: the largest launch
 #define VL_LAUNCH(NN, DY)                                                                                           \
     do {                                                                                                          \
         static bool attr_set[64];                                                                                 \
@@ -373,7 +380,7 @@ static int vl_launch_coarse(const double *ctrl, const double *coef, int N, int n
             if (e != cudaSuccess) { vm_set_error("vm_lean: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VM_ERR_CUDA; } \
             attr_set[dev & 63] = true;                                                                            \
         }                                                                                                         \
-        k_lean_coarse<NN, DY><<<ctas, warps_cta * 32, smem, st>>>(ctrl, coef, N, n, nx, ny, step_x, step_y, rb, nbands, ncb, T, counter); \
+        k_lean_coarse<NN, DY><<<ctas, warps_cta * 32, vl_coarse_smem_bytes(warps_cta), st>>>(ctrl, coef, N, n, nx, ny, step_x, step_y, rb, nbands, ncb, T, counter); \
     } while (0)
     if (g_vl_b1_dyr) {
         switch (N) {
@@ -819,6 +826,250 @@ k_lean_fine(const void *__restrict__ src_all, const uint8_t *__restrict__ bg, in
 }
 
 // ---------------------------------------------------------------------------------------
+// stage B2, persistent variant (default): the same tile work as k_lean_fine, but every CTA walks a
+// contiguous run of 64 x 32 tiles and the bulk async copies of tile i+1 (coarse window, source box,
+// background rows, axis entries) are in flight while tile i is resampled, so no warp waits for DRAM
+// in steady state.  512 threads (64 columns x 8 strips of 4 rows), 2 CTAs per SM, double-buffered
+// box / background / axis entries, single-buffered coarse window (refilled as soon as the tile's
+// column-interpolated rows have been formed).  Everything a tile needs to issue its copies comes from
+// one 32-byte record written by k_lean_recs.
+// ---------------------------------------------------------------------------------------
+#define VL_PS 8                                    // strips per CTA
+#define VL_PR 4                                    // rows per thread and tile
+#define VL_PTH (VL_PS * VL_PR)                     // tile height (32)
+static_assert(VL_PTH <= VL_FROWS_MAX, "tile height");
+
+// rmin/bh/cmin/bw: source box (bw = 0: taps from global memory); kr0/nkr/kc0/nkc: coarse window
+// (nkr = 0: axis tables are not monotone windows -> fully generic tile)
+struct __align__(16) VlTileRec { int rmin, bh, cmin, bw, kr0, nkr, kc0, nkc; };
+
+struct __align__(16) VlPSmem {
+    double2 T[VL_TR * VL_TC];
+    double2 Cs[VL_TR * VL_FW];
+    unsigned char bgt[2][VL_PTH * VL_FW * 3];
+    vm_axis_entry rows[2][VL_PTH];
+    vm_axis_entry cols[2][VL_FW];
+    VlTileRec rec[2];
+    unsigned long long bar[2];
+    uint2 box[2];                                  // 2 x box_cap entries (dynamic)
+};
+static inline size_t vl_p_smem_bytes(int box_cap) { return sizeof(VlPSmem) + (size_t)(2 * box_cap - 2) * sizeof(uint2); }
+
+template <int SRC>
+__global__ void __launch_bounds__(128)
+k_lean_recs(const double2 *__restrict__ T, int nx, int ny, const vm_axis_entry *__restrict__ rows,
+            const vm_axis_entry *__restrict__ cols, int h, int w, int tiles_x, int tiles_y, int n_tiles,
+            int box_cap, VlTileRec *__restrict__ recs) {
+    constexpr int EPV = 16 / (int)sizeof(typename VlSrc<SRC>::elem);
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (t >= n_tiles) return;
+    const int per = tiles_x * tiles_y;
+    const int frame = t / per, tl = t - frame * per;
+    const int ty = tl / tiles_x, tx = tl - ty * tiles_x;
+    const int I0 = ty * VL_PTH, J0 = tx * VL_FW;
+    const int th = min(VL_PTH, h - I0), tw = min(VL_FW, w - J0);
+    const vm_axis_entry r0 = vm_ld_axis(rows + I0), r1 = vm_ld_axis(rows + I0 + th - 1);
+    const vm_axis_entry c0 = vm_ld_axis(cols + J0), c1 = vm_ld_axis(cols + J0 + tw - 1);
+    const int kr0 = r0.i0, kr1 = max(r1.i1, r1.i0), kc0 = c0.i0, kc1 = max(c1.i1, c1.i0);
+    const int nkr = kr1 - kr0 + 1, nkc = kc1 - kc0 + 1;
+    VlTileRec rec = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool ok = nkr >= 1 && nkc >= 1 && nkr <= VL_TR && nkc <= VL_TC && kr0 >= 0 && kr1 < nx && kc0 >= 0 && kc1 < ny;
+    if (ok) {                                      // every (i0, i1) of the tile inside the window
+        for (int i = lane; i < th; i += 32) {
+            const vm_axis_entry e = vm_ld_axis(rows + I0 + i);
+            ok = ok && e.i0 >= kr0 && e.i0 <= kr1 && e.i1 >= kr0 && e.i1 <= kr1;
+        }
+        for (int j = lane; j < tw; j += 32) {
+            const vm_axis_entry e = vm_ld_axis(cols + J0 + j);
+            ok = ok && e.i0 >= kc0 && e.i0 <= kc1 && e.i1 >= kc0 && e.i1 <= kc1;
+        }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (ok) {
+        rec.kr0 = kr0; rec.nkr = nkr; rec.kc0 = kc0; rec.nkc = nkc;
+        const double2 *Tf = T + (int64_t)frame * nx * ny + (int64_t)kr0 * ny + kc0;
+        int rlo = INT_MAX, rhi = INT_MIN, clo = INT_MAX, chi = INT_MIN, bad = 0;
+        for (int r = 0; r < nkr; ++r)
+            for (int c = lane; c < nkc; c += 32) {
+                const double2 v = __ldg(Tf + (int64_t)r * ny + c);
+                if (!(fabs(v.x) < 1.0e9) || !(fabs(v.y) < 1.0e9)) bad = 1;
+                else {
+                    const int f0 = __double2int_rd(v.x), f1 = __double2int_rd(v.y);
+                    rlo = min(rlo, f0); rhi = max(rhi, f0); clo = min(clo, f1); chi = max(chi, f1);
+                }
+            }
+        rlo = __reduce_min_sync(0xffffffffu, rlo); rhi = __reduce_max_sync(0xffffffffu, rhi);
+        clo = __reduce_min_sync(0xffffffffu, clo); chi = __reduce_max_sync(0xffffffffu, chi);
+        bad = __reduce_max_sync(0xffffffffu, bad);
+        // rows [rmin, rmax] x columns [cmin, cmin + bw) hold every tap of every in-frame fast pixel
+        const int rmin = max(rlo, 0), rmax = min(rhi + 1, h - 1);
+        int cmin = max(clo, 0) & ~(EPV - 1);
+        const int cmax = min(chi + 1, w - 1);
+        const int bh = rmax - rmin + 1;
+        const int bw = (cmax - cmin + 1 + EPV - 1) & ~(EPV - 1);
+        if (cmin + bw > w) cmin = w - bw;
+        if (!bad && bh >= 1 && bw >= EPV && cmin >= 0 && (w & (EPV - 1)) == 0 && bh * bw <= box_cap) {
+            rec.rmin = rmin; rec.bh = bh; rec.cmin = cmin; rec.bw = bw;
+        }
+    }
+    if (lane == 0) recs[t] = rec;
+}
+
+__device__ __forceinline__ void vl_mbar_wait_parity(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+}
+
+template <int SRC>
+__global__ void __launch_bounds__(VL_FW * VL_PS, 2)
+k_lean_fine_p(const void *__restrict__ src_all, const uint8_t *__restrict__ bg, int n_bg, int frame0,
+              const double2 *__restrict__ T, int nx, int ny, const vm_axis_entry *__restrict__ rows,
+              const vm_axis_entry *__restrict__ cols, int h, int w, int tiles_x, int tiles_y, int n_tiles,
+              int tiles_per_cta, int box_cap, const VlTileRec *__restrict__ recs, float4 *__restrict__ out,
+              int32_t *__restrict__ status) {
+    typedef typename VlSrc<SRC>::elem elem;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    VlPSmem &S = *reinterpret_cast<VlPSmem *>(smem_raw);
+    const int x = threadIdx.x, strip = threadIdx.y;
+    const int tid = strip * VL_FW + x;
+    const bool issuer = tid < 32;                                       // warp 0 issues the bulk copies
+    const int t_begin = blockIdx.x * tiles_per_cta, t_end = min(t_begin + tiles_per_cta, n_tiles);
+    if (t_begin >= t_end) return;
+    const uint32_t bar[2] = {vl_smem_u32(&S.bar[0]), vl_smem_u32(&S.bar[1])};
+    const bool bulk_bg = (w & 15) == 0 && (reinterpret_cast<uintptr_t>(bg) & 15) == 0;
+    const bool src_al = (reinterpret_cast<uintptr_t>(src_all) & 15) == 0;
+    const int64_t hw = (int64_t)h * w;
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar[0]));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar[1]));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    // tile coordinates as running counters (no division per tile)
+    const int per = tiles_x * tiles_y;
+    int frame = t_begin / per, ty = (t_begin - frame * per) / tiles_x, tx = t_begin - frame * per - ty * tiles_x;
+    int nframe = frame, nty = ty, ntx = tx;                             // coordinates of the tile being prefetched
+    auto advance = [&](int &f, int &yy, int &xx) { if (++xx == tiles_x) { xx = 0; if (++yy == tiles_y) { yy = 0; ++f; } } };
+
+    // issue every bulk copy of tile (f, yy, xx) with record r into buffer b; `with_T`: the coarse window too
+    auto issue = [&](const VlTileRec &r, int f, int yy, int xx, int b, bool with_T, bool rest) {
+        const int I0 = yy * VL_PTH, J0 = xx * VL_FW;
+        const int th = min(VL_PTH, h - I0), tw = min(VL_FW, w - J0);
+        const bool staged = r.nkr > 0;
+        const bool boxed = staged && r.bw > 0 && src_al;
+        const bool bg_sm = staged && bulk_bg && tw == VL_FW;
+        if (rest && tid == 0) {
+            S.rec[b] = r;
+            uint32_t bytes = 0;
+            if (staged) bytes = (uint32_t)(r.nkr * r.nkc * 16) + (uint32_t)((th + tw) * 16) +
+                                (boxed ? (uint32_t)(r.bh * r.bw * (int)sizeof(elem)) : 0u) + (bg_sm ? (uint32_t)(th * VL_FW * 3) : 0u);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar[b]), "r"(bytes) : "memory");
+        }
+        __syncwarp();
+        if (!staged) return;
+        if (rest) {
+            if (tid == 0) {
+                vl_bulk_g2s(vl_smem_u32(S.rows[b]), rows + I0, (uint32_t)(th * 16), bar[b]);
+                vl_bulk_g2s(vl_smem_u32(S.cols[b]), cols + J0, (uint32_t)(tw * 16), bar[b]);
+            }
+            if (boxed) {
+                elem *boxp = reinterpret_cast<elem *>(S.box + (size_t)b * box_cap);
+                const uint32_t row_bytes = (uint32_t)(r.bw * (int)sizeof(elem));
+                const elem *g = reinterpret_cast<const elem *>(src_all) + (int64_t)f * hw + (int64_t)r.rmin * w + r.cmin;
+                for (int k = tid; k < r.bh; k += 32) vl_bulk_g2s(vl_smem_u32(boxp + k * r.bw), g + (int64_t)k * w, row_bytes, bar[b]);
+            }
+            if (bg_sm) {
+                int bgi = frame0 + f;
+                if (bgi >= n_bg) bgi %= n_bg;
+                const uint8_t *g = bg + ((int64_t)bgi * hw + (int64_t)I0 * w + J0) * 3;
+                for (int k = tid; k < th; k += 32) vl_bulk_g2s(vl_smem_u32(S.bgt[b] + k * (VL_FW * 3)), g + (int64_t)k * w * 3, VL_FW * 3, bar[b]);
+            }
+        }
+        if (with_T) {
+            const double2 *g = T + (int64_t)f * nx * ny + (int64_t)r.kr0 * ny + r.kc0;
+            for (int k = tid; k < r.nkr; k += 32) vl_bulk_g2s(vl_smem_u32(S.T + k * VL_TC), g + (int64_t)k * ny, (uint32_t)(r.nkc * 16), bar[b]);
+        }
+    };
+
+    VlTileRec rnext = {0, 0, 0, 0, 0, 0, 0, 0};                          // record of tile t + 1 (warp 0 only)
+    if (issuer) {
+        const VlTileRec r0 = recs[t_begin];
+        issue(r0, frame, ty, tx, 0, true, true);
+        if (t_begin + 1 < t_end) rnext = recs[t_begin + 1];
+    }
+    advance(nframe, nty, ntx);
+
+    int outside = 0, slow = 0;
+    for (int t = t_begin, i = 0; t < t_end; ++t, ++i) {
+        const int b = i & 1;
+        // ---- S0: tile t has landed ---------------------------------------------------------
+        if (issuer) vl_mbar_wait_parity(bar[b], (uint32_t)((i >> 1) & 1));
+        __syncthreads();                                                // also: everybody is done with tile t-1
+        if (!issuer) vl_mbar_wait_parity(bar[b], (uint32_t)((i >> 1) & 1));   // completes at once: orders the async writes
+        const VlTileRec rec = S.rec[b];
+        const int I0 = ty * VL_PTH, J0 = tx * VL_FW;
+        const int th = min(VL_PTH, h - I0), tw = min(VL_FW, w - J0);
+        const bool staged = rec.nkr > 0;
+        // ---- S1: column-interpolated coarse rows -----------------------------------------------
+        if (staged && x < tw) {
+            const vm_axis_entry ce = S.cols[b][x];
+            const double yf = ce.frac, y1 = 1.0 - yf;
+            const double2 *Ta = S.T + (ce.i0 - rec.kc0), *Tb = S.T + (ce.i1 - rec.kc0);
+            for (int k = strip; k < rec.nkr; k += VL_PS) {
+                const VlC c = vl_col_lerp(Ta[k * VL_TC], Tb[k * VL_TC], y1, yf);
+                S.Cs[k * VL_FW + x] = make_double2(c.x, c.y);
+            }
+        }
+        __syncthreads();                                                // Cs complete, S.T free again
+        // ---- S2: prefetch tile t + 1 (its buffer was last read while tile t - 1 was resampled) ---------
+        if (issuer && t + 1 < t_end) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic reads of S.T / buffer b^1 before the async writes
+            issue(rnext, nframe, nty, ntx, b ^ 1, true, true);
+            if (t + 2 < t_end) rnext = recs[t + 2];
+        }
+        // ---- S3: resample + composite the thread's rows ---------------------------------------------
+        const int r_first = strip * VL_PR;
+        const int nrows = min(VL_PR, th - r_first);
+        if (x < tw && nrows > 0) {
+            const elem *src = reinterpret_cast<const elem *>(src_all) + (int64_t)frame * hw;
+            int bgi = frame0 + frame;
+            if (bgi >= n_bg) bgi %= n_bg;
+            const int64_t p0 = (int64_t)(I0 + r_first) * w + J0 + x;
+            const uint8_t *bgp = bg + ((int64_t)bgi * hw + p0) * 3;
+            float4 *op = out + (int64_t)frame * hw + p0;
+            if (!staged) {
+                const vm_axis_entry ce = vm_ld_axis(cols + J0 + x);
+                const double2 *Tf = T + (int64_t)frame * nx * ny;
+                vl_strip_generic<SRC>(src, Tf + ce.i0, Tf + ce.i1, ny, rows + I0 + r_first, ce.frac, bgp, op, nrows, h, w, &outside);
+            } else {
+                const bool boxed = rec.bw > 0 && src_al;
+                const bool bg_sm = bulk_bg && tw == VL_FW;
+                const elem *boxp = reinterpret_cast<const elem *>(S.box + (size_t)b * box_cap);
+                const unsigned char *bgl = S.bgt[b] + (r_first * VL_FW + x) * 3;
+                const double2 *Csj = S.Cs + x;
+                const vm_axis_entry *rp = S.rows[b] + r_first;
+                if (boxed && bg_sm) vl_strip_tile<SRC, true, true>(src, boxp, rec.rmin, rec.cmin, rec.bw, Csj, rec.kr0, rp, bgl, bgp, op, nrows, h, w, &outside);
+                else if (boxed)     vl_strip_tile<SRC, true, false>(src, boxp, rec.rmin, rec.cmin, rec.bw, Csj, rec.kr0, rp, bgl, bgp, op, nrows, h, w, &outside);
+                else                vl_strip_tile<SRC, false, false>(src, boxp, 0, 0, 0, Csj, rec.kr0, rp, bgl, bgp, op, nrows, h, w, &outside);
+            }
+        }
+        if (tid == 0 && !(staged && rec.bw > 0 && src_al)) ++slow;
+        advance(frame, ty, tx);
+        advance(nframe, nty, ntx);
+    }
+    if (status) {
+        if (outside) atomicAdd(status + VM_STATUS_TPS_OUTSIDE, outside);
+        if (slow) atomicAdd(status + VM_STATUS_SLOW_TILES, slow);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 static inline int64_t vl_align(int64_t v) { return (v + 255) & ~(int64_t)255; }
@@ -837,6 +1088,7 @@ int vm_lean_set_option(const char *key, int value) {
     if (!strcmp(key, "lean_b1_warps") && value >= 1 && value <= VL_B1_WARPS_HI) { g_vl_b1_warps = value; return VM_OK; }
     if (!strcmp(key, "lean_b1_dyr") && value >= 0 && value <= 1) { g_vl_b1_dyr = value; return VM_OK; }
     if (!strcmp(key, "lean_timing") && value >= 0 && value <= 1) { g_vl_timing = value; return VM_OK; }
+    if (!strcmp(key, "lean_persist") && value >= 0 && value <= 1) { g_vl_persist = value; return VM_OK; }
     if (!strcmp(key, "lean_sub") && value >= 0 && value <= 4096) { g_vl_sub = value; return VM_OK; }
     if (!strcmp(key, "lean_box_cap") && value >= 0 && value <= 16384) { g_vl_box_cap = value; return VM_OK; }
     if (!strcmp(key, "lean_minb") && value >= 2 && value <= 4) { g_vl_minb = value; return VM_OK; }
@@ -911,7 +1163,19 @@ int vm_lean_launch(int mode, const uint8_t *fg, const float *backward, const flo
                               counters + par * 32, side);
         if (rc != VM_OK) return rc;
         if (tev) cudaEventRecord(g_vl_tev[dev][1], st);
-        {
+        const bool persist = g_vl_persist != 0;
+        const int ptx = (w + VL_FW - 1) / VL_FW, pty = (h + VL_PTH - 1) / VL_PTH;      // tiling of the persistent kernel
+        // persistent kernel: 2 CTAs per SM share 227 KB; two source-box buffers per CTA
+        int pbox_cap = (int)((((227 * 1024) / 2 - 1024 - (int64_t)sizeof(VlPSmem)) / 16) & ~63);
+        if (g_vl_box_cap > 0 && g_vl_box_cap < pbox_cap) pbox_cap = g_vl_box_cap;
+        VlTileRec *recs = reinterpret_cast<VlTileRec *>(boxes);
+        if (persist) {
+            const int n_tiles = ptx * pty * m;
+            if (mode != 0) k_lean_recs<1><<<(n_tiles + 3) / 4, 128, 0, side>>>(T, nx, ny, rows, cols, h, w, ptx, pty, n_tiles, pbox_cap, recs);
+            else           k_lean_recs<0><<<(n_tiles + 3) / 4, 128, 0, side>>>(T, nx, ny, rows, cols, h, w, ptx, pty, n_tiles, pbox_cap, recs);
+            rc = vm_check_launch("vm_lean tile record stage");
+            if (rc != VM_OK) return rc;
+        } else {
             const int n_tiles = (int)(grid.x * grid.y * m);
             if (mode != 0) k_lean_boxes<1><<<(n_tiles + 3) / 4, 128, 0, side>>>(T, nx, ny, rows, cols, h, w, rpt, grid.x, grid.y, n_tiles, box_cap, boxes);
             else           k_lean_boxes<0><<<(n_tiles + 3) / 4, 128, 0, side>>>(T, nx, ny, rows, cols, h, w, rpt, grid.x, grid.y, n_tiles, box_cap, boxes);
@@ -951,7 +1215,29 @@ int vm_lean_launch(int mode, const uint8_t *fg, const float *backward, const flo
         k_lean_fine<S, MB><<<sgrid, block, fine_smem, st>>>(S ? (const void *)packed : (const void *)(fg + ff0 * px * 4), \
                                                             bg, n_bg, ff0, Ts, nx, ny, rows, cols, h, w, rpt, bs, o4, status); \
     } while (0)
-            if (mode != 0) { if (g_vl_minb == 4) VL_FINE(1, 4); else if (g_vl_minb == 3) VL_FINE(1, 3); else VL_FINE(1, 2); }
+            if (persist) {
+                const int n_tiles = ptx * pty * ms;
+                const int ctas = 2 * vl_sm_count();
+                const int per_cta = (n_tiles + ctas - 1) / ctas;
+                const int grid_p = (n_tiles + per_cta - 1) / per_cta;
+                const size_t psmem = vl_p_smem_bytes(pbox_cap);
+                const VlTileRec *rs = recs + (int64_t)fs * ptx * pty;
+                const dim3 pblock(VL_FW, VL_PS);
+#define VL_FINE_P(S)                                                                                                \
+    do {                                                                                                            \
+        static size_t attr_p[64];                                                                                   \
+        if (attr_p[dev & 63] < psmem) {                                                                             \
+            cudaError_t e = cudaFuncSetAttribute(k_lean_fine_p<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem); \
+            if (e != cudaSuccess) { vm_set_error("vm_lean: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VM_ERR_CUDA; } \
+            attr_p[dev & 63] = psmem;                                                                               \
+        }                                                                                                           \
+        k_lean_fine_p<S><<<grid_p, pblock, psmem, st>>>(S ? (const void *)packed : (const void *)(fg + ff0 * px * 4), bg, n_bg, ff0, \
+                                                        Ts, nx, ny, rows, cols, h, w, ptx, pty, n_tiles, per_cta, pbox_cap, rs, o4, status); \
+    } while (0)
+                if (mode != 0) VL_FINE_P(1); else VL_FINE_P(0);
+#undef VL_FINE_P
+            }
+            else if (mode != 0) { if (g_vl_minb == 4) VL_FINE(1, 4); else if (g_vl_minb == 3) VL_FINE(1, 3); else VL_FINE(1, 2); }
             else           { if (g_vl_minb == 4) VL_FINE(0, 4); else if (g_vl_minb == 3) VL_FINE(0, 3); else VL_FINE(0, 2); }
 #undef VL_FINE
             g_vl_launches += 1;
