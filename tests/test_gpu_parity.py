@@ -421,18 +421,24 @@ def test_lean_partition_independent(vm):
     base3, _ = P.tps_composite(args[0], args[3], ctrl, coef)
     assert int(st0[4]) < 4, "most tiles of a mild grid must take the shared-memory box path"
     defaults = {"lean_chunk": 64, "lean_rb": 0, "lean_minb": 4, "lean_box_cap": 0, "lean_fine_rows": 8, "lean_persist": 0,
-                "lean_sub": 0}
+                "lean_sub": 0, "lean_mega": 0, "lean_overlap": 0, "lean_b1_warps": 16, "lean_b1_dyr": 1, "flow_stage_layout": 0}
+    configs = [{"lean_chunk": 1}, {"lean_chunk": 2}, {"lean_chunk": 3}, {"lean_rb": 4}, {"lean_rb": 16}, {"lean_rb": 32},
+               {"lean_sub": 2}, {"lean_minb": 2}, {"lean_minb": 3}, {"lean_fine_rows": 3}, {"lean_fine_rows": 5},
+               {"lean_box_cap": 64}, {"lean_persist": 1}, {"lean_persist": 1, "lean_box_cap": 64}, {"lean_persist": 1, "lean_chunk": 2},
+               {"lean_mega": 1}, {"lean_mega": 1, "lean_chunk": 2}, {"lean_mega": 1, "lean_box_cap": 64},
+               {"lean_overlap": 1, "lean_chunk": 2, "lean_b1_warps": 6}, {"lean_b1_dyr": 0, "lean_b1_warps": 24},
+               {"flow_stage_layout": 1}]
     try:
-        for key, values in (("lean_chunk", (1, 2, 3)), ("lean_rb", (4, 16, 32)), ("lean_box_cap", (64,)), ("lean_sub", (2,)),
-                            ("lean_minb", (2, 3)), ("lean_fine_rows", (3, 5)), ("lean_persist", (1,)), ("lean_box_cap", (64,))):
-            for v in values:
+        for cfg in configs:
+            for key, v in cfg.items():
                 Nt.set_option(key, v)
-                out, st = P.flow_tps_composite(*args)
-                out3, _ = P.tps_composite(args[0], args[3], ctrl, coef)
-                assert torch.equal(out, base) and torch.equal(out3, base3), f"{key}={v} changes the result"
-                if key == "lean_box_cap":
-                    assert int(st[4]) > 0, "box capacity 64 must push tiles onto the gather path"
-            if key != "lean_persist":                      # the per-tile kernel stays selected for its own options
+            out, st = P.flow_tps_composite(*args)
+            out3, _ = P.tps_composite(args[0], args[3], ctrl, coef)
+            torch.cuda.synchronize()
+            assert torch.equal(out, base) and torch.equal(out3, base3), f"{cfg} changes the result"
+            if cfg.get("lean_box_cap") == 64:
+                assert int(st[4]) > 0, "box capacity 64 must push tiles onto the gather path"
+            for key in cfg:
                 Nt.set_option(key, defaults[key])
     finally:
         for key, v in defaults.items():

@@ -345,3 +345,116 @@ __device__ __forceinline__ vm_axis_entry vm_ld_axis(const vm_axis_entry *p) {
     return e;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// fused flow stage (C2 / stage A of C4) - shared by vm_flow.cu and the dependency-driven kernel of vm_lean.cu
+// ---------------------------------------------------------------------------------------
+#define C2_TW 128
+#define C2_TH 8                    /* rows in flight per CTA (one per warp) */
+#define C2_ROWS 40                 /* rows per CTA: each warp walks C2_ROWS / C2_TH of them */
+
+// alpha = ta / 261120 as float32 with <= 1.2e-7 relative error and exact 0 / 1 end points
+__device__ __forceinline__ float vm_alpha_f32(uint32_t ta) {
+    const uint32_t nta = 261120u - ta;
+    const float s = (float)min(ta, nta) * VM_ALPHA_INV;
+    return (ta > nta) ? 1.f - s : s;
+}
+
+// PACKED = 0: out_bgr (n,h,w,3) uint8 + out_alpha (n,h,w) float32 (the C2 result);
+// PACKED = 1: out_bgr is a (n,h,w) uint2 array {B|G<<8|R<<16, alpha code} - the stage-A
+//             intermediate of the split C4 pipeline (see vm_tps.cu), out_alpha unused;
+// PACKED = 2: same, with the raw alpha numerator {B|G<<8|R<<16, TA} (TA = 0 where masked) -
+//             the intermediate of the lean pipeline (vm_lean.cu), alpha = TA / 261120.
+template <int PACKED> __device__ __forceinline__ uint32_t vm_pack_alpha(const VmFlowPx &px) {
+    return px.masked ? 0u : (PACKED == 2 ? px.ta : vm_alpha_code(px.ta));
+}
+
+// One flow-stage unit = 128 columns x C2_ROWS rows of frame `frame`, executed by 256 threads: warp k walks
+// rows k, k + 8, ...; the two 16-byte flow loads of the next row are in flight while the current row's
+// taps are gathered and blended.
+template <bool HAS_FWD, int PACKED>
+__device__ __forceinline__ void vm_flow_unit_t(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd,
+                                             const float2 *__restrict__ fwd, int h, int w, int frame, int ty, int tx, int tid,
+                                             uint8_t *__restrict__ out_bgr, float *__restrict__ out_alpha,
+                                             int32_t *__restrict__ status) {
+    const int ibeg = ty * C2_ROWS + (tid >> 5), iend = min((ty + 1) * C2_ROWS, h);
+    const int j = tx * C2_TW + (tid & 31) * 4;
+    if (ibeg >= iend || j >= w) return;
+    const int64_t fbase = (int64_t)frame * h * w;
+    const uint32_t *fg32 = reinterpret_cast<const uint32_t *>(fg) + fbase;
+    const float2 *bf = bwd + fbase;
+    const float2 *ff = HAS_FWD ? fwd + fbase : nullptr;
+    const float fj = (float)j;
+    int flags = 0;
+    if (j + 3 < w && (w & 3) == 0) {
+        float4 n01 = __ldcs(reinterpret_cast<const float4 *>(bf + ibeg * w + j));       // streamed once: evict first
+        float4 n23 = __ldcs(reinterpret_cast<const float4 *>(bf + ibeg * w + j + 2));
+        for (int i = ibeg; i < iend; i += C2_TH) {
+            const float4 f01 = n01, f23 = n23;
+            if (i + C2_TH < iend) {
+                n01 = __ldcs(reinterpret_cast<const float4 *>(bf + (i + C2_TH) * w + j));
+                n23 = __ldcs(reinterpret_cast<const float4 *>(bf + (i + C2_TH) * w + j + 2));
+            }
+            const int p = i * w + j;
+            const float fi = (float)i;
+            const float2 fl[4] = {{f01.x, f01.y}, {f01.z, f01.w}, {f23.x, f23.y}, {f23.z, f23.w}};
+            VmFlowPx px[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                px[k] = vm_flow_px<HAS_FWD>(fg32, ff, h, w, i, j + k, fi, fj + (float)k, fl[k], flags);
+            if (PACKED) {
+                uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<uint2 *>(out_bgr) + fbase + p);
+                op[0] = make_uint4(px[0].bgr, vm_pack_alpha<PACKED>(px[0]), px[1].bgr, vm_pack_alpha<PACKED>(px[1]));
+                op[1] = make_uint4(px[2].bgr, vm_pack_alpha<PACKED>(px[2]), px[3].bgr, vm_pack_alpha<PACKED>(px[3]));
+            } else {
+                float al[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) al[k] = px[k].masked ? 0.f : vm_alpha_f32(px[k].ta);
+                // 12 bytes of BGR: b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3
+                const uint32_t c0 = px[0].bgr, c1 = px[1].bgr, c2 = px[2].bgr, c3 = px[3].bgr;
+                uint32_t *ob = reinterpret_cast<uint32_t *>(out_bgr + (fbase + p) * 3);
+                __stcs(ob, c0 | (c1 << 24));
+                __stcs(ob + 1, (c1 >> 8) | (c2 << 16));
+                __stcs(ob + 2, (c2 >> 16) | (c3 << 8));
+                __stcs(reinterpret_cast<float4 *>(out_alpha + fbase + p), make_float4(al[0], al[1], al[2], al[3]));
+            }
+        }
+    } else {
+        for (int i = ibeg; i < iend; i += C2_TH) {
+            const int p = i * w + j;
+            const float fi = (float)i;
+            for (int k = 0; k < 4 && j + k < w; ++k) {
+                const float2 f = __ldg(bf + p + k);
+                const VmFlowPx px = vm_flow_px<HAS_FWD>(fg32, ff, h, w, i, j + k, fi, fj + (float)k, f, flags);
+                if (PACKED) {
+                    reinterpret_cast<uint2 *>(out_bgr)[fbase + p + k] = make_uint2(px.bgr, vm_pack_alpha<PACKED>(px));
+                    continue;
+                }
+                uint8_t *ob = out_bgr + (fbase + p + k) * 3;
+                ob[0] = (uint8_t)px.bgr; ob[1] = (uint8_t)(px.bgr >> 8); ob[2] = (uint8_t)(px.bgr >> 16);
+                out_alpha[fbase + p + k] = px.masked ? 0.f : vm_alpha_f32(px.ta);
+            }
+        }
+    }
+    if (HAS_FWD && flags && status) {
+        if (flags & 1) atomicAdd(status + VM_STATUS_INDEX_ERR, 1);
+        if (flags & 2) atomicAdd(status + VM_STATUS_NAN_ERR, 1);
+    }
+}
+
+
+template <bool HAS_FWD, int PACKED>
+__device__ __forceinline__ void vm_flow_unit(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd,
+                                             const float2 *__restrict__ fwd, int h, int w, int frame, int ty, int tx,
+                                             uint8_t *__restrict__ out_bgr, float *__restrict__ out_alpha,
+                                             int32_t *__restrict__ status) {
+    vm_flow_unit_t<HAS_FWD, PACKED>(fg, bwd, fwd, h, w, frame, ty, tx, (int)threadIdx.x, out_bgr, out_alpha, status);
+}
+
+// packed {bgr, TA} output, explicit flat thread index (for CTAs that are not 256 x 1 shaped)
+template <bool HAS_FWD>
+__device__ __forceinline__ void vm_flow_unit_flat(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd,
+                                                  const float2 *__restrict__ fwd, int h, int w, int frame, int ty, int tx,
+                                                  int tid, uint2 *__restrict__ packed, int32_t *__restrict__ status) {
+    vm_flow_unit_t<HAS_FWD, 2>(fg, bwd, fwd, h, w, frame, ty, tx, tid, reinterpret_cast<uint8_t *>(packed), nullptr, status);
+}

@@ -33,6 +33,7 @@ int g_vl_timing = 0;         // 1: bracket the stages of the first chunk of ever
 static cudaEvent_t g_vl_tev[64][5];
 static bool g_vl_tev_ok[64];
 static long long g_vl_launches = 0;   // kernels launched by this library's lean path (bench.py "gpu_launches")
+int g_vl_mega = 0;           // 1 (C4 only): flow stage + resampling in one dependency-driven persistent kernel (k_lean_mega)
 int g_vl_persist = 0;        // 1: persistent double-buffered resampling kernel (k_lean_fine_p); 0: one CTA per tile (k_lean_fine)
 int g_vl_sub = 0;            // frames per flow-stage / resampling sub-round inside a round (0: the whole round)
 int g_vl_box_cap = 0;        // source-box entries per B2 tile (0: as many as the occupancy target allows)
@@ -637,18 +638,18 @@ __device__ __noinline__ void vl_strip_generic(const typename VlSrc<SRC>::elem *_
 // one warp polls the mbarrier (phase 0), the CTA barrier releases everybody else without spinning;
 // every thread then observes the completed phase itself (one try_wait that succeeds at once), which is
 // what orders the async-proxy writes of the bulk copies before its own shared-memory reads
-__device__ __forceinline__ void vl_cta_wait(uint32_t bar, bool poll, bool used) {
+__device__ __forceinline__ void vl_cta_wait(uint32_t bar, bool poll, bool used, uint32_t parity) {
     uint32_t ok = 0;
     if (poll) {
         while (!ok)
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                         : "=r"(ok) : "r"(bar) : "memory");
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     }
     __syncthreads();
     if (used && !poll) {
         while (!ok)
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                         : "=r"(ok) : "r"(bar) : "memory");
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     }
 }
 
@@ -708,19 +709,20 @@ k_lean_boxes(const double2 *__restrict__ T, int nx, int ny, const vm_axis_entry 
     if (lane == 0) boxes[t] = rec;
 }
 
-template <int SRC, int MINB>
-__global__ void __launch_bounds__(VL_FW * VL_FS, MINB)
-k_lean_fine(const void *__restrict__ src_all, const uint8_t *__restrict__ bg, int n_bg, int frame0,
-            const double2 *__restrict__ T, int nx, int ny, const vm_axis_entry *__restrict__ rows,
-            const vm_axis_entry *__restrict__ cols, int h, int w, int rpt, const VlTileBox *__restrict__ boxes,
-            float4 *__restrict__ out, int32_t *__restrict__ status) {
+// One B2 tile (VL_FW columns x VL_FS * rpt rows at tile (bx, by) of frame `frame`) by the 256 threads of a
+// CTA.  S.bar[0] must have been initialised (count 1); `phase` is its current parity and is toggled when
+// the tile used it, so the function can be called for tile after tile by a persistent CTA.
+template <int SRC, bool XCTA>      // XCTA: the source was written by other CTAs of the same kernel (full proxy fence)
+__device__ __forceinline__ void vl_fine_tile(VlFineSmem &S, uint32_t &phase, const void *__restrict__ src_all,
+                                             const uint8_t *__restrict__ bg, int n_bg, int frame0,
+                                             const double2 *__restrict__ T, int nx, int ny,
+                                             const vm_axis_entry *__restrict__ rows, const vm_axis_entry *__restrict__ cols,
+                                             int h, int w, int rpt, VlTileBox rec, int frame, int by, int bx,
+                                             float4 *__restrict__ out, int &outside, int &slow) {
     typedef typename VlSrc<SRC>::elem elem;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    VlFineSmem &S = *reinterpret_cast<VlFineSmem *>(smem_raw);
     const int tid = threadIdx.y * VL_FW + threadIdx.x;
-    const int J0 = blockIdx.x * VL_FW, I0 = blockIdx.y * (VL_FS * rpt);
+    const int J0 = bx * VL_FW, I0 = by * (VL_FS * rpt);
     const int tw = min(VL_FW, w - J0), th = min(VL_FS * rpt, h - I0);
-    const int frame = blockIdx.z;
     const int jc = min((int)threadIdx.x, tw - 1), j = J0 + jc;
     const uint32_t bar0 = vl_smem_u32(&S.bar[0]);
     const int64_t fbase = (int64_t)frame * h * w;
@@ -730,16 +732,10 @@ k_lean_fine(const void *__restrict__ src_all, const uint8_t *__restrict__ bg, in
     const uint8_t *bgf = bg + (int64_t)bgi * h * w * 3;
     const double2 *Tf = T + (int64_t)frame * nx * ny;
 
-    // ---- P0: axis entries, tile record, barrier ---------------------------------------------
+    // ---- P0: axis entries ------------------------------------------------------------------
     const vm_axis_entry ce = vm_ld_axis(cols + j);
-    const VlTileBox rec = boxes[((int64_t)frame * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x];
     vm_axis_entry myrow = {0.0, 0, 0};
     if (tid < th) { myrow = vm_ld_axis(rows + I0 + tid); S.rows[tid] = myrow; }
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
     __syncthreads();
     const int kr0 = S.rows[0].i0, kr1 = max(S.rows[th - 1].i1, S.rows[th - 1].i0);
     const int nkr = kr1 - kr0 + 1;
@@ -757,22 +753,26 @@ k_lean_fine(const void *__restrict__ src_all, const uint8_t *__restrict__ bg, in
     const int64_t p0 = (int64_t)(I0 + strip0) * w + j;
     const uint8_t *bgp = bgf + p0 * 3;
     float4 *op = out + fbase + p0;
-    int outside = 0;
     const bool active = (int)threadIdx.x < tw && nrows > 0;
 
     if (!all_staged) {                                                  // generic axis tables: everything from global memory
         if (active) vl_strip_generic<SRC>(src, Tf + ce.i0, Tf + ce.i1, ny, rows + I0 + strip0, ce.frac, bgp, op, nrows, h, w, &outside);
-        if (status && outside) atomicAdd(status + VM_STATUS_TPS_OUTSIDE, outside);
+        if (tid == 0) ++slow;
         return;
     }
 
     // ---- P1: bulk async copies (TMA): background rows + source box, all on one mbarrier -------
     const bool bg_sm = tw == VL_FW && (w & 15) == 0 && (reinterpret_cast<uintptr_t>(bg) & 15) == 0;
     const bool boxed = rec.bw > 0 && (reinterpret_cast<uintptr_t>(src_all) & 15) == 0;
+    const bool used = bg_sm || boxed;
     elem *boxp = reinterpret_cast<elem *>(S.box);
-    if (tid < 32 && (bg_sm || boxed)) {                                 // warp 0: one lane per row, 32 copies per instruction
+    if (tid < 32 && used) {                                             // warp 0: one lane per row, 32 copies per instruction
         if (tid == 0) {
             const uint32_t bytes = (bg_sm ? (uint32_t)(th * VL_FW * 3) : 0u) + (boxed ? (uint32_t)(rec.bh * rec.bw * (int)sizeof(elem)) : 0u);
+            // earlier generic accesses (this CTA's reads of the buffers; with XCTA also the acquired global
+            // writes of other CTAs) are ordered before the async-proxy copies
+            if (XCTA) asm volatile("fence.proxy.async;" ::: "memory");
+            else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0), "r"(bytes) : "memory");
         }
         __syncwarp();
@@ -809,20 +809,117 @@ k_lean_fine(const void *__restrict__ src_all, const uint8_t *__restrict__ bg, in
             }
         }
     }
-    vl_cta_wait(bar0, tid < 32 && (bg_sm || boxed), bg_sm || boxed);
+    vl_cta_wait(bar0, tid < 32 && used, used, phase);
+    if (used) phase ^= 1u;
 
     const unsigned char *bgl = S.bgt + (strip0 * VL_FW + (int)threadIdx.x) * 3;
     const double2 *Csj = S.Cs + threadIdx.x;
 
     // ---- P3: per-pixel resampling + composite ------------------------------------------------
-    if (!boxed && status && tid == 0) atomicAdd(status + VM_STATUS_SLOW_TILES, 1);
+    if (!boxed && tid == 0) ++slow;
     if (active) {
         const vm_axis_entry *rp = S.rows + strip0;
         if (boxed && bg_sm) vl_strip_tile<SRC, true, true>(src, boxp, rec.rmin, rec.cmin, rec.bw, Csj, kr0, rp, bgl, bgp, op, nrows, h, w, &outside);
         else if (boxed)     vl_strip_tile<SRC, true, false>(src, boxp, rec.rmin, rec.cmin, rec.bw, Csj, kr0, rp, bgl, bgp, op, nrows, h, w, &outside);
         else                vl_strip_tile<SRC, false, false>(src, boxp, 0, 0, 0, Csj, kr0, rp, bgl, bgp, op, nrows, h, w, &outside);
     }
-    if (status && outside) atomicAdd(status + VM_STATUS_TPS_OUTSIDE, outside);
+}
+
+__device__ __forceinline__ void vl_bar_init(VlFineSmem &S) {
+    if (threadIdx.y * VL_FW + threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(vl_smem_u32(&S.bar[0])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+}
+
+template <int SRC, int MINB>
+__global__ void __launch_bounds__(VL_FW * VL_FS, MINB)
+k_lean_fine(const void *__restrict__ src_all, const uint8_t *__restrict__ bg, int n_bg, int frame0,
+            const double2 *__restrict__ T, int nx, int ny, const vm_axis_entry *__restrict__ rows,
+            const vm_axis_entry *__restrict__ cols, int h, int w, int rpt, const VlTileBox *__restrict__ boxes,
+            float4 *__restrict__ out, int32_t *__restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    VlFineSmem &S = *reinterpret_cast<VlFineSmem *>(smem_raw);
+    const VlTileBox rec = boxes[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x];
+    vl_bar_init(S);
+    uint32_t phase = 0;
+    int outside = 0, slow = 0;
+    vl_fine_tile<SRC, false>(S, phase, src_all, bg, n_bg, frame0, T, nx, ny, rows, cols, h, w, rpt, rec, blockIdx.z, blockIdx.y, blockIdx.x,
+                      out, outside, slow);
+    if (status) {
+        if (outside) atomicAdd(status + VM_STATUS_TPS_OUTSIDE, outside);
+        if (slow) atomicAdd(status + VM_STATUS_SLOW_TILES, slow);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Stage A + stage B2 in one persistent kernel ("mega", option lean_mega, off by default: measured 78 us
+// per frame against 45 us for the separate kernels - CTAs spin on the frame dependency because their
+// progress drifts apart by more than the two-frame lag, and the packed frames still reach DRAM because
+// every frame has its own region, so dirty lines are written back): every CTA walks a fixed,
+// interleaved list of work items - flow-stage units of frame s and resampling tiles of frame s-2 -
+// so the packed intermediate of a frame is consumed from L2 two frames after it was produced and
+// never makes the round trip through HBM.  A tile of frame f waits until all flow-stage units of
+// frame f have been published (release: __threadfence + atomicAdd; acquire: volatile load +
+// __threadfence).  Items are taken in increasing order by every CTA and the units a tile depends on
+// come earlier in the list, so the wait cannot deadlock as long as every CTA of the grid is resident
+// (the host sizes the grid with the occupancy API).
+// ---------------------------------------------------------------------------------------
+#define VL_MEGA_LAG 2
+
+template <bool HAS_FWD>
+__global__ void __launch_bounds__(VL_FW * VL_FS, 4)
+k_lean_mega(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd, const float2 *__restrict__ fwd,
+            uint2 *__restrict__ packed, const uint8_t *__restrict__ bg, int n_bg, int frame0,
+            const double2 *__restrict__ T, int nx, int ny, const vm_axis_entry *__restrict__ rows,
+            const vm_axis_entry *__restrict__ cols, int h, int w, int n, int rpt,
+            const VlTileBox *__restrict__ boxes, float4 *__restrict__ out, int32_t *__restrict__ status,
+            unsigned int *__restrict__ frame_done) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    VlFineSmem &S = *reinterpret_cast<VlFineSmem *>(smem_raw);
+    const int tid = threadIdx.y * VL_FW + threadIdx.x;
+    const int atx = (w + C2_TW - 1) / C2_TW, aty = (h + C2_ROWS - 1) / C2_ROWS, nA = atx * aty;      // flow-stage units per frame
+    const int btx = (w + VL_FW - 1) / VL_FW, bty = (h + VL_FS * rpt - 1) / (VL_FS * rpt), nB = btx * bty;   // tiles per frame
+    const int P = nA + nB;
+    const int64_t total = (int64_t)(n + VL_MEGA_LAG) * P;
+    vl_bar_init(S);
+    uint32_t phase = 0;
+    int outside = 0, slow = 0;
+    for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+        const int slot = (int)(item / P), k = (int)(item - (int64_t)slot * P);
+        // Bresenham interleave of nA units among P positions
+        const int a_before = (int)(((int64_t)k * nA) / P), a_after = (int)(((int64_t)(k + 1) * nA) / P);
+        if (a_after > a_before) {                                       // ---- flow-stage unit a_before of frame `slot`
+            if (slot >= n) continue;
+            const int ty = a_before / atx, tx = a_before - ty * atx;
+            // the 2-D thread index of this kernel is irrelevant to the unit: it uses threadIdx.x of a 256-thread CTA
+            vm_flow_unit_flat<HAS_FWD>(fg, bwd, fwd, h, w, slot, ty, tx, tid, packed, status);
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                atomicAdd(frame_done + slot, 1u);
+            }
+        } else {                                                        // ---- resampling tile (k - a_before) of frame slot - LAG
+            const int f = slot - VL_MEGA_LAG;
+            if (f < 0) continue;
+            const int b = k - a_before;
+            const int by = b / btx, bx = b - by * btx;
+            if (tid == 0) {
+                while (*reinterpret_cast<volatile unsigned int *>(frame_done + f) < (unsigned)nA) __nanosleep(200);
+                __threadfence();
+            }
+            __syncthreads();                                            // (also: everybody is done with the previous tile's buffers)
+            const VlTileBox rec = boxes[((int64_t)f * bty + by) * btx + bx];
+            vl_fine_tile<1, true>(S, phase, packed, bg, n_bg, frame0, T, nx, ny, rows, cols, h, w, rpt, rec, f, by, bx, out, outside, slow);
+            __syncthreads();
+        }
+    }
+    if (status) {
+        if (outside) atomicAdd(status + VM_STATUS_TPS_OUTSIDE, outside);
+        if (slow) atomicAdd(status + VM_STATUS_SLOW_TILES, slow);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1078,7 +1175,8 @@ int64_t vm_lean_scratch_bytes(int n, int h, int w) {
     const int m = n < g_vl_chunk ? n : g_vl_chunk;
     const int64_t tiles = (int64_t)m * ((w + VL_FW - 1) / VL_FW) * ((h + 3) / 4);     // >= tiles for any rows-per-thread setting
     return 512 + vl_align((int64_t)m * h * w * 8) +
-           (g_vl_overlap ? 2 : 1) * (vl_align((int64_t)m * (h / 2 + 1) * (w / 2 + 1) * 16) + vl_align(tiles * 16));
+           (g_vl_overlap ? 2 : 1) * (vl_align((int64_t)m * (h / 2 + 1) * (w / 2 + 1) * 16) + vl_align(tiles * 16)) +
+           vl_align((int64_t)m * 4);
 }
 
 int vm_lean_set_option(const char *key, int value) {
@@ -1088,6 +1186,7 @@ int vm_lean_set_option(const char *key, int value) {
     if (!strcmp(key, "lean_b1_warps") && value >= 1 && value <= VL_B1_WARPS_HI) { g_vl_b1_warps = value; return VM_OK; }
     if (!strcmp(key, "lean_b1_dyr") && value >= 0 && value <= 1) { g_vl_b1_dyr = value; return VM_OK; }
     if (!strcmp(key, "lean_timing") && value >= 0 && value <= 1) { g_vl_timing = value; return VM_OK; }
+    if (!strcmp(key, "lean_mega") && value >= 0 && value <= 1) { g_vl_mega = value; return VM_OK; }
     if (!strcmp(key, "lean_persist") && value >= 0 && value <= 1) { g_vl_persist = value; return VM_OK; }
     if (!strcmp(key, "lean_sub") && value >= 0 && value <= 4096) { g_vl_sub = value; return VM_OK; }
     if (!strcmp(key, "lean_box_cap") && value >= 0 && value <= 16384) { g_vl_box_cap = value; return VM_OK; }
@@ -1123,6 +1222,7 @@ int vm_lean_launch(int mode, const uint8_t *fg, const float *backward, const flo
     unsigned char *tb0 = base + vl_align((int64_t)mc * px * 8);
     double2 *Tset[2] = {reinterpret_cast<double2 *>(tb0), reinterpret_cast<double2 *>(tb0 + t_bytes + box_bytes)};
     VlTileBox *Bset[2] = {reinterpret_cast<VlTileBox *>(tb0 + t_bytes), reinterpret_cast<VlTileBox *>(tb0 + 2 * t_bytes + box_bytes)};
+    unsigned int *frame_done = reinterpret_cast<unsigned int *>(tb0 + (g_vl_overlap ? 2 : 1) * (t_bytes + box_bytes));
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
     const bool overlap = g_vl_overlap && cap == cudaStreamCaptureStatusNone;
@@ -1193,6 +1293,38 @@ int vm_lean_launch(int mode, const uint8_t *fg, const float *backward, const flo
         for (int fs = 0; fs < m; fs += sub) {
             const int ms = (m - fs < sub) ? m - fs : sub;
             const int ff0 = f0 + fs;
+            const bool mega = g_vl_mega && mode != 0 && !persist && (w & 3) == 0;
+            if (mega) {
+                // flow-stage units and resampling tiles from one interleaved list; every CTA must be resident
+                const float2 *b2 = reinterpret_cast<const float2 *>(backward + ff0 * px * 2);
+                const float2 *f2 = (mode == 2 && forward) ? reinterpret_cast<const float2 *>(forward + ff0 * px * 2) : nullptr;
+                float4 *o4m = reinterpret_cast<float4 *>(out) + ff0 * px;
+                if (cudaMemsetAsync(frame_done, 0, sizeof(unsigned int) * ms, st) != cudaSuccess) { vm_set_error("vm_lean: cudaMemsetAsync failed"); return VM_ERR_CUDA; }
+                int per_sm = 0;
+                cudaError_t e = cudaSuccess;
+#define VL_MEGA(FW)                                                                                                 \
+    do {                                                                                                            \
+        static size_t attr_m[64];                                                                                   \
+        if (attr_m[dev & 63] < fine_smem) {                                                                         \
+            e = cudaFuncSetAttribute(k_lean_mega<FW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fine_smem);   \
+            if (e == cudaSuccess) attr_m[dev & 63] = fine_smem;                                                     \
+        }                                                                                                           \
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lean_mega<FW>, VL_FW * VL_FS, fine_smem); \
+        if (e == cudaSuccess && per_sm >= 1)                                                                        \
+            k_lean_mega<FW><<<per_sm * vl_sm_count(), block, fine_smem, st>>>(fg + ff0 * px * 4, b2, f2, (uint2 *)packed, bg, n_bg, ff0, \
+                Ts0, nx, ny, rows, cols, h, w, ms, rpt, bs0, o4m, status, frame_done);                               \
+    } while (0)
+                const double2 *Ts0 = T + (int64_t)fs * nx * ny;
+                const VlTileBox *bs0 = boxes + fs * tiles_per_frame;
+                if (f2) VL_MEGA(true); else VL_MEGA(false);
+#undef VL_MEGA
+                if (e != cudaSuccess || per_sm < 1) { vm_set_error("vm_lean: mega kernel set-up failed: %s", cudaGetErrorString(e)); return VM_ERR_CUDA; }
+                g_vl_launches += 1;
+                rc = vm_check_launch(what);
+                if (rc != VM_OK) return rc;
+                if (tev) cudaEventRecord(g_vl_tev[dev][3], st);
+                continue;
+            }
             if (mode != 0) {
                 rc = vm_launch_flow_stage(fg + ff0 * px * 4, backward + ff0 * px * 2, (mode == 2 && forward) ? forward + ff0 * px * 2 : nullptr,
                                           ms, h, w, packed, status, st, true);
