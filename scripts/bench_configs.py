@@ -62,3 +62,30 @@ case("C3 TPS (16 control points) + composite, 512x512 x 256", "c3", 512, 512, 25
 case("C3 TPS (25 control points) + composite, 1080p x 64", "c3", 1080, 1920, 64, 5, 23)
 case("C4 flow warp + mask + TPS + composite, 1080p x 64 (headline)", "c4", 1080, 1920, 64, 5, 39)
 case("C4 flow warp + mask + TPS + composite, 4K x 16", "c4", 2160, 3840, 16, 5, 39)
+
+
+def case_augment(h, w, iters):
+    """C5 (informational): the drop-in augmentation.augment on device-resident tensors, one frame per call -
+    host RNG draws, the host TPS solve (twice, as the reference) and two host syncs (object_size, fg_center) included."""
+    import time
+    import numpy as np
+    frame = O.synth_frame(4242, h, w)
+    fg = torch.from_numpy(np.ascontiguousarray(frame[..., :3])).to(dev)
+    alpha = torch.from_numpy(frame[..., 3] / 255.).to(dev)
+    bgf = torch.from_numpy(O.synth_background(7, h, w)).to(dev)
+    np.random.seed(1)
+    for _ in range(2):
+        vm.augmentation.augment(fg, bgf, alpha)
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    for _ in range(iters):
+        vm.augmentation.augment(fg, bgf, alpha)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t) / iters
+    gbs = 17 * h * w / dt / 1e9
+    print(json.dumps({"config": "C5 augmentation.augment drop-in, 1080p, one frame per call (host orchestration included)",
+                      "height": h, "width": w, "ms_per_frame": dt * 1e3, "frames_per_s": 1 / dt, "algorithmic_bytes_per_px": 17,
+                      "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak}), flush=True)
+
+
+case_augment(1080, 1920, 20)
