@@ -20,6 +20,7 @@
 #include "vm_common.cuh"
 #include <math.h>
 #include <string.h>
+#include <atomic>
 #include <mutex>
 
 int vm_launch_flow_stage(const uint8_t *fg, const float *backward, const float *forward, int n, int h, int w,
@@ -32,7 +33,7 @@ int g_vl_fine_rows = 8;      // fine rows per B2 thread
 int g_vl_timing = 0;         // 1: bracket the stages of the first chunk of every call with CUDA events (vm_lean_stage_ms)
 static cudaEvent_t g_vl_tev[64][5];
 static bool g_vl_tev_ok[64];
-static long long g_vl_launches = 0;   // kernels launched by this library's lean path (bench.py "gpu_launches")
+static std::atomic<long long> g_vl_launches{0};   // kernels launched by this library's lean path (bench.py "gpu_launches")
 int g_vl_mega = 0;           // 1 (C4 only): flow stage + resampling in one dependency-driven persistent kernel (k_lean_mega)
 int g_vl_persist = 0;        // 1: persistent double-buffered resampling kernel (k_lean_fine_p); 0: one CTA per tile (k_lean_fine)
 int g_vl_sub = 0;            // frames per flow-stage / resampling sub-round inside a round (0: the whole round)
@@ -1404,4 +1405,4 @@ extern "C" int vm_lean_stage_ms(float *out4) {
 }
 
 // number of kernels the lean path has launched in this process (all devices)
-extern "C" long long vm_lean_launch_count(void) { return g_vl_launches; }
+extern "C" long long vm_lean_launch_count(void) { return g_vl_launches.load(); }
