@@ -182,6 +182,29 @@ int vm_flow_tps_composite_bgra(const uint8_t *fg, const float *backward, const f
  * events around the stages of variant 4 (read back with vm_lean_stage_ms).                   */
 int vm_set_option(const char *key, int value);
 
+/* Batched augmentation (reference augmentation.py:102-135, `augment` for a whole clip; BASELINE config 5).
+ * The host draws the reference's random parameters frame by frame and solves the TPS systems; the device
+ * stages are:
+ *   vm_alpha_stats_bgra   object_size / fg_center sums of every BGRA frame (augmentation.py:10-21):
+ *                         out (n,3) uint64 {count(A != 0), sum(rows), sum(cols)}, zeroed by the caller;
+ *   vm_tps_coarse_packed  spline on the coarse grid (tps.py:101-123) as (n,nx,ny) double2 {row, col}
+ *                         (`counter`: one zeroed device word of workspace);
+ *   vm_aug_tps            tps.warp_images on B,G,R (uint8, half-up) and alpha = A/255 of every frame on the
+ *                         (h+1) x (w+1) grid (tps.py:14-75) -> (n,h+1,w+1) uint2 {B|G<<8|R<<16, float32 alpha bits};
+ *   vm_aug_affine         the two cv2.warpAffine passes of augmentation.warp_image (augmentation.py:59-62:
+ *                         integer translation, then rotation/scale, both (w,h)) fused with
+ *                         change_illumination (augmentation.py:88-99).  mode 1: src = vm_aug_tps output ->
+ *                         out_bgr (n,h,w,3) uint8 + out_alpha (n,h,w) float32; mode 0: src = (n,h,w,3) uint8
+ *                         background -> out_bgr.  params: device array of n {double M[6]; int32 tu, tv}
+ *                         (M = 2x3 matrix of the second pass); luts: device (n,256) uint8 S/V tables.      */
+int vm_alpha_stats_bgra(const uint8_t *bgra, int n, int h, int w, unsigned long long *out, void *stream);
+int vm_tps_coarse_packed(const double *ctrl, const double *coef, int n, int N, int nx, int ny,
+                         double step_x, double step_y, void *T, unsigned int *counter, void *stream);
+int vm_aug_tps(const uint8_t *fg_bgra, const void *T, int nx, int ny, const vm_axis_entry *rows,
+               const vm_axis_entry *cols, int n, int h, int w, void *inter, int32_t *status, void *stream);
+int vm_aug_affine(int mode, const void *src, const void *params, const uint8_t *luts, int n, int h, int w,
+                  uint8_t *out_bgr, float *out_alpha, void *stream);
+
 /* Measurement hooks of the default fused path (no reference counterpart; used by bench.py).
  * vm_lean_stage_ms: durations in ms of {spline, tile boxes, flow stage, resampling+composite}
  * of the first chunk of the last call made with "lean_timing" = 1 on the current device, after

@@ -89,3 +89,26 @@ def case_augment(h, w, iters):
 
 
 case_augment(1080, 1920, 20)
+
+
+def case_augment_clip(h, w, n, iters):
+    """C5, batched: augmentation.augment_clip on a device-resident clip (host RNG + pinv per frame included)."""
+    import time
+    import numpy as np
+    fg, _, _, bg = bench.make_clip(torch, 99, n, h, w, dev)
+    bgn = bg[torch.arange(n) % bg.shape[0]].contiguous()
+    np.random.seed(1)
+    vm.augmentation.augment_clip(fg, bgn)
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    for _ in range(iters):
+        vm.augmentation.augment_clip(fg, bgn)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t) / iters
+    gbs = 17 * h * w * n / dt / 1e9
+    print(json.dumps({"config": f"C5 augmentation.augment_clip, 1080p x {n} per call (host RNG + pinv per frame included)",
+                      "height": h, "width": w, "frames_per_launch": n, "ms_per_call": dt * 1e3, "frames_per_s": n / dt,
+                      "algorithmic_bytes_per_px": 17, "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak}), flush=True)
+
+
+case_augment_clip(1080, 1920, 64, 5)

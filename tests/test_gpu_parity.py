@@ -600,3 +600,39 @@ def test_fused_wild_flows(vm):
     for k in range(n):
         rb, ra = O.pipeline_c2(frames[k], fb_ok[k], ff[k])
         assert np.array_equal(bgr[k].cpu().numpy()[clean[k]], rb[clean[k]])
+
+
+# ------------------------------------------------------------------ batched augmentation (config 5)
+
+@pytest.mark.parametrize("shape", [(96, 128), (61, 83), (200, 333)])
+def test_augment_clip_matches_sequential_augment(vm, shape):
+    """augment_clip == [augment(frame) for frame in clip] with the same global np.random state: same draws in
+    the same order, same uint8 images (up to knife-edge samples of the TPS stage, whose up-sampling order
+    differs by ~1e-13 px from the drop-in kernel) and the same alpha within 1e-5."""
+    h, w = shape
+    n = 3
+    A = vm.augmentation
+    frames = np.stack([O.synth_frame(700 + k, h, w) for k in range(n)])
+    bgs = np.stack([O.synth_background(20 + k, h, w) for k in range(n)])
+    np.random.seed(2024)
+    seq = [A.augment(np.ascontiguousarray(frames[k, ..., :3]), bgs[k], frames[k, ..., 3] / 255.) for k in range(n)]
+    after_seq = np.random.uniform()
+    np.random.seed(2024)
+    nfg, nbg, nal = A.augment_clip(frames, bgs)
+    assert np.random.uniform() == after_seq, "augment_clip must consume exactly the draws of n augment() calls"
+    assert nfg.dtype == np.uint8 and nbg.dtype == np.uint8 and nal.dtype == np.float32
+    for k in range(n):
+        rfg, rbg, ral = seq[k]
+        assert np.array_equal(nbg[k], rbg)
+        assert np.count_nonzero(np.any(nfg[k] != rfg, axis=-1)) <= 2
+        assert np.allclose(nal[k], ral, rtol=RTOL, atol=1e-6)
+
+
+def test_augment_clip_golden(vm, golden):
+    """One-frame clip against the golden vectors of the unmodified reference's augment()."""
+    bgra, bg = golden["wi_fg"], golden["aug_bg"]                      # BGRA uint8: alpha = A/255 as in read_fg_img
+    np.random.seed(77)
+    nfg, nbg, nal = vm.augmentation.augment_clip(bgra[None], bg[None])
+    assert np.allclose(nal[0], golden["aug_alpha_out"], rtol=RTOL, atol=1e-6)
+    assert np.abs(nbg[0].astype(int) - golden["aug_bg_out"].astype(int)).max() <= 1
+    assert np.count_nonzero(np.abs(nfg[0].astype(int) - golden["aug_fg_out"].astype(int)) > 1) <= 2

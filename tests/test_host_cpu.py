@@ -59,6 +59,16 @@ def test_tps_solve_bit_equal_to_oracle(vm):
         assert np.array_equal(vm.pipeline._tps_kernel_matrix(dgrid), O.tps_system(dgrid))
 
 
+def test_batched_solve_bit_equal_to_per_frame_solve(vm):
+    """solve_grids' stacked / threaded pinv == the reference's per-frame np.dot(pinv(L), V) (tps.py:119)."""
+    P = vm.pipeline
+    grids = [O.synth_grids(900 + k, 1080, 1920, 5) for k in range(20)] + [O.synth_grids(5, 512, 512, 4)] * 0
+    ref = np.stack([P.tps_solve(d, g) for (g, d) in grids])
+    for chunk in (grids, grids[:3]):
+        got = np.concatenate([P._solve_chunk(chunk[i:i + 8]) for i in range(0, len(chunk), 8)])
+        assert np.array_equal(got, ref[:len(chunk)])
+
+
 def test_axis_tables_match_reference_index_math(vm):
     for h in (61, 64, 500, 1080, 1081):
         xs = h / 2

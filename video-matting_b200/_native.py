@@ -40,6 +40,10 @@ SIGNATURES = {
     "vm_tps_composite_bgra": [_P, _P, _I, _P, _P, _I, _I, _I, _D, _D, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "vm_flow_tps_composite_bgra": [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _D, _D, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "vm_set_option": [_c.c_char_p, _I],
+    "vm_tps_coarse_packed": [_P, _P, _I, _I, _I, _I, _D, _D, _P, _P, _P],
+    "vm_aug_tps": [_P, _P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P],
+    "vm_alpha_stats_bgra": [_P, _I, _I, _I, _P, _P],
+    "vm_aug_affine": [_I, _P, _P, _P, _I, _I, _I, _P, _P, _P],
     "vm_lean_stage_ms": [_P],
     "vm_lean_launch_count": [],
 }

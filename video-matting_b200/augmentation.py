@@ -41,11 +41,14 @@ def deform_grid(h, w, n=5):
     cols = (w / (n - 1)) * np.arange(n)
     grid = np.transpose([np.repeat(rows, n), np.tile(cols, n)])
     moved = grid.copy()
-    for k, (y, x) in enumerate(grid):
-        if 0. < x < w:
-            moved[k, 1] += np.random.uniform(-bound, bound)
-        if 0. < y < h:
-            moved[k, 0] += np.random.uniform(-bound, bound)
+    # one vector draw = the reference's scalar draws in the same order (legacy RandomState.uniform consumes
+    # one double per value either way): per point, x if 0 < x < w, then y if 0 < y < h
+    need = np.stack([(grid[:, 1] > 0.) & (grid[:, 1] < w), (grid[:, 0] > 0.) & (grid[:, 0] < h)], axis=1)   # (n*n, {x, y})
+    draws = np.random.uniform(-bound, bound, size=int(need.sum()))
+    flat = np.zeros(need.shape)
+    flat[need] = draws                                               # row-major over (point, {x, y}): the reference's order
+    moved[:, 1] += flat[:, 0]
+    moved[:, 0] += flat[:, 1]
     return grid, moved
 
 
@@ -134,6 +137,77 @@ def augment(fg, bg, alpha):
     b = np.random.uniform(0.7, 1.3)
     c = np.random.uniform(-0.07, 0.07)
     return change_illumination(new_fg, a, b, c), change_illumination(new_bg, a, b, c), new_alpha
+
+
+AUG_PARAMS = np.dtype([("M", "<f8", (6,)), ("tu", "<i4"), ("tv", "<i4")])       # csrc/vm_affine.cu VmAugParams
+
+
+def augment_clip(fg_bgra, bg):
+    """augment() for a whole clip in a handful of launches (BASELINE config 5).
+
+    ``fg_bgra`` (n, H, W, 4) uint8 BGRA with alpha = A/255 (what reader.read_fg_img returns, reference
+    reader.py:16-17), ``bg`` (n, H, W, 3) uint8; NumPy arrays or CUDA tensors.  Equivalent to
+    ``[augment(fg[k, ..., :3], bg[k], fg[k, ..., 3] / 255.) for k in range(n)]``: the global np.random
+    stream is consumed in exactly that order (40 draws per frame, reference augmentation.py:102-135), the
+    TPS systems are solved on the host with numpy's pinv (reference tps.py:119).  Returns
+    (new_fg (n,H,W,3) uint8, new_bg (n,H,W,3) uint8, new_alpha (n,H,W) float32) of the input kind."""
+    import ctypes
+    lib = N.load()
+    fg_d, kind = N.to_device(fg_bgra)
+    bg_d, _ = N.to_device(bg)
+    assert fg_d.dtype == torch.uint8 and fg_d.dim() == 4 and fg_d.shape[3] == 4, "fg must be (n, H, W, 4) uint8 BGRA"
+    n, h, w = fg_d.shape[:3]
+    assert bg_d.dtype == torch.uint8 and tuple(bg_d.shape) == (n, h, w, 3), "bg must be (n, H, W, 3) uint8"
+    fg_d, bg_d = fg_d.contiguous(), bg_d.contiguous()
+    dev = fg_d.device
+    new_fg = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+    new_bg = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+    new_alpha = torch.empty((n, h, w), dtype=torch.float32, device=dev)
+    if n == 0:
+        return tuple(N.from_device(t, kind) for t in (new_fg, new_bg, new_alpha))
+    # ---- object_size / fg_center of every frame: one kernel, one host read --------------------------
+    stats = torch.zeros((n, 3), dtype=torch.int64, device=dev)
+    N.check(lib.vm_alpha_stats_bgra(N.ptr(fg_d), n, h, w, N.ptr(stats), N.stream_ptr()))
+    stats = stats.cpu().numpy()
+    # ---- the reference's random draws, frame by frame, in its order -----------------------------------
+    bt, br, bs = 0.05, 10, 0.15
+    par_bg = np.zeros(n, dtype=AUG_PARAMS); par_fg = np.zeros(n, dtype=AUG_PARAMS)
+    luts = np.zeros((n, 256), dtype=np.uint8)
+    grids = []
+    for k in range(n):
+        cnt, si, sj = (int(v) for v in stats[k])
+        fg_size = np.sqrt(cnt)
+        tu_bg = int(np.random.uniform(-w * bt, w * bt)); tv_bg = int(np.random.uniform(-h * bt, h * bt))
+        scale_bg = np.random.uniform(1., 1. + bs)
+        grids.append(deform_grid(h, w))
+        tu_fg = int(np.random.uniform(-fg_size * bt, fg_size * bt)); tv_fg = int(np.random.uniform(-fg_size * bt, fg_size * bt))
+        rot_fg = np.random.uniform(-br, br)
+        scale_fg = np.random.uniform(1., 1. + bs)
+        if cnt == 0:
+            raise ValueError("cannot convert float NaN to integer")       # int(np.mean([])) in fg_center
+        center = (int(sj / cnt), int(si / cnt))
+        a = np.random.uniform(0.95, 1.05); b = np.random.uniform(0.7, 1.3); c = np.random.uniform(-0.07, 0.07)
+        par_bg[k] = (_rotation_matrix((w // 2, h // 2), 0., scale_bg).reshape(6), tu_bg, tv_bg)
+        par_fg[k] = (_rotation_matrix(center, rot_fg, scale_fg).reshape(6), tu_fg, tv_fg)
+        luts[k] = illumination_lut(a, b, c)
+    # ---- host TPS solve (system built from the deformed grid, tps.py:51), then the device stages -----
+    plan = P.get_plan((0, 0, h, w), 2, dev)
+    ctrl, coef = P.solve_grids(grids, dev)
+    up = lambda arr: torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).to(dev)
+    par_bg_d, par_fg_d, luts_d = up(par_bg), up(par_fg), up(luts)
+    T = torch.empty((n, plan.nx, plan.ny, 2), dtype=torch.float64, device=dev)
+    counter = torch.zeros(64, dtype=torch.int32, device=dev)
+    inter = torch.empty((n, h + 1, w + 1, 2), dtype=torch.int32, device=dev)
+    status = N.new_status(dev)
+    Np = ctrl.shape[1]
+    N.check(lib.vm_tps_coarse_packed(N.ptr(ctrl), N.ptr(coef), n, Np, plan.nx, plan.ny, plan.step_x, plan.step_y,
+                                     N.ptr(T), N.ptr(counter), N.stream_ptr()))
+    N.check(lib.vm_aug_tps(N.ptr(fg_d), N.ptr(T), plan.nx, plan.ny, N.ptr(plan.rows), N.ptr(plan.cols), n, h, w,
+                           N.ptr(inter), N.ptr(status), N.stream_ptr()))
+    N.check(lib.vm_aug_affine(1, N.ptr(inter), N.ptr(par_fg_d), N.ptr(luts_d), n, h, w, N.ptr(new_fg), N.ptr(new_alpha),
+                              N.stream_ptr()))
+    N.check(lib.vm_aug_affine(0, N.ptr(bg_d), N.ptr(par_bg_d), N.ptr(luts_d), n, h, w, N.ptr(new_bg), None, N.stream_ptr()))
+    return tuple(N.from_device(t, kind) for t in (new_fg, new_bg, new_alpha))
 
 
 def augmentation(dim_dataset, voc_dataset, sig_dataset):

@@ -67,6 +67,40 @@ extern "C" int vm_warp_affine(const void *src, int dtype, int channels, int sh, 
 // ---------------------------------------------------------------------------------------
 struct VmLut256 { uint8_t v[256]; };
 
+// one pixel of change_illumination: BGR2HSV (integer tables) -> S/V through `slut` -> HSV2BGR (float
+// formulation of OpenCV's HSV2RGB_f with hscale = 6/180).  Returns B | G<<8 | R<<16.
+__device__ __forceinline__ uint32_t vm_illum_px(int b, int g, int r, const int *__restrict__ sdiv, const int *__restrict__ hdiv,
+                                                const uint8_t *__restrict__ slut) {
+    const int v = max(max(b, g), r), vmin = min(min(b, g), r), d = v - vmin;
+    int hh = (v == r) ? (g - b) : ((v == g) ? (b - r + 2 * d) : (r - g + 4 * d));
+    const int s = (d * sdiv[v] + (1 << 11)) >> 12;
+    hh = (hh * hdiv[d] + (1 << 11)) >> 12;
+    if (hh < 0) hh += 180;
+    const int s2 = slut[s], v2 = slut[v];
+    const float fv = (float)v2 * (1.f / 255.f), fs = (float)s2 * (1.f / 255.f);
+    float ob = fv, og = fv, orr = fv;
+    if (s2 != 0) {
+        float hf = (float)hh * (6.f / 180.f);
+        const float fl = floorf(hf);
+        int sec = (int)fl;
+        hf -= fl;
+        sec %= 6; if (sec < 0) sec += 6;
+        float tab[4];
+        tab[0] = fv;
+        tab[1] = __fmul_rn(fv, 1.f - fs);
+        tab[2] = __fmul_rn(fv, 1.f - __fmul_rn(fs, hf));
+        tab[3] = __fmul_rn(fv, 1.f - __fmul_rn(fs, 1.f - hf));
+        const int ib[6] = {1, 1, 3, 0, 0, 2}, ig[6] = {3, 0, 0, 2, 1, 1}, ir[6] = {0, 2, 1, 1, 3, 0};
+        ob = tab[ib[sec]]; og = tab[ig[sec]]; orr = tab[ir[sec]];
+    }
+    const uint32_t B = (uint32_t)max(0, min(255, __float2int_rn(ob * 255.f)));
+    const uint32_t G = (uint32_t)max(0, min(255, __float2int_rn(og * 255.f)));
+    const uint32_t R = (uint32_t)max(0, min(255, __float2int_rn(orr * 255.f)));
+    return B | (G << 8) | (R << 16);
+}
+
+
+
 __global__ void __launch_bounds__(256)
 k_illumination(const uint8_t *__restrict__ bgr, int64_t npx, VmLut256 lut, uint8_t *__restrict__ out) {
     __shared__ int sdiv[256], hdiv[256];
@@ -80,33 +114,8 @@ k_illumination(const uint8_t *__restrict__ bgr, int64_t npx, VmLut256 lut, uint8
     __syncthreads();
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npx;
          p += (int64_t)gridDim.x * blockDim.x) {
-        const int b = bgr[p * 3], g = bgr[p * 3 + 1], r = bgr[p * 3 + 2];
-        const int v = max(max(b, g), r), vmin = min(min(b, g), r), d = v - vmin;
-        int hh = (v == r) ? (g - b) : ((v == g) ? (b - r + 2 * d) : (r - g + 4 * d));
-        const int s = (d * sdiv[v] + (1 << 11)) >> 12;
-        hh = (hh * hdiv[d] + (1 << 11)) >> 12;
-        if (hh < 0) hh += 180;
-        const int s2 = slut[s], v2 = slut[v];
-        // HSV2BGR, float formulation (OpenCV HSV2RGB_f with hscale = 6/180)
-        const float fv = (float)v2 * (1.f / 255.f), fs = (float)s2 * (1.f / 255.f);
-        float ob = fv, og = fv, orr = fv;
-        if (s2 != 0) {
-            float hf = (float)hh * (6.f / 180.f);
-            const float fl = floorf(hf);
-            int sec = (int)fl;
-            hf -= fl;
-            sec %= 6; if (sec < 0) sec += 6;
-            float tab[4];
-            tab[0] = fv;
-            tab[1] = __fmul_rn(fv, 1.f - fs);
-            tab[2] = __fmul_rn(fv, 1.f - __fmul_rn(fs, hf));
-            tab[3] = __fmul_rn(fv, 1.f - __fmul_rn(fs, 1.f - hf));
-            const int ib[6] = {1, 1, 3, 0, 0, 2}, ig[6] = {3, 0, 0, 2, 1, 1}, ir[6] = {0, 2, 1, 1, 3, 0};
-            ob = tab[ib[sec]]; og = tab[ig[sec]]; orr = tab[ir[sec]];
-        }
-        out[p * 3] = (uint8_t)max(0, min(255, __float2int_rn(ob * 255.f)));
-        out[p * 3 + 1] = (uint8_t)max(0, min(255, __float2int_rn(og * 255.f)));
-        out[p * 3 + 2] = (uint8_t)max(0, min(255, __float2int_rn(orr * 255.f)));
+        const uint32_t o = vm_illum_px(bgr[p * 3], bgr[p * 3 + 1], bgr[p * 3 + 2], sdiv, hdiv, slut);
+        out[p * 3] = (uint8_t)o; out[p * 3 + 1] = (uint8_t)(o >> 8); out[p * 3 + 2] = (uint8_t)(o >> 16);
     }
 }
 
@@ -170,4 +179,130 @@ extern "C" int vm_alpha_stats(const void *alpha, int dtype, int h, int w, unsign
     default: vm_set_error("vm_alpha_stats: unsupported dtype %d", dtype); return VM_ERR_ARG;
     }
     return vm_check_launch("vm_alpha_stats");
+}
+
+// ---------------------------------------------------------------------------------------
+// Batched augmentation (augmentation.py:102-135 for a whole clip): alpha statistics of BGRA frames, and
+// the fused tail of warp_image + change_illumination:
+//   warpAffine([[1,0,tu],[0,1,tv]], (w,h))  - an exact integer shift of the (sh, sw) source, 0 outside -
+//   warpAffine(getRotationMatrix2D(...), (w,h)) - cv2 fixed-point bilinear of that shifted (h, w) image -
+//   change_illumination (uint8 colours only).
+// Each tap (Y, X) of the second pass is the shifted image's pixel: source[Y - tv][X - tu] when 0 <= Y < h,
+// 0 <= X < w and the source index is inside (sh, sw); 0 otherwise - so the two passes need no intermediate.
+// ---------------------------------------------------------------------------------------
+struct VmAugParams { double M[6]; int tu, tv; };         // M: 2x3 matrix of the second pass; (tu, tv) of the first
+#define VA_AFF_ROWS 16                                   // rows per CTA of k_aug_affine (amortises the table set-up)
+
+__global__ void __launch_bounds__(256)
+k_alpha_stats_bgra(const uint32_t *__restrict__ bgra, int h, int w, unsigned long long *__restrict__ out) {
+    const int frame = blockIdx.y;
+    const uint32_t *a = bgra + (int64_t)frame * h * w;
+    unsigned long long cnt = 0, si = 0, sj = 0;
+    const int64_t n = (int64_t)h * w;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        if (__ldg(a + p) >> 24) {
+            const int i = (int)(p / w);
+            cnt += 1; si += (unsigned long long)i; sj += (unsigned long long)(p - (int64_t)i * w);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+        si += __shfl_down_sync(0xffffffffu, si, o);
+        sj += __shfl_down_sync(0xffffffffu, sj, o);
+    }
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        atomicAdd(out + frame * 3, cnt); atomicAdd(out + frame * 3 + 1, si); atomicAdd(out + frame * 3 + 2, sj);
+    }
+}
+
+// out (n, 3) uint64 {count(A != 0), sum(rows), sum(cols)} per frame; `out` must be zeroed by the caller
+extern "C" int vm_alpha_stats_bgra(const uint8_t *bgra, int n, int h, int w, unsigned long long *out, void *stream) {
+    VM_REQUIRE(bgra && out, "null pointer");
+    VM_REQUIRE(n >= 0 && n < 65536 && h >= 1 && w >= 1, "bad size");
+    if (n == 0) return VM_OK;
+    const dim3 grid(min(vm_blocks((int64_t)h * w, 1024), 592u), n);
+    k_alpha_stats_bgra<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t *>(bgra), h, w, out);
+    return vm_check_launch("vm_alpha_stats_bgra");
+}
+
+// FG: source = packed (sh, sw) = (h+1, w+1) intermediate {bgr, alpha float bits} of vm_aug_tps -> new_fg uint8 x3
+// (after the illumination change) + new_alpha float32.  !FG: source = (h, w, 3) uint8 background -> new_bg.
+template <bool FG>
+__global__ void __launch_bounds__(256)
+k_aug_affine(const void *__restrict__ src_all, const VmAugParams *__restrict__ params, const uint8_t *__restrict__ luts,
+             int h, int w, uint8_t *__restrict__ out_bgr, float *__restrict__ out_alpha) {
+    __shared__ int sdiv[256], hdiv[256];
+    __shared__ uint8_t slut[256];
+    __shared__ VmAffineInv Ash;
+    __shared__ int tsh[2];
+    const int frame = blockIdx.z;
+    {
+        const int k = threadIdx.x;
+        sdiv[k] = k ? __double2int_rn(1044480.0 / (double)k) : 0;            // 255 << 12
+        hdiv[k] = k ? __double2int_rn(737280.0 / (6.0 * (double)k)) : 0;     // 180 << 12
+        slut[k] = luts[frame * 256 + k];
+        if (k == 0) {
+            const VmAugParams P = params[frame];
+            double D = P.M[0] * P.M[4] - P.M[1] * P.M[3];                      // OpenCV's closed-form inverse
+            D = D != 0 ? 1. / D : 0;
+            VmAffineInv r;
+            r.i00 = P.M[4] * D; r.i01 = P.M[1] * (-D);
+            r.i10 = P.M[3] * (-D); r.i11 = P.M[0] * D;
+            r.b0 = -r.i00 * P.M[2] - r.i01 * P.M[5];
+            r.b1 = -r.i10 * P.M[2] - r.i11 * P.M[5];
+            Ash = r; tsh[0] = P.tu; tsh[1] = P.tv;
+        }
+    }
+    __syncthreads();
+    const int sh = FG ? h + 1 : h, sw = FG ? w + 1 : w;
+    const int tu = tsh[0], tv = tsh[1];
+    const VmAffineInv A = Ash;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    const int yend = min((int)(blockIdx.y + 1) * VA_AFF_ROWS, h);
+    for (int y = blockIdx.y * VA_AFF_ROWS; y < yend; ++y) {
+        int SX, SY;
+        vm_affine_coords(A, x, y, SX, SY);
+        const int ix = vm_sat_s16(SX >> 5), iy = vm_sat_s16(SY >> 5), fx = SX & 31, fy = SY & 31;
+        uint32_t c[4];
+        double al[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int Y = iy + (t >> 1), X = ix + (t & 1);
+            const int sy = Y - tv, sx = X - tu;
+            const bool ok = (unsigned)Y < (unsigned)h && (unsigned)X < (unsigned)w && (unsigned)sy < (unsigned)sh && (unsigned)sx < (unsigned)sw;
+            c[t] = 0u; al[t] = 0.0;
+            if (ok) {
+                if (FG) {
+                    const uint2 e = __ldg(reinterpret_cast<const uint2 *>(src_all) + ((int64_t)frame * sh + sy) * sw + sx);
+                    c[t] = e.x; al[t] = (double)__uint_as_float(e.y);
+                } else {
+                    const uint8_t *p = reinterpret_cast<const uint8_t *>(src_all) + (((int64_t)frame * sh + sy) * sw + sx) * 3;
+                    c[t] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+                }
+            }
+        }
+        int ch[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            ch[k] = VmTap<uint8_t>::blend((c[0] >> (8 * k)) & 255, (c[1] >> (8 * k)) & 255, (c[2] >> (8 * k)) & 255, (c[3] >> (8 * k)) & 255, fx, fy);
+        const uint32_t o = vm_illum_px(ch[0], ch[1], ch[2], sdiv, hdiv, slut);
+        const int64_t p = ((int64_t)frame * h + y) * w + x;
+        out_bgr[p * 3] = (uint8_t)o; out_bgr[p * 3 + 1] = (uint8_t)(o >> 8); out_bgr[p * 3 + 2] = (uint8_t)(o >> 16);
+        if (FG) out_alpha[p] = (float)VmTap<double>::blend(al[0], al[1], al[2], al[3], fx, fy);
+    }
+}
+
+// mode 0: background (src = (n,h,w,3) uint8, out_alpha unused); mode 1: foreground (src = vm_aug_tps intermediate).
+// params: device array of n {double M[6]; int tu, tv}; luts: device (n, 256) uint8 S/V tables.
+extern "C" int vm_aug_affine(int mode, const void *src, const void *params, const uint8_t *luts, int n, int h, int w,
+                             uint8_t *out_bgr, float *out_alpha, void *stream) {
+    VM_REQUIRE(src && params && luts && out_bgr && (mode == 0 || out_alpha), "null pointer");
+    VM_REQUIRE(n >= 0 && n < 65536 && h >= 1 && h < 65536 && w >= 1, "bad size");
+    if (n == 0) return VM_OK;
+    const dim3 grid((w + 255) / 256, (h + VA_AFF_ROWS - 1) / VA_AFF_ROWS, n);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 1) k_aug_affine<true><<<grid, 256, 0, st>>>(src, (const VmAugParams *)params, luts, h, w, out_bgr, out_alpha);
+    else k_aug_affine<false><<<grid, 256, 0, st>>>(src, (const VmAugParams *)params, luts, h, w, out_bgr, out_alpha);
+    return vm_check_launch("vm_aug_affine");
 }

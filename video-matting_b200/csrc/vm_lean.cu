@@ -1406,3 +1406,113 @@ extern "C" int vm_lean_stage_ms(float *out4) {
 
 // number of kernels the lean path has launched in this process (all devices)
 extern "C" long long vm_lean_launch_count(void) { return g_vl_launches.load(); }
+
+// ---------------------------------------------------------------------------------------
+// Batched augmentation (SURVEY 8a-11 / BASELINE config 5): TPS stage of augmentation.warp_image for a
+// whole clip.  BGRA frames (alpha = A/255, reader.py:16) are resampled through the per-frame spline on
+// the (h+1) x (w+1) grid of tps.warp_images (tps.py:55) into a packed intermediate {B|G<<8|R<<16 with the
+// uint8 half-up rounding of map_coordinates, alpha' as float32 bits}; the two warpAffine passes and the
+// illumination change follow in vm_affine.cu (k_aug_affine).  Taps come straight from global memory:
+// this path is bound by its host orchestration (RNG draws and pinv per frame), not by this kernel.
+// ---------------------------------------------------------------------------------------
+__device__ __noinline__ uint2 vl_exact_cols(const uint32_t *__restrict__ src, double t0, double t1, int h, int w, int *outside) {
+    const VmBilin64 s = vm_mapcoord_setup(t0, t1, h, w);
+    if (!s.inside) {
+        (*outside)++;
+        return make_uint2(0u, 0u);                                      // map_coordinates: cval = 0
+    }
+    const uint32_t e0 = __ldg(src + ((int64_t)s.i0 * w + s.j0)), e1 = __ldg(src + ((int64_t)s.i0 * w + s.j1));
+    const uint32_t e2 = __ldg(src + ((int64_t)s.i1 * w + s.j0)), e3 = __ldg(src + ((int64_t)s.i1 * w + s.j1));
+    uint32_t bgr = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        bgr |= (uint32_t)vm_round_half_up_u8(vm_mapcoord_blend(s, (double)((e0 >> (8 * c)) & 255u), (double)((e1 >> (8 * c)) & 255u),
+                                                               (double)((e2 >> (8 * c)) & 255u), (double)((e3 >> (8 * c)) & 255u))) << (8 * c);
+    const double a64 = vm_mapcoord_blend(s, (double)(e0 >> 24) / 255.0, (double)(e1 >> 24) / 255.0,
+                                         (double)(e2 >> 24) / 255.0, (double)(e3 >> 24) / 255.0);
+    return make_uint2(bgr, __float_as_uint((float)a64));
+}
+
+#define VA_ROWS 16
+__global__ void __launch_bounds__(128)
+k_aug_tps(const uint32_t *__restrict__ fg, const double2 *__restrict__ T, int nx, int ny,
+          const vm_axis_entry *__restrict__ rows, const vm_axis_entry *__restrict__ cols, int h, int w,
+          uint2 *__restrict__ inter, int32_t *__restrict__ status) {
+    const int oh = h + 1, ow = w + 1;
+    const int j = blockIdx.x * 128 + threadIdx.x, frame = blockIdx.z;
+    const int ibeg = blockIdx.y * VA_ROWS, iend = min(ibeg + VA_ROWS, oh);
+    if (j >= ow) return;
+    const uint32_t *src = fg + (int64_t)frame * h * w;
+    uint2 *op = inter + (int64_t)frame * oh * ow + j;
+    const vm_axis_entry ce = vm_ld_axis(cols + j);
+    const double yf = ce.frac, y1 = 1.0 - yf;
+    const double2 *Ta = T + (int64_t)frame * nx * ny + ce.i0, *Tb = T + (int64_t)frame * nx * ny + ce.i1;
+    int k0 = -1, k1 = -1, outside = 0;
+    VlC C0 = {0.0, 0.0}, C1 = {0.0, 0.0};
+    for (int i = ibeg; i < iend; ++i) {
+        const vm_axis_entry re = vm_ld_axis(rows + i);
+        if (re.i0 != k0) {
+            if (re.i0 == k1) C0 = C1; else C0 = vl_col_lerp(__ldg(Ta + re.i0 * ny), __ldg(Tb + re.i0 * ny), y1, yf);
+            k0 = re.i0;
+        }
+        if (re.i1 != k1) {
+            if (re.i1 == k0) C1 = C0; else C1 = vl_col_lerp(__ldg(Ta + re.i1 * ny), __ldg(Tb + re.i1 * ny), y1, yf);
+            k1 = re.i1;
+        }
+        const double xf = re.frac, x1 = 1.0 - xf;
+        const double t0 = fma(C1.x, xf, C0.x * x1), t1 = fma(C1.y, xf, C0.y * x1);
+        int n0, n1;
+        uint32_t fa, fb;
+        const bool fast = vl_geometry(t0, t1, h, w, n0, n1, fa, fb);
+        uint2 o;
+        if (fast) {
+            const uint32_t *g0 = src + (n0 * w + n1), *g1 = g0 + w;
+            const uint32_t e0 = __ldg(g0), e1 = __ldg(g0 + 1), e2 = __ldg(g1), e3 = __ldg(g1 + 1);
+            const uint32_t A1 = fa >> 1, A0 = 0x80000000u - A1, B1 = fb >> 1, B0 = 0x80000000u - B1;
+            const uint32_t W00 = __umulhi(A0, B0), W01 = __umulhi(A0, B1), W10 = __umulhi(A1, B0), W11 = __umulhi(A1, B1);
+            const uint32_t w0 = W00 >> 6, w1 = W01 >> 6, w2 = W10 >> 6, w3 = W11 >> 6;
+            uint32_t bgr = 0;
+            bool knife = false;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const uint32_t v = ((e0 >> (8 * c)) & 255u) * w0 + ((e1 >> (8 * c)) & 255u) * w1 + ((e2 >> (8 * c)) & 255u) * w2 +
+                                   ((e3 >> (8 * c)) & 255u) * w3 + (8388608u + 1100u);
+                bgr |= (v >> 24) << (8 * c);
+                knife |= (v & 0x00FFFFFFu) < 1108u;
+            }
+            const unsigned long long a2f = (unsigned long long)(e0 >> 24) * W00 + (unsigned long long)(e1 >> 24) * W01 +
+                                           (unsigned long long)(e2 >> 24) * W10 + (unsigned long long)(e3 >> 24) * W11;
+            o = make_uint2(bgr, __float_as_uint((float)a2f * (float)(1.0 / (255.0 * 1073741824.0))));
+            if (knife) o = vl_exact_cols(src, t0, t1, h, w, &outside);
+        } else {
+            o = vl_exact_cols(src, t0, t1, h, w, &outside);
+        }
+        op[(int64_t)i * ow] = o;
+    }
+    if (status && outside) atomicAdd(status + VM_STATUS_TPS_OUTSIDE, outside);
+}
+
+// coarse transform of n frames as (n, nx, ny) double2 {row coordinate, column coordinate} - the spline stage
+// of the fused paths as a stand-alone entry point.  `counter`: one zero-initialisable device word.
+extern "C" int vm_tps_coarse_packed(const double *ctrl, const double *coef, int n, int N, int nx, int ny, double step_x,
+                                    double step_y, void *T, unsigned int *counter, void *stream) {
+    VM_REQUIRE(ctrl && coef && T && counter, "null pointer");
+    VM_REQUIRE(n >= 0 && N >= 1 && N <= VL_MAX_N && nx >= 1 && ny >= 1, "bad size");
+    if (n == 0) return VM_OK;
+    int dev = 0;
+    int rc = vl_init(&dev);
+    if (rc != VM_OK) return rc;
+    return vl_launch_coarse(ctrl, coef, N, n, nx, ny, step_x, step_y, reinterpret_cast<double2 *>(T), counter, (cudaStream_t)stream);
+}
+
+extern "C" int vm_aug_tps(const uint8_t *fg_bgra, const void *T, int nx, int ny, const vm_axis_entry *rows,
+                          const vm_axis_entry *cols, int n, int h, int w, void *inter, int32_t *status, void *stream) {
+    VM_REQUIRE(fg_bgra && T && rows && cols && inter, "null pointer");
+    VM_REQUIRE(n >= 0 && n < 65536 && h >= 2 && w >= 2 && (int64_t)(h + 1) * (w + 1) < (1ll << 28), "bad size");
+    if (n == 0) return VM_OK;
+    const dim3 grid((w + 1 + 127) / 128, (h + 1 + VA_ROWS - 1) / VA_ROWS, n);
+    VM_REQUIRE(grid.y <= 65535, "frame too tall");
+    k_aug_tps<<<grid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t *>(fg_bgra), reinterpret_cast<const double2 *>(T), nx, ny,
+                                                       rows, cols, h, w, reinterpret_cast<uint2 *>(inter), status);
+    return vm_check_launch("vm_aug_tps");
+}
