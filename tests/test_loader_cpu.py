@@ -1,0 +1,95 @@
+"""CPU tests of the batch-loader row: the oracle restatement against the golden
+vectors produced by the unmodified reference ``loader.py`` and against cv2.resize, plus the
+host-side crop planning of the product against the oracle's array slicing."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import vm_loader_oracle as LO
+import vm_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import make_loader_golden as MG  # noqa: E402
+
+cv2 = pytest.importorskip("cv2")
+
+
+@pytest.fixture(scope="module")
+def lgold():
+    with np.load(os.path.join(ROOT, "tests", "golden", "loader_golden.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def sample_files(lgold, tag, d):
+    return MG.write_inputs(str(d), {k: lgold[f"{tag}_file_{k}"] for k in ("fg", "prev", "bg", "flo", "hw")})
+
+
+def decode(paths):
+    fg = cv2.imread(paths["fg"], cv2.IMREAD_UNCHANGED)
+    prev = cv2.imread(paths["prev"], cv2.IMREAD_UNCHANGED)
+    bg = cv2.imread(paths["bg"])
+    tri = cv2.imread(paths["tri"], 0)
+    flo, ok = O.parse_flo(open(paths["flo"], "rb").read())
+    assert ok
+    return fg, prev, bg, tri, flo
+
+
+def close(got, ref, what):
+    assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"
+    err = np.abs(got - ref)
+    tol = 1e-5 * np.abs(ref) + 1e-9
+    assert np.all(err <= tol), f"{what}: max err {err.max():.3e}"
+
+
+@pytest.mark.parametrize("shape,dsize", [
+    ((480, 480, 3), (320, 320)), ((640, 640, 3), (320, 320)), ((320, 320, 3), (320, 320)),
+    ((561, 998, 3), (320, 320)), ((77, 131), (320, 320)), ((640, 640), (320, 320)),
+    ((333, 640, 3), (320, 320)), ((640, 1280, 3), (320, 640)), ((200, 100, 3), (96, 128)),
+    ((641, 640, 1), (320, 320)), ((3, 2, 3), (16, 16)), ((2, 5), (7, 9)), ((480, 640, 3), (128, 96))])
+def test_resize_model_matches_cv2(shape, dsize):
+    rng = np.random.default_rng(sum(shape) + dsize[0])
+    src = rng.uniform(0, 255, shape)
+    ref = cv2.resize(src, dsize, interpolation=cv2.INTER_LINEAR)
+    got = LO.resize_linear_f64(src, dsize)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1e-9
+
+
+def test_get_padded_img_matches_reference_draw_order():
+    # the reference draws rows before columns, one randint per axis (loader.py:15-34)
+    rng = np.random.RandomState(5)
+    img = np.arange(6 * 9 * 2, dtype=np.float64).reshape(6, 9, 2)
+    out = LO.get_padded_img(img, 8, 4, rng)
+    rng2 = np.random.RandomState(5)
+    oi = rng2.randint(0, 8 - 6 + 1)
+    ij = rng2.randint(0, 9 - 4 + 1)
+    exp = np.zeros((8, 9, 2))
+    exp[oi:oi + 6, 0:4] = img[:, ij:ij + 4]
+    assert np.array_equal(out, exp)
+
+
+@pytest.mark.parametrize("tag", [c[0] for c in MG.CASES])
+def test_oracle_matches_reference_golden(lgold, tag, tmp_path):
+    lat = int(lgold["lattice"])
+    fg, prev, bg, tri, flo = decode(sample_files(lgold, tag, tmp_path))
+    w_in, h_in, seed = (int(v) for v in lgold[f"{tag}_meta"])
+    input_size = (w_in, h_in)
+    res = LO.video_sample(fg, bg, prev, flo, input_size, np.random.RandomState(seed))
+    for name, a in zip(("cmp", "bg", "label", "warped", "fg"), res):
+        close(a[::lat, ::lat], lgold[f"{tag}_video_{name}"], f"{tag} video {name}")
+    shapes = [a.shape + (0,) * (3 - a.ndim) for a in res]
+    assert np.array_equal(np.array(shapes), lgold[f"{tag}_video_shapes"])
+    res = LO.simple_sample(fg, bg, input_size, np.random.RandomState(seed + 100))
+    for name, a in zip(("cmp", "bg", "label", "fg"), res):
+        close(a[::lat, ::lat], lgold[f"{tag}_simple_{name}"], f"{tag} simple {name}")
+    res = LO.trimap_sample(fg, tri, bg, input_size, np.random.RandomState(seed + 200))
+    for name, a in zip(("inp", "label", "fg"), res):
+        close(a[::lat, ::lat], lgold[f"{tag}_trimap_{name}"], f"{tag} trimap {name}")
+
+
+def test_psnr(lgold):
+    assert abs(LO.psnr(lgold["psnr_a"], lgold["psnr_b"]) - float(lgold["psnr_3"])) < 1e-9
+    assert abs(LO.psnr(lgold["psnr_a"][:, :, 0], lgold["psnr_b"][:, :, 0]) - float(lgold["psnr_1"])) < 1e-9
