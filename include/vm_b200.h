@@ -205,6 +205,54 @@ int vm_aug_tps(const uint8_t *fg_bgra, const void *T, int nx, int ny, const vm_a
 int vm_aug_affine(int mode, const void *src, const void *params, const uint8_t *luts, int n, int h, int w,
                   uint8_t *out_bgr, float *out_alpha, void *stream);
 
+/* ---- batch loader: loader.load_and_crop / simple_load_crop / video_load_crop ----
+ * reference: loader.py:39-85, 119-157, 285-330 (one sample), loader.py:93-116, 160-171, 333-345 (batch).
+ * The host decodes the files, draws the reference's np.random.randint sequence (crop type, padding
+ * offsets of get_padded_img loader.py:10-36, crop origins) and describes each sample by two views;
+ * the device does everything after the decode for the whole batch in one launch: flow.warp_img of the
+ * previous alpha (flow.py:9-18), padding, crop, cv2.resize(INTER_LINEAR) of the float64 planes
+ * (loader.py:316-319), create_composite_image (reader.py:72-79), VGG-mean subtraction (loader.py:322-323)
+ * and the optional mirror of get_batch (loader.py:107-110).
+ *
+ * A view maps the window that is resized back to image pixels: window (r, c) is canvas
+ * (wi + r, wj + c); canvas cells inside [vi0,vi1) x [vj0,vj1) hold image pixel
+ * (si + row - vi0, sj + col - vj0), all others hold 0 (the zero canvas of get_padded_img).
+ * mode 0: separable linear interpolation with scale = 1 / (dst / src) per axis (double coefficients,
+ * as OpenCV 4.13 does for CV_64F); mode 1: 2x2 block mean (OpenCV's INTER_AREA switch for exact 2x).  */
+typedef struct {
+    int32_t win_h, win_w;            /* size of the resized window                                */
+    int32_t wi, wj;                  /* window origin in the canvas                               */
+    int32_t vi0, vi1, vj0, vj1;      /* canvas rectangle that holds image data                    */
+    int32_t si, sj;                  /* image pixel at canvas (vi0, vj0)                          */
+    int32_t mode, reserved;
+    double  scale_y, scale_x;
+} vm_loader_view;
+
+typedef struct {
+    const uint8_t *fg;               /* (fh, fw, 4) uint8 BGRA: foreground B,G,R and A = 255 * alpha; may be a
+                                        sub-rectangle of the decoded image whose origin is (oy, ox)       */
+    const uint8_t *prev;             /* alpha byte of the previous frame's pixel (0, 0), pixels prev_stride
+                                        bytes apart, rows pw pixels long, (ph, pw) pixels; or NULL        */
+    const float   *flow;             /* (fh, fw, 2) float32 on the same rectangle as fg; required with prev */
+    const uint8_t *bg;               /* (bh, bw, 3) uint8 BGR                                              */
+    int32_t fh, fw, bh, bw;
+    int32_t oy, ox;                  /* full-image coordinates of fg / flow element (0, 0)                 */
+    int32_t ph, pw, prev_stride;
+    int32_t flip;                    /* flip != 0: outputs mirrored along the columns                      */
+    vm_loader_view fgv, bgv;
+} vm_loader_sample;
+
+/* samples: DEVICE array of n descriptors.  Outputs are (n, out_h, out_w, C) of out_dtype (VM_F64 as the
+ * reference, or VM_F32): cmp C=3 (composite - mean), bg C=3 (resized background - mean), label C=1
+ * (alpha), warped C=3 (resized flow-warped previous alpha, repeated), fg C=3 (resized foreground); any of
+ * them may be NULL.  mean_host: 3 doubles on the HOST (params.VGG_MEAN).                                */
+int vm_loader_batch(const vm_loader_sample *samples, int n, int out_h, int out_w, const double *mean_host,
+                    int out_dtype, void *cmp, void *bg, void *label, void *warped, void *fg, void *stream);
+
+/* loader.psnr (loader.py:214-227): adds sum((a - b)^2) over n elements into the device double *out
+ * (zeroed by the caller); dtype VM_F32 or VM_F64.                                                       */
+int vm_sq_err_sum(const void *a, const void *b, int dtype, int64_t n, double *out, void *stream);
+
 /* Measurement hooks of the default fused path (no reference counterpart; used by bench.py).
  * vm_lean_stage_ms: durations in ms of {spline, tile boxes, flow stage, resampling+composite}
  * of the first chunk of the last call made with "lean_timing" = 1 on the current device, after

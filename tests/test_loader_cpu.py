@@ -93,3 +93,69 @@ def test_oracle_matches_reference_golden(lgold, tag, tmp_path):
 def test_psnr(lgold):
     assert abs(LO.psnr(lgold["psnr_a"], lgold["psnr_b"]) - float(lgold["psnr_3"])) < 1e-9
     assert abs(LO.psnr(lgold["psnr_a"][:, :, 0], lgold["psnr_b"][:, :, 0]) - float(lgold["psnr_1"])) < 1e-9
+
+
+# ---- host-side planning of the product (no GPU needed) ------------------------------------------
+
+def view_window(img, v):
+    """NumPy emulation of what csrc/vm_loader.cu reads through a view descriptor."""
+    out = np.zeros((int(v["win_h"]), int(v["win_w"])) + img.shape[2:], dtype=np.float64)
+    for r in range(out.shape[0]):
+        cr = int(v["wi"]) + r
+        if not (int(v["vi0"]) <= cr < int(v["vi1"])):
+            continue
+        c0, c1 = max(int(v["vj0"]), int(v["wj"])), min(int(v["vj1"]), int(v["wj"]) + out.shape[1])
+        if c1 > c0:
+            src_r = cr - int(v["vi0"]) + int(v["si"])
+            src_c = c0 - int(v["vj0"]) + int(v["sj"])
+            out[r, c0 - int(v["wj"]):c1 - int(v["wj"])] = img[src_r, src_c:src_c + (c1 - c0)]
+    return out
+
+
+@pytest.mark.parametrize("fg_hw,bg_hw,input_size,seed", [
+    ((400, 520), (300, 410), (320, 320), 0), ((250, 700), (640, 640), (320, 320), 1),
+    ((700, 250), (333, 222), (160, 160), 2), ((100, 90), (50, 60), (64, 48), 3),
+    ((660, 650), (320, 320), (320, 320), 4), ((640, 640), (640, 640), (320, 320), 5),
+    ((480, 900), (100, 100), (320, 320), 6), ((320, 320), (320, 320), (320, 320), 7)])
+def test_plan_matches_oracle_crops(vm, fg_hw, bg_hw, input_size, seed):
+    rng = np.random.default_rng(seed)
+    fg = rng.integers(0, 256, size=fg_hw + (4,), dtype=np.uint8)
+    bg = rng.integers(0, 256, size=bg_hw + (3,), dtype=np.uint8)
+    for rep in range(4):
+        np.random.seed(1000 * seed + rep)
+        fgv, bgv = vm.loader._plan_sample(fg_hw[0], fg_hw[1], bg_hw[0], bg_hw[1], input_size)
+        state_after = np.random.get_state()[1][:8].copy(), np.random.get_state()[2]
+        ref = LO.simple_sample(fg, bg, input_size, np.random.RandomState(1000 * seed + rep))
+        # same number of draws consumed as the reference sequence
+        r2 = np.random.RandomState(1000 * seed + rep)
+        LO.simple_sample(fg, bg, input_size, r2)
+        assert np.array_equal(state_after[0], r2.get_state()[1][:8]) and state_after[1] == r2.get_state()[2]
+        got_fg = LO.resize_linear_f64(view_window(fg[..., :3], fgv), input_size)
+        got_bg = LO.resize_linear_f64(view_window(bg, bgv), input_size) - LO.VGG_MEAN
+        assert np.array_equal(got_fg, ref[3])
+        assert np.array_equal(got_bg, ref[1])
+        assert int(fgv["mode"]) == int(fgv["win_h"] == 2 * input_size[1] and fgv["win_w"] == 2 * input_size[0])
+        # staging copies only the rectangle a view can touch; the re-based view reads the same window
+        for img, v in ((fg, fgv), (bg, bgv)):
+            (r0, r1, c0, c1), v2 = vm.loader._touched(v, img.shape[0], img.shape[1])
+            assert 0 <= r0 < r1 <= img.shape[0] and 0 <= c0 < c1 <= img.shape[1]
+            assert np.array_equal(view_window(img[r0:r1, c0:c1], v2), view_window(img, v))
+
+
+def test_product_get_padded_img_matches_oracle(vm):
+    img = np.random.default_rng(0).uniform(0, 1, (37, 91, 5))
+    for k, (ch, cw) in enumerate([(64, 64), (20, 120), (64, 50), (37, 91), (10, 10)]):
+        np.random.seed(k)
+        got = vm.loader.get_padded_img(img, ch, cw)
+        assert np.array_equal(got, LO.get_padded_img(img, ch, cw, np.random.RandomState(k)))
+
+
+def test_descriptor_layout_matches_header(vm):
+    import re
+    hdr = open(os.path.join(ROOT, "include", "vm_b200.h")).read()
+    body = re.search(r"typedef struct \{([^}]*)\} vm_loader_view;", hdr).group(1)
+    names = re.findall(r"\b(\w+)\s*[,;]", re.sub(r"/\*.*?\*/", "", body, flags=re.S))
+    assert names == list(vm.loader.VIEW_DTYPE.names)
+    body = re.search(r"typedef struct \{([^}]*)\} vm_loader_sample;", hdr).group(1)
+    names = re.findall(r"\*?(\w+)\s*[,;]", re.sub(r"/\*.*?\*/", "", body, flags=re.S))
+    assert names == list(vm.loader.SAMPLE_DTYPE.names)

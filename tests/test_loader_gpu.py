@@ -1,0 +1,149 @@
+"""GPU parity tests of the batch loader: video-matting_b200/loader.py (through the
+C ABI entry vm_loader_batch) against the golden vectors of the unmodified reference loader.py and
+against the NumPy oracle on the same files and the same np.random seeds.
+
+Tolerance (floats, BASELINE north_star): |got - ref| <= 1e-5 * |ref| + 1e-9 on 0..255 data."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import vm_loader_oracle as LO
+import vm_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import make_loader_golden as MG  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+cv2 = pytest.importorskip("cv2")
+
+
+@pytest.fixture(scope="module")
+def lgold():
+    with np.load(os.path.join(ROOT, "tests", "golden", "loader_golden.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def files_of(lgold, tag, d):
+    os.makedirs(str(d), exist_ok=True)
+    return MG.write_inputs(str(d), {k: lgold[f"{tag}_file_{k}"] for k in ("fg", "prev", "bg", "flo", "hw")})
+
+
+def close(got, ref, what, rtol=1e-5, atol=1e-9):
+    got, ref = np.asarray(got), np.asarray(ref)
+    assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"
+    err = np.abs(got - ref)
+    assert np.all(err <= rtol * np.abs(ref) + atol), f"{what}: max err {err.max():.3e}"
+
+
+@pytest.mark.parametrize("tag", [c[0] for c in MG.CASES])
+def test_load_crop_variants_match_reference_and_oracle(vm, lgold, tag, tmp_path):
+    L = vm.loader
+    lat = int(lgold["lattice"])
+    p = files_of(lgold, tag, tmp_path)
+    w_in, h_in, seed = (int(v) for v in lgold[f"{tag}_meta"])
+    size = (w_in, h_in)
+    fg = cv2.imread(p["fg"], cv2.IMREAD_UNCHANGED)
+    prev = cv2.imread(p["prev"], cv2.IMREAD_UNCHANGED)
+    bg = cv2.imread(p["bg"])
+    tri = cv2.imread(p["tri"], 0)
+    flo, _ = O.parse_flo(open(p["flo"], "rb").read())
+
+    np.random.seed(seed)
+    got = L.video_load_crop((p["fg"], p["bg"], p["prev"], p["flo"]), size)
+    ref = LO.video_sample(fg, bg, prev, flo, size, np.random.RandomState(seed))
+    for name, g, r in zip(("cmp", "bg", "label", "warped", "fg"), got, ref):
+        assert g.dtype == np.float64
+        close(g, r, f"{tag} video {name} vs oracle")
+        close(g[::lat, ::lat], lgold[f"{tag}_video_{name}"], f"{tag} video {name} vs reference")
+    assert np.array_equal(got[4], ref[4]), "resized foreground is bit-equal to the oracle"
+
+    np.random.seed(seed + 100)
+    got = L.simple_load_crop((p["fg"], p["tri"], p["bg"]), size)
+    for name, g in zip(("cmp", "bg", "label", "fg"), got):
+        close(g[::lat, ::lat], lgold[f"{tag}_simple_{name}"], f"{tag} simple {name} vs reference")
+
+    np.random.seed(seed + 200)
+    got = L.load_and_crop((p["fg"], p["tri"], p["bg"]), size)
+    ref = LO.trimap_sample(fg, tri, bg, size, np.random.RandomState(seed + 200))
+    for name, g, r in zip(("inp", "label", "fg"), got, ref):
+        close(g, r, f"{tag} trimap {name} vs oracle")
+        close(g[::lat, ::lat], lgold[f"{tag}_trimap_{name}"], f"{tag} trimap {name} vs reference")
+
+
+def batch_entries(lgold, tmp_path):
+    ev, es = [], []
+    for tag in lgold["batch_tags"]:
+        p = files_of(lgold, str(tag), tmp_path / str(tag))
+        ev.append((p["fg"], p["bg"], p["prev"], p["flo"]))
+        es.append((p["fg"], p["tri"], p["bg"]))
+    return ev, es
+
+
+def test_batch_entry_points_match_reference(vm, lgold, tmp_path):
+    L = vm.loader
+    lat = 2 * int(lgold["lattice"])
+    ev, es = batch_entries(lgold, tmp_path)
+    np.random.seed(4242)
+    for name, g in zip(("cmp", "bg", "label", "warped", "fg"), L.video_batch(ev, (320, 320))):
+        close(g[:, ::lat, ::lat], lgold[f"batch_video_{name}"], f"video_batch {name}")
+    np.random.seed(4243)
+    for name, g in zip(("cmp", "bg", "label", "fg"), L.simple_batch(es, (320, 320))):
+        close(g[:, ::lat, ::lat], lgold[f"batch_simple_{name}"], f"simple_batch {name}")
+    np.random.seed(4244)                                        # rd_mirror=True: per-sample flip draws
+    for name, g in zip(("inp", "label", "fg"), L.get_batch(es, (320, 320), False, True)):
+        close(g[:, ::lat, ::lat], lgold[f"batch_get_{name}"], f"get_batch {name}")
+    with pytest.raises(ValueError):
+        L.video_batch(ev, (320, 160))
+    with pytest.raises(ValueError):
+        L.get_batch(es, (320, 320), True, False)
+
+
+def test_device_outputs_and_float32(vm, lgold, tmp_path):
+    import torch
+    L = vm.loader
+    ev, _ = batch_entries(lgold, tmp_path)
+    np.random.seed(7)
+    ref = L.video_batch(ev, (320, 320))
+    np.random.seed(7)
+    dev = L.video_batch(ev, (320, 320), device=True)
+    np.random.seed(7)
+    f32 = L.video_batch(ev, (320, 320), device=True, dtype=np.float32)
+    torch.cuda.synchronize()
+    for r, d, f in zip(ref, dev, f32):
+        assert d.is_cuda and d.dtype == torch.float64 and f.dtype == torch.float32
+        assert np.array_equal(d.cpu().numpy(), r)
+        assert np.array_equal(f.cpu().numpy(), r.astype(np.float32))
+    assert L.video_batch([], (320, 320))[0].shape == (0, 320, 320, 3)
+
+
+def test_same_rng_state_after_call_as_the_oracle(vm, lgold, tmp_path):
+    L = vm.loader
+    p = files_of(lgold, "v1", tmp_path)
+    fg = cv2.imread(p["fg"], cv2.IMREAD_UNCHANGED)
+    bg = cv2.imread(p["bg"])
+    np.random.seed(99)
+    L.simple_load_crop((p["fg"], p["tri"], p["bg"]), (320, 320))
+    after = np.random.uniform()
+    r = np.random.RandomState(99)
+    LO.simple_sample(fg, bg, (320, 320), r)
+    assert after == r.uniform()
+
+
+def test_psnr_and_helpers(vm, lgold, tmp_path):
+    L = vm.loader
+    assert abs(L.psnr(lgold["psnr_a"], lgold["psnr_b"]) - float(lgold["psnr_3"])) < 1e-9
+    assert abs(L.psnr(lgold["psnr_a"][:, :, 0], lgold["psnr_b"][:, :, 0]) - float(lgold["psnr_1"])) < 1e-9
+    np.random.seed(3)
+    n = L.add_noise(lgold["psnr_a"][:, :, 0], var=0.05)
+    assert n.shape == (40, 50, 1) and n.min() >= 0 and n.max() <= 1
+    lst = tmp_path / "list.txt"
+    lst.write_text("a.png t.png b.jpg\nc.png u.png d.jpg\n")
+    fl = L.get_file_list("/root", str(lst))
+    assert fl == [["/root/a.png", "/root/t.png", "/root/b.jpg"], ["/root/c.png", "/root/u.png", "/root/d.jpg"]]
+    assert not L.epoch_is_over(fl, 2) and L.get_batch_list(fl, 1) == [["/root/c.png", "/root/u.png", "/root/d.jpg"]]
+    assert L.epoch_is_over(fl, 2)
+    with pytest.raises(AttributeError):
+        L.simple_load_crop((files_of(lgold, "v0", tmp_path)["fg"], "x", "/nonexistent/bg.png"), (320, 320))

@@ -12,15 +12,24 @@ from . import pipeline as P
 FLO_MAGIC = 202021.25
 
 
-def read_fg_img(img_path):
-    """reads a foreground RGBA image -> (alpha float64 (H,W), bgr uint8 (H,W,3)) - reference
-    reader.py:10-18, including the uint16 -> uint8 conversion quirk."""
+def read_bgra(img_path):
+    """Decoded (H, W, 4) uint8 BGRA image after the uint16 -> uint8 conversion of reference
+    reader.py:12-15 (alpha = A / 255, foreground = B,G,R): the device layout of a foreground."""
     import cv2
     img = cv2.imread(img_path, cv2.IMREAD_UNCHANGED)
     if img.dtype == np.uint16:
         # ((img+1)/256 - 1).astype(uint8) with img+1 wrapping in uint16 and -1.0 wrapping to 255
         t = ((img.astype(np.uint32) + 1) & 0xFFFF) / 256. - 1.
         img = (np.trunc(t).astype(np.int64) & 0xFF).astype(np.uint8)
+    if img.ndim != 3 or img.shape[2] < 4:
+        raise IndexError("index 3 is out of bounds for axis 2 (the foreground must be RGBA)")
+    return img
+
+
+def read_fg_img(img_path):
+    """reads a foreground RGBA image -> (alpha float64 (H,W), bgr uint8 (H,W,3)) - reference
+    reader.py:10-18, including the uint16 -> uint8 conversion quirk."""
+    img = read_bgra(img_path)
     alpha = img[:, :, 3] / 255.
     bgr = img[:, :, :3]
     return alpha, bgr
