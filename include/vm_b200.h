@@ -253,6 +253,13 @@ int vm_loader_batch(const vm_loader_sample *samples, int n, int out_h, int out_w
  * (zeroed by the caller); dtype VM_F32 or VM_F64.                                                       */
 int vm_sq_err_sum(const void *a, const void *b, int dtype, int64_t n, double *out, void *stream);
 
+/* ---- data.trimap_from_matte -------------------------------------------------------
+ * reference: data.py:37-67, a pure-Python raster scan.  matte: (n, h, w) float64 in [0,1] (VM_F64, the
+ * reference's argument) or the uint8 alpha bytes (VM_U8: 255 = 1., 0 = 0.); out (n, h, w) uint8 in
+ * {0, 128, 255}.  Reproduces the scan-order dependence of the reference: an alpha==1 (alpha==0) pixel
+ * becomes 128 iff a fractional pixel within Chebyshev distance 3 (1) follows it in raster order.      */
+int vm_trimap_from_matte(const void *matte, int dtype, int n, int h, int w, uint8_t *out, void *stream);
+
 /* Measurement hooks of the default fused path (no reference counterpart; used by bench.py).
  * vm_lean_stage_ms: durations in ms of {spline, tile boxes, flow stage, resampling+composite}
  * of the first chunk of the last call made with "lean_timing" = 1 on the current device, after

@@ -161,3 +161,56 @@ def psnr(img, img_ref):
     a = img.reshape(img.shape[0], img.shape[1], -1).astype(np.float64)
     b = img_ref.reshape(img_ref.shape[0], img_ref.shape[1], -1).astype(np.float64)
     return 10. * np.log10(1. / (1e-6 + np.mean(np.sum(np.square(a - b), axis=2))))
+
+
+# --------------------------------------------------------------------------------------
+# data.trimap_from_matte                          (reference data.py:37-67)
+# --------------------------------------------------------------------------------------
+
+def trimap_from_matte_loop(matte):
+    """The reference's raster-order loop, restated literally (small images only): every pixel
+    first receives its own class (255 / 0 / 128); a fractional pixel then paints 128 over the
+    alpha==1 pixels within +-3 and the alpha==0 pixels within +-1 of it.  Because a pixel's own
+    class is written when the scan reaches it, paint applied *before* that moment is lost."""
+    assert matte.dtype == np.float64
+    h, w = matte.shape
+    out = np.zeros((h, w), dtype=np.uint8)
+    for i in range(h):
+        for j in range(w):
+            m = matte[i, j]
+            if m == 1.:
+                out[i, j] = 255
+            elif m == 0.:
+                out[i, j] = 0
+            else:
+                out[i, j] = 128
+                for k in range(max(0, i - 3), min(h, i + 4)):
+                    for l in range(max(0, j - 3), min(w, j + 4)):
+                        if matte[k, l] == 1.:
+                            out[k, l] = 128
+                        elif matte[k, l] == 0. and abs(k - i) <= 1 and abs(l - j) <= 1:
+                            out[k, l] = 128
+    return out
+
+
+def trimap_from_matte(matte):
+    """Closed form of the loop above: a pixel with alpha == 1 (== 0) becomes 128 iff a fractional
+    pixel lies within Chebyshev distance 3 (1) of it AND comes later in raster order."""
+    assert matte.dtype == np.float64
+    h, w = matte.shape
+    frac = (matte != 1.) & (matte != 0.)
+    out = np.where(matte == 1., 255, np.where(matte == 0., 0, 128)).astype(np.uint8)
+    pad = np.zeros((h + 6, w + 6), dtype=bool)
+    pad[3:h + 3, 3:w + 3] = frac
+    later = {1: np.zeros((h, w), dtype=bool), 3: np.zeros((h, w), dtype=bool)}
+    for dk in range(-3, 4):
+        for dl in range(-3, 4):
+            if dk < 0 or (dk == 0 and dl <= 0):
+                continue                                        # not later in raster order
+            hit = pad[3 + dk:3 + dk + h, 3 + dl:3 + dl + w]
+            later[3] |= hit
+            if abs(dk) <= 1 and abs(dl) <= 1:
+                later[1] |= hit
+    out[(matte == 1.) & later[3]] = 128
+    out[(matte == 0.) & later[1]] = 128
+    return out

@@ -142,6 +142,13 @@ def main():
         np.random.seed(4244)
         for name, a in zip(("inp", "label", "fg"), loader.get_batch(entries_s, (320, 320), False, True)):
             out[f"batch_get_{name}"] = np.ascontiguousarray(a[:, ::LAT * 2, ::LAT * 2])
+        # data.trimap_from_matte (reference data.py:37-67, pure-Python loop: small images only)
+        import data
+        for tag, (h, w), seed in (("t0", (37, 53), 1), ("t1", (24, 24), 2)):
+            import vm_oracle as O
+            a8 = np.clip(128 + 384 * O._smooth_noise(np.random.default_rng(seed), h, w, 6), 0, 255).astype(np.uint8)
+            out[f"{tag}_matte_u8"] = a8
+            out[f"{tag}_trimap"] = data.trimap_from_matte(a8 / 255.)
         # psnr
         rng = np.random.default_rng(9)
         a, b = rng.uniform(0, 1, (40, 50, 3)), rng.uniform(0, 1, (40, 50, 3))

@@ -159,3 +159,13 @@ def test_descriptor_layout_matches_header(vm):
     body = re.search(r"typedef struct \{([^}]*)\} vm_loader_sample;", hdr).group(1)
     names = re.findall(r"\*?(\w+)\s*[,;]", re.sub(r"/\*.*?\*/", "", body, flags=re.S))
     assert names == list(vm.loader.SAMPLE_DTYPE.names)
+
+
+def test_trimap_oracle_matches_reference(lgold):
+    for tag in ("t0", "t1"):
+        m = lgold[f"{tag}_matte_u8"] / 255.
+        assert np.array_equal(LO.trimap_from_matte_loop(m), lgold[f"{tag}_trimap"])
+        assert np.array_equal(LO.trimap_from_matte(m), lgold[f"{tag}_trimap"])
+    rng = np.random.default_rng(0)
+    m = rng.choice([0., 1., 0.5], size=(23, 31), p=[0.45, 0.45, 0.1])
+    assert np.array_equal(LO.trimap_from_matte(m), LO.trimap_from_matte_loop(m))

@@ -147,3 +147,23 @@ def test_psnr_and_helpers(vm, lgold, tmp_path):
     assert L.epoch_is_over(fl, 2)
     with pytest.raises(AttributeError):
         L.simple_load_crop((files_of(lgold, "v0", tmp_path)["fg"], "x", "/nonexistent/bg.png"), (320, 320))
+
+
+def test_trimap_from_matte_matches_reference_and_oracle(vm, lgold):
+    import torch
+    D = vm.data
+    for tag in ("t0", "t1"):
+        m8 = lgold[f"{tag}_matte_u8"]
+        got = D.trimap_from_matte(m8 / 255.)
+        assert got.dtype == np.uint8 and np.array_equal(got, lgold[f"{tag}_trimap"])
+        assert np.array_equal(D.trimap_from_matte(m8), lgold[f"{tag}_trimap"])
+    with pytest.raises(AssertionError):
+        D.trimap_from_matte(np.zeros((4, 4), np.float32))
+    # large stack against the closed-form oracle (odd sizes, tile borders)
+    a8 = np.stack([O.synth_frame(s, 203, 331)[..., 3] for s in range(3)])
+    got = D.trimap_from_matte(torch.from_numpy(a8).cuda()).cpu().numpy()
+    for k in range(3):
+        assert np.array_equal(got[k], LO.trimap_from_matte(a8[k] / 255.))
+    edge = np.zeros((9, 40))
+    edge[4, :] = 0.5; edge[:, 0] = 1.; edge[:, 39] = 1.; edge[0, :] = 1.; edge[8, 5:9] = 0.3
+    assert np.array_equal(D.trimap_from_matte(edge), LO.trimap_from_matte_loop(edge))

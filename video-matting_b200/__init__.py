@@ -8,7 +8,7 @@ The directory name carries a hyphen (``video-matting_b200``); load it with
 (``import flow, tps, augmentation, reader``).
 """
 from . import _native, pipeline          # noqa: F401
-from . import flow, reader, tps, augmentation, loader   # noqa: F401
+from . import flow, reader, tps, augmentation, loader, data   # noqa: F401
 
 __version__ = "0.1.0"
 
@@ -17,5 +17,5 @@ def install_dropin():
     """Register the drop-in modules under the reference's bare names."""
     import sys
     for name, mod in (("flow", flow), ("reader", reader), ("tps", tps), ("augmentation", augmentation),
-                      ("loader", loader)):
+                      ("loader", loader), ("data", data)):
         sys.modules[name] = mod

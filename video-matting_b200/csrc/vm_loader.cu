@@ -187,3 +187,62 @@ extern "C" int vm_sq_err_sum(const void *a, const void *b, int dtype, int64_t n,
     else { vm_set_error("vm_sq_err_sum: dtype must be VM_F32 or VM_F64"); return VM_ERR_ARG; }
     return vm_check_launch("vm_sq_err_sum");
 }
+
+// ---------------------------------------------------------------------------------------
+// data.trimap_from_matte (data.py:37-67).  The reference scans in raster order: every pixel first
+// receives its own class (255 / 0 / 128), and a fractional pixel then paints 128 over the alpha==1
+// pixels within +-3 and the alpha==0 pixels within +-1.  Paint that lands on a pixel before the scan
+// reaches it is overwritten, so: a 1-pixel (0-pixel) ends up 128 iff a fractional pixel within
+// Chebyshev distance 3 (1) comes LATER in raster order.  One thread per pixel; the 8 x 32 tile and
+// its halo (3 rows below, 3 columns either side) are classified once into shared memory.
+// ---------------------------------------------------------------------------------------
+#define TM_W 32
+#define TM_H 8
+#define TM_R 3
+
+template <typename T> __device__ __forceinline__ int vm_matte_class(T v);
+template <> __device__ __forceinline__ int vm_matte_class<double>(double v) { return v == 1.0 ? 1 : (v == 0.0 ? 0 : 2); }
+template <> __device__ __forceinline__ int vm_matte_class<uint8_t>(uint8_t v) { return v == 255 ? 1 : (v == 0 ? 0 : 2); }
+
+template <typename T>
+__global__ void __launch_bounds__(TM_W * TM_H)
+k_trimap(const T *__restrict__ matte, int h, int w, uint8_t *__restrict__ out) {
+    __shared__ uint8_t frac[TM_H + TM_R][TM_W + 2 * TM_R];      // 1 where the pixel is fractional (in frame)
+    const int x0 = blockIdx.x * TM_W, y0 = blockIdx.y * TM_H;
+    const int64_t plane = (int64_t)blockIdx.z * h * w;
+    for (int k = threadIdx.y * TM_W + threadIdx.x; k < (TM_H + TM_R) * (TM_W + 2 * TM_R); k += TM_W * TM_H) {
+        const int r = k / (TM_W + 2 * TM_R), c = k - r * (TM_W + 2 * TM_R);
+        const int y = y0 + r, x = x0 + c - TM_R;
+        int cls = 0;
+        if (y < h && x >= 0 && x < w) cls = vm_matte_class<T>(__ldg(matte + plane + (int64_t)y * w + x));
+        frac[r][c] = cls == 2;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int own = vm_matte_class<T>(__ldg(matte + plane + (int64_t)y * w + x));
+    uint8_t v = own == 2 ? 128 : (own == 1 ? 255 : 0);
+    if (own != 2) {
+        const int R = own == 1 ? 3 : 1;                         // crop = 3 for alpha == 1, dilate = 1 for alpha == 0
+        bool later = false;
+        for (int dk = 0; dk <= R; ++dk)
+            for (int dl = -R; dl <= R; ++dl) {
+                if (dk == 0 && dl <= 0) continue;               // same row: only pixels to the right come later
+                later |= frac[threadIdx.y + dk][threadIdx.x + TM_R + dl] != 0;
+            }
+        if (later) v = 128;
+    }
+    out[plane + (int64_t)y * w + x] = v;
+}
+
+extern "C" int vm_trimap_from_matte(const void *matte, int dtype, int n, int h, int w, uint8_t *out, void *stream) {
+    VM_REQUIRE(matte && out, "null pointer");
+    VM_REQUIRE(n >= 0 && n < 65536 && h >= 1 && w >= 1 && (h + TM_H - 1) / TM_H < 65536, "bad size");
+    if (n == 0) return VM_OK;
+    dim3 grid((w + TM_W - 1) / TM_W, (h + TM_H - 1) / TM_H, n), block(TM_W, TM_H);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == VM_F64) k_trimap<double><<<grid, block, 0, st>>>((const double *)matte, h, w, out);
+    else if (dtype == VM_U8) k_trimap<uint8_t><<<grid, block, 0, st>>>((const uint8_t *)matte, h, w, out);
+    else { vm_set_error("vm_trimap_from_matte: dtype must be VM_U8 or VM_F64"); return VM_ERR_ARG; }
+    return vm_check_launch("vm_trimap_from_matte");
+}

@@ -1,0 +1,14 @@
+"""Bare-name shim: put this directory on sys.path and `import data` resolves to the B200
+implementation (video_matting_b200.data) instead of the reference module."""
+import importlib.util as _u
+import os as _os
+import sys as _sys
+
+if "video_matting_b200" not in _sys.modules:
+    _pkg = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+    _spec = _u.spec_from_file_location("video_matting_b200", _os.path.join(_pkg, "__init__.py"),
+                                       submodule_search_locations=[_pkg])
+    _mod = _u.module_from_spec(_spec)
+    _sys.modules["video_matting_b200"] = _mod
+    _spec.loader.exec_module(_mod)
+_sys.modules[__name__] = _sys.modules["video_matting_b200"].data
