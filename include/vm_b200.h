@@ -260,6 +260,11 @@ int vm_sq_err_sum(const void *a, const void *b, int dtype, int64_t n, double *ou
  * becomes 128 iff a fractional pixel within Chebyshev distance 3 (1) follows it in raster order.      */
 int vm_trimap_from_matte(const void *matte, int dtype, int n, int h, int w, uint8_t *out, void *stream);
 
+/* ---- reader.read_fg_img, uint16 branch (clip ingest) ------------------------
+ * reference: reader.py:13-15, (((img + 1) / 256.) - 1).astype(uint8) with the uint16 wrap of img + 1 and
+ * the x86 wrap of -1.0 -> 255.  src: n uint16 elements as decoded (16-byte aligned), dst: n uint8.       */
+int vm_fg_from_u16(const uint16_t *src, int64_t n, uint8_t *dst, void *stream);
+
 /* Measurement hooks of the default fused path (no reference counterpart; used by bench.py).
  * vm_lean_stage_ms: durations in ms of {spline, tile boxes, flow stage, resampling+composite}
  * of the first chunk of the last call made with "lean_timing" = 1 on the current device, after

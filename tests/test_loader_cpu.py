@@ -169,3 +169,15 @@ def test_trimap_oracle_matches_reference(lgold):
     rng = np.random.default_rng(0)
     m = rng.choice([0., 1., 0.5], size=(23, 31), p=[0.45, 0.45, 0.1])
     assert np.array_equal(LO.trimap_from_matte(m), LO.trimap_from_matte_loop(m))
+
+
+def test_u16_quirk_closed_form_is_the_reference_expression():
+    # csrc/vm_loader.cu: vm_u16_quirk; reference reader.py:13-15 evaluated literally in numpy
+    v = np.arange(65536, dtype=np.uint32)
+    q = (v + 1) & 0xFFFF
+    closed = np.where(q == 0, 255, np.where(q < 256, 0, (q >> 8) - 1)).astype(np.uint8)
+    assert np.array_equal(closed, O.fg_from_uint16(v.astype(np.uint16)))
+    v16 = v.astype(np.uint16)
+    with np.errstate(all="ignore"):
+        literal = (((v16 + np.uint16(1)) / 256.) - 1)
+    assert np.array_equal(closed, (np.trunc(literal).astype(np.int64) & 0xFF).astype(np.uint8))

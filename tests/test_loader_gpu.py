@@ -167,3 +167,57 @@ def test_trimap_from_matte_matches_reference_and_oracle(vm, lgold):
     edge = np.zeros((9, 40))
     edge[4, :] = 0.5; edge[:, 0] = 1.; edge[:, 39] = 1.; edge[0, :] = 1.; edge[8, 5:9] = 0.3
     assert np.array_equal(D.trimap_from_matte(edge), LO.trimap_from_matte_loop(edge))
+
+
+def test_fg_from_u16_exhaustive(vm):
+    import torch
+    N = vm._native
+    v = np.arange(65536 + 5, dtype=np.uint32).astype(np.uint16)          # 65541 elements: vector body + tail
+    src = torch.from_numpy(v.view(np.int16)).cuda().view(torch.uint16)
+    dst = torch.empty(v.size, dtype=torch.uint8, device="cuda")
+    N.check(N.load().vm_fg_from_u16(N.ptr(src), v.size, N.ptr(dst), N.stream_ptr()))
+    assert np.array_equal(dst.cpu().numpy(), O.fg_from_uint16(v))
+
+
+@pytest.mark.parametrize("wide", [False, True])
+def test_load_clip_matches_per_file_readers(vm, tmp_path, wide, capsys):
+    R = vm.reader
+    h, w, n = 45, 70, 5
+    fgp, fbp, ffp, bgp = [], [], [], []
+    rng = np.random.default_rng(3)
+    for k in range(n):
+        fr = O.synth_frame(k, h, w)
+        img = (fr.astype(np.uint16) * 257 + rng.integers(0, 257, fr.shape).astype(np.uint16)) if wide else fr
+        if wide:
+            img.reshape(-1)[:8] = [0, 1, 254, 255, 256, 511, 65534, 65535]
+        fgp.append(str(tmp_path / f"fg{k}.png"))
+        assert cv2.imwrite(fgp[-1], img)
+        fb, ff = O.synth_flows(k, h, w)
+        for lst, name, f in ((fbp, "b", fb), (ffp, "f", ff)):
+            lst.append(str(tmp_path / f"{name}{k}.flo"))
+            O.write_flo(lst[-1], f)
+    for k, shape in enumerate(((h, w), (33, 91))):
+        bgp.append(str(tmp_path / f"bg{k}.png"))
+        assert cv2.imwrite(bgp[-1], O.synth_background(k, *shape))
+    clip = R.load_clip(fgp, fbp, ffp, bgp, chunk=2, threads=3)
+    assert clip["fg"].shape == (n, h, w, 4) and clip["fg"].is_cuda
+    for k in range(n):
+        alpha, bgr = R.read_fg_img(fgp[k])
+        got = clip["fg"][k].cpu().numpy()
+        assert np.array_equal(got[..., :3], bgr) and np.array_equal(got[..., 3] / 255., alpha)
+        assert np.array_equal(clip["backward"][k].cpu().numpy(), R.read_flow(fbp[k]))
+        assert np.array_equal(clip["forward"][k].cpu().numpy(), R.read_flow(ffp[k]))
+    assert np.array_equal(clip["bg"][0].cpu().numpy(), cv2.imread(bgp[0]))
+    assert np.array_equal(clip["bg"][1].cpu().numpy(), cv2.resize(cv2.imread(bgp[1]), (w, h), interpolation=cv2.INTER_LINEAR))
+    # reference conventions: short .flo -> ValueError; bad magic -> message, parsing continues
+    short = str(tmp_path / "short.flo")
+    open(short, "wb").write(open(fbp[0], "rb").read()[:-8])
+    with pytest.raises(ValueError):
+        R.load_clip(fgp[:1], [short])
+    bad = bytearray(open(fbp[0], "rb").read())
+    bad[0] ^= 0xFF
+    open(str(tmp_path / "bad.flo"), "wb").write(bytes(bad))
+    capsys.readouterr()
+    c2 = R.load_clip(fgp[:1], [str(tmp_path / "bad.flo")])
+    assert "ERROR: invalid key" in capsys.readouterr().out
+    assert np.array_equal(c2["backward"][0].cpu().numpy(), R.read_flow(fbp[0]))

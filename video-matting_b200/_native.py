@@ -47,6 +47,7 @@ SIGNATURES = {
     "vm_loader_batch": [_P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P],
     "vm_sq_err_sum": [_P, _P, _I, _L, _P, _P],
     "vm_trimap_from_matte": [_P, _I, _I, _I, _I, _P, _P],
+    "vm_fg_from_u16": [_P, _L, _P, _P],
     "vm_lean_stage_ms": [_P],
     "vm_lean_launch_count": [],
 }

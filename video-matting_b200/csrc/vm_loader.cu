@@ -246,3 +246,41 @@ extern "C" int vm_trimap_from_matte(const void *matte, int dtype, int n, int h, 
     else { vm_set_error("vm_trimap_from_matte: dtype must be VM_U8 or VM_F64"); return VM_ERR_ARG; }
     return vm_check_launch("vm_trimap_from_matte");
 }
+
+// ---------------------------------------------------------------------------------------
+// reader.read_fg_img, uint16 branch (reader.py:13-15): (((img + 1) / 256.) - 1).astype(uint8) where
+// img + 1 wraps in uint16 and the cast of -1.0 wraps to 255.  With v' = (v + 1) mod 2^16:
+// v' = 0 -> 255, 1..255 -> 0 (a value in (-1, 0) truncates to 0), otherwise (v' >> 8) - 1.
+// Eight elements per thread (16-byte loads, 8-byte stores); the tail is done element-wise.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t vm_u16_quirk(uint32_t v) {
+    const uint32_t q = (v + 1u) & 0xFFFFu;
+    return q == 0u ? 255u : (q < 256u ? 0u : (q >> 8) - 1u);
+}
+
+__global__ void __launch_bounds__(256) k_fg_from_u16(const uint16_t *__restrict__ src, int64_t n, uint8_t *__restrict__ dst) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i >= n) return;
+    if (i + 8 <= n) {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(src + i));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[2] = {0u, 0u};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            o[k >> 1] |= vm_u16_quirk(w[k] & 0xFFFFu) << (16 * (k & 1));
+            o[k >> 1] |= vm_u16_quirk(w[k] >> 16) << (16 * (k & 1) + 8);
+        }
+        __stcs(reinterpret_cast<uint2 *>(dst + i), make_uint2(o[0], o[1]));
+    } else {
+        for (int64_t k = i; k < n; ++k) dst[k] = (uint8_t)vm_u16_quirk(src[k]);
+    }
+}
+
+extern "C" int vm_fg_from_u16(const uint16_t *src, int64_t n, uint8_t *dst, void *stream) {
+    VM_REQUIRE(src && dst && n >= 0, "bad argument");
+    VM_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0, "unaligned buffer");
+    if (n == 0) return VM_OK;
+    const int64_t threads = (n + 7) / 8;
+    k_fg_from_u16<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, n, dst);
+    return vm_check_launch("vm_fg_from_u16");
+}

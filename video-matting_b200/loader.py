@@ -222,13 +222,13 @@ def _run(kind, entries, input_size, mirror=False, device=False, dtype=np.float64
         N.check(lib.vm_loader_batch(ctypes.c_void_p(table), n, out_h, out_w, mean, N.dtype_code(out["cmp"]),
                                     N.ptr(out["cmp"]), N.ptr(out["bg"]), N.ptr(out["label"]), N.ptr(out["warped"]),
                                     N.ptr(out["fg"]), N.stream_ptr()))
-        dev.record_stream(torch.cuda.current_stream())
-        if not device:
-            torch.cuda.current_stream().synchronize()                           # the pinned buffer is reused by torch
-        del host
+        del host, dev            # both were used on the current stream only: torch's allocators order their reuse
     if device:
         return out
-    return {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
+    host_out = {k: (torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v, non_blocking=True)
+                    if v is not None else None) for k, v in out.items()}
+    torch.cuda.current_stream().synchronize()
+    return {k: (v.numpy() if v is not None else None) for k, v in host_out.items()}
 
 
 def _square(input_size):
