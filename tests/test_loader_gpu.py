@@ -221,3 +221,26 @@ def test_load_clip_matches_per_file_readers(vm, tmp_path, wide, capsys):
     c2 = R.load_clip(fgp[:1], [str(tmp_path / "bad.flo")])
     assert "ERROR: invalid key" in capsys.readouterr().out
     assert np.array_equal(c2["backward"][0].cpu().numpy(), R.read_flow(fbp[0]))
+
+
+def test_device_batch_equals_file_batch(vm, lgold, tmp_path):
+    import torch
+    L = vm.loader
+    ev, es = batch_entries(lgold, tmp_path)
+    fg = [torch.from_numpy(cv2.imread(e[0], cv2.IMREAD_UNCHANGED)).cuda() for e in ev]
+    bg = [torch.from_numpy(cv2.imread(e[1])).cuda() for e in ev]
+    prev = [torch.from_numpy(cv2.imread(e[2], cv2.IMREAD_UNCHANGED)).cuda() for e in ev]
+    flo = [torch.from_numpy(O.parse_flo(open(e[3], "rb").read())[0].copy()).cuda() for e in ev]
+    np.random.seed(11)
+    ref = L.video_batch(ev, (320, 320))
+    np.random.seed(11)
+    got = L.device_batch(fg, bg, (320, 320), prev=prev, flow=flo)
+    for name, r in zip(("cmp", "bg", "label", "warped", "fg"), ref):
+        assert np.array_equal(got[name].cpu().numpy(), r), name
+    np.random.seed(12)
+    ref = L.get_batch(es, (320, 320), False, True)
+    np.random.seed(12)
+    got = L.device_batch(fg, bg, (320, 320), mirror=True)
+    assert got["warped"] is None
+    assert np.array_equal(torch.cat((got["cmp"], got["bg"]), 3).cpu().numpy(), ref[0])
+    assert np.array_equal(got["label"].cpu().numpy(), ref[1]) and np.array_equal(got["fg"].cpu().numpy(), ref[2])

@@ -416,8 +416,10 @@ static int vl_launch_coarse(const double *ctrl, const double *coef, int N, int n
 // plans whose axis tables are not monotone windows take everything from global memory.
 // ---------------------------------------------------------------------------------------
 #define VL_FW 64                                   // columns per CTA
-#define VL_FS 4                                    // row strips per CTA
-#define VL_FROWS_MAX 32                            // fine rows per CTA (VL_FS * rpt)
+#ifndef VL_FS
+#define VL_FS 4                                    // row strips per CTA (256 threads; -DVL_FS=2: 128-thread CTAs, 64 x 16 tiles)
+#endif
+#define VL_FROWS_MAX (VL_FS * 8)                   // fine rows per CTA (VL_FS * rpt)
 #define VL_TC (VL_FW / 2 + 4)                      // coarse columns staged per CTA (36)
 #define VL_TR (VL_FROWS_MAX / 2 + 4)               // coarse rows staged per CTA (20)
 #define VL_BOX_MAX 5632                            // source-box entries staged per CTA (8 B each)
@@ -935,15 +937,15 @@ k_lean_mega(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd, cons
 #define VL_PS 8                                    // strips per CTA
 #define VL_PR 4                                    // rows per thread and tile
 #define VL_PTH (VL_PS * VL_PR)                     // tile height (32)
-static_assert(VL_PTH <= VL_FROWS_MAX, "tile height");
+#define VL_PTR (VL_PTH / 2 + 4)                    // coarse rows staged per tile of the persistent kernel (20)
 
 // rmin/bh/cmin/bw: source box (bw = 0: taps from global memory); kr0/nkr/kc0/nkc: coarse window
 // (nkr = 0: axis tables are not monotone windows -> fully generic tile)
 struct __align__(16) VlTileRec { int rmin, bh, cmin, bw, kr0, nkr, kc0, nkc; };
 
 struct __align__(16) VlPSmem {
-    double2 T[VL_TR * VL_TC];
-    double2 Cs[VL_TR * VL_FW];
+    double2 T[VL_PTR * VL_TC];
+    double2 Cs[VL_PTR * VL_FW];
     unsigned char bgt[2][VL_PTH * VL_FW * 3];
     vm_axis_entry rows[2][VL_PTH];
     vm_axis_entry cols[2][VL_FW];
@@ -972,7 +974,7 @@ k_lean_recs(const double2 *__restrict__ T, int nx, int ny, const vm_axis_entry *
     const int kr0 = r0.i0, kr1 = max(r1.i1, r1.i0), kc0 = c0.i0, kc1 = max(c1.i1, c1.i0);
     const int nkr = kr1 - kr0 + 1, nkc = kc1 - kc0 + 1;
     VlTileRec rec = {0, 0, 0, 0, 0, 0, 0, 0};
-    bool ok = nkr >= 1 && nkc >= 1 && nkr <= VL_TR && nkc <= VL_TC && kr0 >= 0 && kr1 < nx && kc0 >= 0 && kc1 < ny;
+    bool ok = nkr >= 1 && nkc >= 1 && nkr <= VL_PTR && nkc <= VL_TC && kr0 >= 0 && kr1 < nx && kc0 >= 0 && kc1 < ny;
     if (ok) {                                      // every (i0, i1) of the tile inside the window
         for (int i = lane; i < th; i += 32) {
             const vm_axis_entry e = vm_ld_axis(rows + I0 + i);
@@ -1191,7 +1193,7 @@ int vm_lean_set_option(const char *key, int value) {
     if (!strcmp(key, "lean_persist") && value >= 0 && value <= 1) { g_vl_persist = value; return VM_OK; }
     if (!strcmp(key, "lean_sub") && value >= 0 && value <= 4096) { g_vl_sub = value; return VM_OK; }
     if (!strcmp(key, "lean_box_cap") && value >= 0 && value <= 16384) { g_vl_box_cap = value; return VM_OK; }
-    if (!strcmp(key, "lean_minb") && value >= 2 && value <= 4) { g_vl_minb = value; return VM_OK; }
+    if (!strcmp(key, "lean_minb") && (value == 2 || value == 3 || value == 4 || value == 6 || value == 8)) { g_vl_minb = value; return VM_OK; }
     if (!strcmp(key, "lean_fine_rows") && value >= 1 && value <= 256) { g_vl_fine_rows = value; return VM_OK; }
     return VM_ERR_ARG;
 }
@@ -1370,8 +1372,8 @@ int vm_lean_launch(int mode, const uint8_t *fg, const float *backward, const flo
                 if (mode != 0) VL_FINE_P(1); else VL_FINE_P(0);
 #undef VL_FINE_P
             }
-            else if (mode != 0) { if (g_vl_minb == 4) VL_FINE(1, 4); else if (g_vl_minb == 3) VL_FINE(1, 3); else VL_FINE(1, 2); }
-            else           { if (g_vl_minb == 4) VL_FINE(0, 4); else if (g_vl_minb == 3) VL_FINE(0, 3); else VL_FINE(0, 2); }
+            else if (mode != 0) { if (g_vl_minb == 8) VL_FINE(1, 8); else if (g_vl_minb == 6) VL_FINE(1, 6); else if (g_vl_minb == 4) VL_FINE(1, 4); else if (g_vl_minb == 3) VL_FINE(1, 3); else VL_FINE(1, 2); }
+            else           { if (g_vl_minb == 8) VL_FINE(0, 8); else if (g_vl_minb == 6) VL_FINE(0, 6); else if (g_vl_minb == 4) VL_FINE(0, 4); else if (g_vl_minb == 3) VL_FINE(0, 3); else VL_FINE(0, 2); }
 #undef VL_FINE
             g_vl_launches += 1;
             rc = vm_check_launch(what);

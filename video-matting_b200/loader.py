@@ -231,6 +231,54 @@ def _run(kind, entries, input_size, mirror=False, device=False, dtype=np.float64
     return {k: (v.numpy() if v is not None else None) for k, v in host_out.items()}
 
 
+def device_batch(fg, bg, input_size, prev=None, flow=None, mirror=False, dtype=np.float64):
+    """Training batch from frames that are already on the device (no files, no PCIe): the same
+    planning (reference np.random order, loader.py:47-69 / 295-315) and the same kernel as
+    ``video_batch`` / ``simple_batch``.
+
+    fg: list of (H,W,4) uint8 BGRA CUDA tensors (or one (n,H,W,4) tensor); bg: list of (h,w,3) uint8 CUDA
+    tensors; prev + flow: previous BGRA frames and (H,W,2) float32 flows for the video variant.
+    Returns a dict of CUDA tensors {cmp, bg, label, fg, warped}; nothing is synchronised."""
+    N.require_cuda()
+    lib = N.load()
+    out_w, out_h = int(input_size[0]), int(input_size[1])
+    n = len(fg)
+    video = prev is not None
+    if video and (flow is None or len(prev) != n or len(flow) != n):
+        raise ValueError("prev and flow must hold one entry per sample")
+    if len(bg) != n:
+        raise ValueError("one background per sample is required")
+    keep = []                                                   # contiguous views must outlive the launch
+    records = np.zeros(n, dtype=SAMPLE_DTYPE)
+    for k, r in enumerate(records):
+        f, b = fg[k].contiguous(), bg[k].contiguous()
+        if f.dtype != torch.uint8 or f.dim() != 3 or f.shape[2] != 4 or b.dtype != torch.uint8 or b.shape[2] != 3:
+            raise TypeError("fg must be (H,W,4) uint8 BGRA and bg (h,w,3) uint8")
+        keep += [f, b]
+        r["fg"], r["bg"] = f.data_ptr(), b.data_ptr()
+        r["fh"], r["fw"], r["bh"], r["bw"] = f.shape[0], f.shape[1], b.shape[0], b.shape[1]
+        if video:
+            p, fl = prev[k].contiguous(), flow[k].contiguous()
+            if p.shape != f.shape or fl.shape != (f.shape[0], f.shape[1], 2) or fl.dtype != torch.float32:
+                raise ValueError("foreground, previous frame and flow must have the same size")
+            keep += [p, fl]
+            r["prev"], r["flow"] = p.data_ptr() + 3, fl.data_ptr()
+            r["ph"], r["pw"], r["prev_stride"] = p.shape[0], p.shape[1], 4
+        r["fgv"], r["bgv"] = _plan_sample(f.shape[0], f.shape[1], b.shape[0], b.shape[1], input_size)
+        if mirror:
+            r["flip"] = 1 if np.random.uniform(0., 1.) > 0.5 else 0
+    tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+    mk = lambda c: torch.empty((n, out_h, out_w, c), dtype=tdt, device="cuda")
+    out = {"cmp": mk(3), "bg": mk(3), "label": mk(1), "fg": mk(3), "warped": mk(3) if video else None}
+    if n:
+        table = torch.from_numpy(records.view(np.uint8).reshape(-1).copy()).pin_memory().cuda(non_blocking=True)
+        mean = (ctypes.c_double * 3)(*VGG_MEAN)
+        N.check(lib.vm_loader_batch(N.ptr(table), n, out_h, out_w, mean, N.dtype_code(out["cmp"]),
+                                    N.ptr(out["cmp"]), N.ptr(out["bg"]), N.ptr(out["label"]), N.ptr(out["warped"]),
+                                    N.ptr(out["fg"]), N.stream_ptr()))
+    return out
+
+
 def _square(input_size):
     # the reference's batch arrays are (B, input_size[0], input_size[1], C) while cv2.resize makes
     # (input_size[1], input_size[0]) samples: a non-square size fails in the assignment (loader.py:344)
