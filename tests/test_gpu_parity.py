@@ -421,13 +421,13 @@ def test_lean_partition_independent(vm):
     base3, _ = P.tps_composite(args[0], args[3], ctrl, coef)
     assert int(st0[4]) < 4, "most tiles of a mild grid must take the shared-memory box path"
     defaults = {"lean_chunk": 64, "lean_rb": 0, "lean_minb": 4, "lean_box_cap": 0, "lean_fine_rows": 8, "lean_persist": 0,
-                "lean_sub": 0, "lean_mega": 0, "lean_overlap": 0, "lean_b1_warps": 16, "lean_b1_dyr": 1, "flow_stage_layout": 0}
+                "lean_sub": 0, "lean_mega": 0, "lean_overlap": 0, "lean_b1_warps": 16, "lean_b1_dyr": 1, "flow_stage_layout": 0, "lean_floors": 1}
     configs = [{"lean_chunk": 1}, {"lean_chunk": 2}, {"lean_chunk": 3}, {"lean_rb": 4}, {"lean_rb": 16}, {"lean_rb": 32},
                {"lean_sub": 2}, {"lean_minb": 2}, {"lean_minb": 3}, {"lean_fine_rows": 3}, {"lean_fine_rows": 5},
                {"lean_box_cap": 64}, {"lean_persist": 1}, {"lean_persist": 1, "lean_box_cap": 64}, {"lean_persist": 1, "lean_chunk": 2},
                {"lean_mega": 1}, {"lean_mega": 1, "lean_chunk": 2}, {"lean_mega": 1, "lean_box_cap": 64},
                {"lean_overlap": 1, "lean_chunk": 2, "lean_b1_warps": 6}, {"lean_b1_dyr": 0, "lean_b1_warps": 24},
-               {"flow_stage_layout": 1}]
+               {"flow_stage_layout": 1}, {"lean_floors": 0}, {"lean_floors": 0, "lean_box_cap": 64}]
     try:
         for cfg in configs:
             for key, v in cfg.items():
@@ -438,6 +438,8 @@ def test_lean_partition_independent(vm):
             assert torch.equal(out, base) and torch.equal(out3, base3), f"{cfg} changes the result"
             if cfg.get("lean_box_cap") == 64:
                 assert int(st[4]) > 0, "box capacity 64 must push tiles onto the gather path"
+            if cfg == {"lean_floors": 0}:
+                assert int(st[4]) == int(st0[4]), "the packed floors must select the same tile boxes as T itself"
             for key in cfg:
                 Nt.set_option(key, defaults[key])
     finally:

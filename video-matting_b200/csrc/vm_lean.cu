@@ -38,6 +38,7 @@ int g_vl_mega = 0;           // 1 (C4 only): flow stage + resampling in one depe
 int g_vl_persist = 0;        // 1: persistent double-buffered resampling kernel (k_lean_fine_p); 0: one CTA per tile (k_lean_fine)
 int g_vl_sub = 0;            // frames per flow-stage / resampling sub-round inside a round (0: the whole round)
 int g_vl_box_cap = 0;        // source-box entries per B2 tile (0: as many as the occupancy target allows)
+int g_vl_floors = 1;         // 1: the spline stage also writes packed int16 floors of T for the tile-box stage
 int g_vl_minb = 4;           // B2 occupancy target (CTAs of 256 threads per SM: 2, 3 or 4)
 
 // ---------------------------------------------------------------------------------------
@@ -156,6 +157,16 @@ __device__ __noinline__ double vl_u_any(double r2, uint32_t tab_adj) {
     return (r2 == r2) ? 0.0 : r2;
 }
 
+// floor of both coordinates of a coarse point as two int16 (what the tile-box stage needs: a quarter of the
+// bytes of T); 0x8000 in both halves marks a non-finite / absurd value (the tile then takes the gather path)
+#define VL_FLOOR_BAD ((int)0x80008000)
+__device__ __forceinline__ int vl_pack_floor(double v0, double v1) {
+    if (!(fabs(v0) < 1.0e9) || !(fabs(v1) < 1.0e9)) return VL_FLOOR_BAD;
+    // clamped to [-32767, 32766]: 0x7FFF stays free for the box stage's "no point" filler, 0x8000 for VL_FLOOR_BAD
+    const int f0 = max(-32767, min(32766, __double2int_rd(v0))), f1 = max(-32767, min(32766, __double2int_rd(v1)));
+    return (f0 & 0xFFFF) | (f1 << 16);
+}
+
 // N > 0: number of control points known at compile time; 0: run-time count.
 // DYR: (y - Py)^2 of every control point held in registers (16 warps per SM at 128 registers);
 // otherwise it is recomputed per row group and the kernel runs 24 warps per SM.
@@ -163,7 +174,7 @@ template <int N, bool DYR>
 __global__ void __launch_bounds__(DYR ? VL_B1_THREADS : VL_B1_THREADS_HI, 1)
 k_lean_coarse(const double *__restrict__ ctrl, const double *__restrict__ coef, int n_rt, int n_frames, int nx, int ny,
               double step_x, double step_y, int rb, int nbands, int ncb, double2 *__restrict__ T,
-              unsigned int *__restrict__ next_unit) {
+              int *__restrict__ F, unsigned int *__restrict__ next_unit) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     VlCoarseSmem &S = *reinterpret_cast<VlCoarseSmem *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -297,6 +308,7 @@ k_lean_coarse(const double *__restrict__ ctrl, const double *__restrict__ coef, 
                         const double v0 = ((Ws.aff[0] + Ws.aff[1] * x) + Ws.aff[2] * y) + s0[r];
                         const double v1 = ((Ws.aff[3] + Ws.aff[4] * x) + Ws.aff[5] * y) + s1[r];
                         T[((int64_t)frame * nx + k) * ny + l] = make_double2(v0, v1);
+                        if (F) F[((int64_t)frame * nx + k) * ny + l] = vl_pack_floor(v0, v1);
                     }
                 }
             }
@@ -317,6 +329,7 @@ k_lean_coarse(const double *__restrict__ ctrl, const double *__restrict__ coef, 
                     const double v0 = ((Ws.aff[0] + Ws.aff[1] * x) + Ws.aff[2] * y) + s0;
                     const double v1 = ((Ws.aff[3] + Ws.aff[4] * x) + Ws.aff[5] * y) + s1;
                     T[((int64_t)frame * nx + k) * ny + l] = make_double2(v0, v1);
+                    if (F) F[((int64_t)frame * nx + k) * ny + l] = vl_pack_floor(v0, v1);
                 }
             }
         }
@@ -362,7 +375,7 @@ static int vl_sm_count() {
 }
 
 static int vl_launch_coarse(const double *ctrl, const double *coef, int N, int n, int nx, int ny, double step_x,
-                            double step_y, double2 *T, unsigned int *counter, cudaStream_t st) {
+                            double step_y, double2 *T, int *F, unsigned int *counter, cudaStream_t st) {
     if (cudaMemsetAsync(counter, 0, sizeof(unsigned int), st) != cudaSuccess) {
         vm_set_error("vm_lean: cudaMemsetAsync failed");
         return VM_ERR_CUDA;
@@ -382,7 +395,7 @@ static int vl_launch_coarse(const double *ctrl, const double *coef, int N, int n
             if (e != cudaSuccess) { vm_set_error("vm_lean: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VM_ERR_CUDA; } \
             attr_set[dev & 63] = true;                                                                            \
         }                                                                                                         \
-        k_lean_coarse<NN, DY><<<ctas, warps_cta * 32, vl_coarse_smem_bytes(warps_cta), st>>>(ctrl, coef, N, n, nx, ny, step_x, step_y, rb, nbands, ncb, T, counter); \
+        k_lean_coarse<NN, DY><<<ctas, warps_cta * 32, vl_coarse_smem_bytes(warps_cta), st>>>(ctrl, coef, N, n, nx, ny, step_x, step_y, rb, nbands, ncb, T, F, counter); \
     } while (0)
     if (g_vl_b1_dyr) {
         switch (N) {
@@ -666,7 +679,7 @@ __device__ __forceinline__ void vl_bulk_g2s(uint32_t dst, const void *src, uint3
 // One warp per tile; runs right behind B1 on the same stream.
 template <int SRC>
 __global__ void __launch_bounds__(128)
-k_lean_boxes(const double2 *__restrict__ T, int nx, int ny, const vm_axis_entry *__restrict__ rows,
+k_lean_boxes(const double2 *__restrict__ T, const int *__restrict__ F, int nx, int ny, const vm_axis_entry *__restrict__ rows,
              const vm_axis_entry *__restrict__ cols, int h, int w, int rpt, int tiles_x, int tiles_y, int n_tiles,
              int box_cap, VlTileBox *__restrict__ boxes) {
     constexpr int EPV = 16 / (int)sizeof(typename VlSrc<SRC>::elem);
@@ -684,17 +697,41 @@ k_lean_boxes(const double2 *__restrict__ T, int nx, int ny, const vm_axis_entry 
     const int nkr = kr1 - kr0 + 1, nkc = kc1 - kc0 + 1;
     VlTileBox rec = {0, 0, 0, 0};
     if (nkr >= 1 && nkc >= 1 && nkr <= 4096 && nkc <= 4096 && kr0 >= 0 && kr1 < nx && kc0 >= 0 && kc1 < ny) {
-        const double2 *Tf = T + (int64_t)frame * nx * ny + (int64_t)kr0 * ny + kc0;
+        const int64_t woff = (int64_t)frame * nx * ny + (int64_t)kr0 * ny + kc0;
+        const double2 *Tf = T + woff;
         int rlo = INT_MAX, rhi = INT_MIN, clo = INT_MAX, chi = INT_MIN, bad = 0;
-        for (int r = 0; r < nkr; ++r)
-            for (int c = lane; c < nkc; c += 32) {
-                const double2 v = __ldg(Tf + (int64_t)r * ny + c);
-                if (!(fabs(v.x) < 1.0e9) || !(fabs(v.y) < 1.0e9)) bad = 1;
-                else {
-                    const int f0 = __double2int_rd(v.x), f1 = __double2int_rd(v.y);
-                    rlo = min(rlo, f0); rhi = max(rhi, f0); clo = min(clo, f1); chi = max(chi, f1);
+        if (F && nkr <= VL_TR && nkc <= 64) {                            // packed floors written by the spline stage:
+            const int *Ff = F + woff;                                    // every load of the window is issued before the
+            int v[VL_TR][2];                                             // first one is used (the stage is latency bound)
+#pragma unroll
+            for (int r = 0; r < VL_TR; ++r)
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const int c = lane + 32 * g;
+                    v[r][g] = (r < nkr && c < nkc) ? __ldg(Ff + (int64_t)r * ny + c) : 0x7FFF7FFF;     // 0x7FFF7FFF: no point
                 }
-            }
+#pragma unroll
+            for (int r = 0; r < VL_TR; ++r)
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const int x = v[r][g];
+                    if (x == VL_FLOOR_BAD) bad = 1;
+                    else if (x != 0x7FFF7FFF) {
+                        const int f0 = (int)(short)(x & 0xFFFF), f1 = x >> 16;
+                        rlo = min(rlo, f0); rhi = max(rhi, f0); clo = min(clo, f1); chi = max(chi, f1);
+                    }
+                }
+        } else {
+            for (int r = 0; r < nkr; ++r)
+                for (int c = lane; c < nkc; c += 32) {
+                    const double2 v = __ldg(Tf + (int64_t)r * ny + c);
+                    if (!(fabs(v.x) < 1.0e9) || !(fabs(v.y) < 1.0e9)) bad = 1;
+                    else {
+                        const int f0 = __double2int_rd(v.x), f1 = __double2int_rd(v.y);
+                        rlo = min(rlo, f0); rhi = max(rhi, f0); clo = min(clo, f1); chi = max(chi, f1);
+                    }
+                }
+        }
         rlo = __reduce_min_sync(0xffffffffu, rlo); rhi = __reduce_max_sync(0xffffffffu, rhi);
         clo = __reduce_min_sync(0xffffffffu, clo); chi = __reduce_max_sync(0xffffffffu, chi);
         bad = __reduce_max_sync(0xffffffffu, bad);
@@ -988,17 +1025,42 @@ k_lean_recs(const double2 *__restrict__ T, int nx, int ny, const vm_axis_entry *
     ok = __all_sync(0xffffffffu, ok);
     if (ok) {
         rec.kr0 = kr0; rec.nkr = nkr; rec.kc0 = kc0; rec.nkc = nkc;
-        const double2 *Tf = T + (int64_t)frame * nx * ny + (int64_t)kr0 * ny + kc0;
+        const int64_t woff = (int64_t)frame * nx * ny + (int64_t)kr0 * ny + kc0;
+        const double2 *Tf = T + woff;
+        const int *F = nullptr;                                          // the record stage reads T itself
         int rlo = INT_MAX, rhi = INT_MIN, clo = INT_MAX, chi = INT_MIN, bad = 0;
-        for (int r = 0; r < nkr; ++r)
-            for (int c = lane; c < nkc; c += 32) {
-                const double2 v = __ldg(Tf + (int64_t)r * ny + c);
-                if (!(fabs(v.x) < 1.0e9) || !(fabs(v.y) < 1.0e9)) bad = 1;
-                else {
-                    const int f0 = __double2int_rd(v.x), f1 = __double2int_rd(v.y);
-                    rlo = min(rlo, f0); rhi = max(rhi, f0); clo = min(clo, f1); chi = max(chi, f1);
+        if (F && nkr <= VL_TR && nkc <= 64) {                            // packed floors written by the spline stage:
+            const int *Ff = F + woff;                                    // every load of the window is issued before the
+            int v[VL_TR][2];                                             // first one is used (the stage is latency bound)
+#pragma unroll
+            for (int r = 0; r < VL_TR; ++r)
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const int c = lane + 32 * g;
+                    v[r][g] = (r < nkr && c < nkc) ? __ldg(Ff + (int64_t)r * ny + c) : 0x7FFF7FFF;     // 0x7FFF7FFF: no point
                 }
-            }
+#pragma unroll
+            for (int r = 0; r < VL_TR; ++r)
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const int x = v[r][g];
+                    if (x == VL_FLOOR_BAD) bad = 1;
+                    else if (x != 0x7FFF7FFF) {
+                        const int f0 = (int)(short)(x & 0xFFFF), f1 = x >> 16;
+                        rlo = min(rlo, f0); rhi = max(rhi, f0); clo = min(clo, f1); chi = max(chi, f1);
+                    }
+                }
+        } else {
+            for (int r = 0; r < nkr; ++r)
+                for (int c = lane; c < nkc; c += 32) {
+                    const double2 v = __ldg(Tf + (int64_t)r * ny + c);
+                    if (!(fabs(v.x) < 1.0e9) || !(fabs(v.y) < 1.0e9)) bad = 1;
+                    else {
+                        const int f0 = __double2int_rd(v.x), f1 = __double2int_rd(v.y);
+                        rlo = min(rlo, f0); rhi = max(rhi, f0); clo = min(clo, f1); chi = max(chi, f1);
+                    }
+                }
+        }
         rlo = __reduce_min_sync(0xffffffffu, rlo); rhi = __reduce_max_sync(0xffffffffu, rhi);
         clo = __reduce_min_sync(0xffffffffu, clo); chi = __reduce_max_sync(0xffffffffu, chi);
         bad = __reduce_max_sync(0xffffffffu, bad);
@@ -1195,6 +1257,7 @@ int vm_lean_set_option(const char *key, int value) {
     if (!strcmp(key, "lean_box_cap") && value >= 0 && value <= 16384) { g_vl_box_cap = value; return VM_OK; }
     if (!strcmp(key, "lean_minb") && (value == 2 || value == 3 || value == 4 || value == 6 || value == 8)) { g_vl_minb = value; return VM_OK; }
     if (!strcmp(key, "lean_fine_rows") && value >= 1 && value <= 256) { g_vl_fine_rows = value; return VM_OK; }
+    if (!strcmp(key, "lean_floors") && (value == 0 || value == 1)) { g_vl_floors = value; return VM_OK; }
     return VM_ERR_ARG;
 }
 
@@ -1262,11 +1325,15 @@ int vm_lean_launch(int mode, const uint8_t *fg, const float *backward, const flo
         if (overlap && c >= 2) cudaStreamWaitEvent(side, g_vl_ev_free[dev][par], 0);     // set `par` consumed by chunk c-2
         const bool tev = timing && c == 0;
         if (tev) cudaEventRecord(g_vl_tev[dev][0], st);
-        rc = vl_launch_coarse(ctrl + (int64_t)f0 * N * 2, coef + (int64_t)f0 * (N + 3) * 2, N, m, nx, ny, step_x, step_y, T,
+        // packed floors of T for the tile-box stage: they live at the start of the flow stage's output buffer,
+        // which nobody touches until the box stage is done (not with the spline stage on the side stream,
+        // where the previous round's flow stage may still be writing it)
+        const bool persist = g_vl_persist != 0;
+        int *F = (!overlap && !persist && g_vl_floors && h <= 32766 && w <= 32766) ? reinterpret_cast<int *>(packed) : nullptr;
+        rc = vl_launch_coarse(ctrl + (int64_t)f0 * N * 2, coef + (int64_t)f0 * (N + 3) * 2, N, m, nx, ny, step_x, step_y, T, F,
                               counters + par * 32, side);
         if (rc != VM_OK) return rc;
         if (tev) cudaEventRecord(g_vl_tev[dev][1], st);
-        const bool persist = g_vl_persist != 0;
         const int ptx = (w + VL_FW - 1) / VL_FW, pty = (h + VL_PTH - 1) / VL_PTH;      // tiling of the persistent kernel
         // persistent kernel: 2 CTAs per SM share 227 KB; two source-box buffers per CTA
         int pbox_cap = (int)((((227 * 1024) / 2 - 1024 - (int64_t)sizeof(VlPSmem)) / 16) & ~63);
@@ -1280,8 +1347,8 @@ int vm_lean_launch(int mode, const uint8_t *fg, const float *backward, const flo
             if (rc != VM_OK) return rc;
         } else {
             const int n_tiles = (int)(grid.x * grid.y * m);
-            if (mode != 0) k_lean_boxes<1><<<(n_tiles + 3) / 4, 128, 0, side>>>(T, nx, ny, rows, cols, h, w, rpt, grid.x, grid.y, n_tiles, box_cap, boxes);
-            else           k_lean_boxes<0><<<(n_tiles + 3) / 4, 128, 0, side>>>(T, nx, ny, rows, cols, h, w, rpt, grid.x, grid.y, n_tiles, box_cap, boxes);
+            if (mode != 0) k_lean_boxes<1><<<(n_tiles + 3) / 4, 128, 0, side>>>(T, F, nx, ny, rows, cols, h, w, rpt, grid.x, grid.y, n_tiles, box_cap, boxes);
+            else           k_lean_boxes<0><<<(n_tiles + 3) / 4, 128, 0, side>>>(T, F, nx, ny, rows, cols, h, w, rpt, grid.x, grid.y, n_tiles, box_cap, boxes);
             rc = vm_check_launch("vm_lean box stage");
             if (rc != VM_OK) return rc;
         }
@@ -1504,7 +1571,7 @@ extern "C" int vm_tps_coarse_packed(const double *ctrl, const double *coef, int 
     int dev = 0;
     int rc = vl_init(&dev);
     if (rc != VM_OK) return rc;
-    return vl_launch_coarse(ctrl, coef, N, n, nx, ny, step_x, step_y, reinterpret_cast<double2 *>(T), counter, (cudaStream_t)stream);
+    return vl_launch_coarse(ctrl, coef, N, n, nx, ny, step_x, step_y, reinterpret_cast<double2 *>(T), nullptr, counter, (cudaStream_t)stream);
 }
 
 extern "C" int vm_aug_tps(const uint8_t *fg_bgra, const void *T, int nx, int ny, const vm_axis_entry *rows,
