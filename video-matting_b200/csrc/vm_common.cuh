@@ -298,6 +298,85 @@ __device__ __forceinline__ VmFlowPx vm_flow_px(const uint32_t *__restrict__ fg32
     return o;
 }
 
+// G horizontally adjacent pixels at once, in two phases: every tap load and every forward-flow load
+// of the group is issued (from clamped, always valid addresses) before the first value is used, so the
+// 20 gathers of a thread are in flight together instead of as eight dependent round trips.  Pixels that
+// leave the fast path (frame border, out-of-range or NaN coordinates) are redone by the same code as
+// vm_flow_px afterwards; results are identical to four vm_flow_px calls.
+template <bool MASK, int G>
+__device__ __forceinline__ void vm_flow_pxn(const uint32_t *__restrict__ fg32, const float2 *__restrict__ fwd,
+                                            int H, int W, int i, int j, float fi, float fj, const float2 *__restrict__ fb,
+                                            VmFlowPx *__restrict__ o, int &flags) {
+    uint32_t s[G][4];
+    float2 fv[G];
+    // phase 1: addresses and loads only (the geometry is recomputed in phase 2: a few ALU instructions
+    // are cheaper than carrying it in registers across twenty outstanding loads)
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        const float mx = __fadd_rn(fj + (float)k, fb[k].x), my = __fadd_rn(fi, fb[k].y);
+        const bool inr = (fabsf(mx) < 60000.f) & (fabsf(my) < 60000.f);
+        const int ix = vm_fix5_fast(mx) >> 5, iy = vm_fix5_fast(my) >> 5;
+        const bool inner = inr && (unsigned)ix < (unsigned)(W - 1) && (unsigned)iy < (unsigned)(H - 1);
+        const uint32_t *p = fg32 + (inner ? (int)((unsigned)iy * (unsigned)W + (unsigned)ix) : 0);
+        const int dx = inner ? 1 : 0, dy = inner ? W : 0;
+        s[k][0] = __ldg(p); s[k][1] = __ldg(p + dx); s[k][2] = __ldg(p + dy); s[k][3] = __ldg(p + dy + dx);
+        if (MASK) {
+            const int j0 = __float2int_rz(mx), i0 = __float2int_rz(my);
+            const bool fwd_ok = inr && (unsigned)j0 < (unsigned)W && (unsigned)i0 < (unsigned)H;
+            fv[k] = __ldg(fwd + (fwd_ok ? i0 * W + j0 : 0));
+        }
+    }
+    // phase 2: the arithmetic of vm_flow_px on the loaded values
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        const float fjk = fj + (float)k;
+        const float mx = __fadd_rn(fjk, fb[k].x), my = __fadd_rn(fi, fb[k].y);
+        if ((fabsf(mx) < 60000.f) & (fabsf(my) < 60000.f)) {
+            const int SX = vm_fix5_fast(mx), SY = vm_fix5_fast(my);
+            const int ix = SX >> 5, iy = SY >> 5, fx = SX & 31, fy = SY & 31;
+            uint32_t s00 = s[k][0], s01 = s[k][1], s10 = s[k][2], s11 = s[k][3];
+            if (!((unsigned)ix < (unsigned)(W - 1) && (unsigned)iy < (unsigned)(H - 1))) {     // frame border: taps outside read 0
+                const int base = (int)((unsigned)iy * (unsigned)W + (unsigned)ix);
+                const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
+                const bool y0 = (unsigned)iy < (unsigned)H, y1 = (unsigned)(iy + 1) < (unsigned)H;
+                s00 = (y0 && x0) ? __ldg(fg32 + base) : 0u;
+                s01 = (y0 && x1) ? __ldg(fg32 + base + 1) : 0u;
+                s10 = (y1 && x0) ? __ldg(fg32 + base + W) : 0u;
+                s11 = (y1 && x1) ? __ldg(fg32 + base + W + 1) : 0u;
+            }
+            const uint32_t gx = 32 - fx, gy = 32 - fy;
+            const uint32_t w00 = gx * gy, w01 = fx * gy, w10 = gx * fy, w11 = fx * fy;
+            const uint32_t b = ((s00 & 255u) * w00 + (s01 & 255u) * w01 + (s10 & 255u) * w10 + (s11 & 255u) * w11 + 512u) >> 10;
+            const uint32_t g = (__byte_perm(s00, 0, 0x4441) * w00 + __byte_perm(s01, 0, 0x4441) * w01 +
+                                __byte_perm(s10, 0, 0x4441) * w10 + __byte_perm(s11, 0, 0x4441) * w11 + 512u) >> 10;
+            const uint32_t r = (__byte_perm(s00, 0, 0x4442) * w00 + __byte_perm(s01, 0, 0x4442) * w01 +
+                                __byte_perm(s10, 0, 0x4442) * w10 + __byte_perm(s11, 0, 0x4442) * w11 + 512u) >> 10;
+            o[k].ta = (s00 >> 24) * w00 + (s01 >> 24) * w01 + (s10 >> 24) * w10 + (s11 >> 24) * w11;
+            o[k].bgr = b | (g << 8) | (r << 16);
+            o[k].masked = 0;
+            if (MASK) {
+                const int j0 = __float2int_rz(mx), i0 = __float2int_rz(my);
+                if ((unsigned)j0 < (unsigned)W && (unsigned)i0 < (unsigned)H) {
+                    const float c = __fadd_rn(fv[k].x, (float)j0), d = __fadd_rn(fv[k].y, (float)i0);
+                    if ((fabsf(c) < 3.0e38f) & (fabsf(d) < 3.0e38f)) {
+                        const float dj = __fadd_rn(fminf(truncf(c), (float)(W - 1)), -fjk);
+                        const float di = __fadd_rn(fminf(truncf(d), (float)(H - 1)), -fi);
+                        o[k].masked = __fmaf_rn(dj, dj, __fmul_rn(di, di)) > 225.f;
+                    } else {
+                        flags |= 2; o[k].masked = 1;
+                    }
+                } else {
+                    o[k].masked = vm_consistency(fwd, H, W, i, j + k, fb[k], flags);
+                }
+            }
+        } else {
+            const VmWarped wv = vm_flow_warp_bgra(reinterpret_cast<const uint8_t *>(fg32), H, W, i, j + k, fb[k]);
+            o[k].bgr = wv.bgr; o[k].ta = wv.ta;
+            o[k].masked = MASK ? vm_consistency(fwd, H, W, i, j + k, fb[k], flags) : 0;
+        }
+    }
+}
+
 // alpha numerator ta (0..261120) -> signed-complement float: +alpha when alpha <= 1/2,
 // -(1 - alpha) otherwise.  Both alpha and 1 - alpha are then recoverable with ~1e-7 RELATIVE
 // error, which the composite needs (|out - ref| <= 1e-5 rel even where (1-alpha)*B dominates).
@@ -349,6 +428,12 @@ __device__ __forceinline__ vm_axis_entry vm_ld_axis(const vm_axis_entry *p) {
 // ---------------------------------------------------------------------------------------
 // fused flow stage (C2 / stage A of C4) - shared by vm_flow.cu and the dependency-driven kernel of vm_lean.cu
 // ---------------------------------------------------------------------------------------
+#ifndef C2_GROUP
+#define C2_GROUP 1                 /* pixels whose gathers are issued together (vm_flow_pxn): 1 (pixel by pixel, default), 2 or 4.
+                                      Measured (1080p x 64, C2): 1 @ 5 CTAs/SM 13.8 us per frame, 2 @ 4 CTAs/SM 14.0 us, 4 @ 3 CTAs/SM
+                                      16.9 us, 4 @ 4 CTAs/SM (spills) 19.9 us - the registers that keep more gathers in flight per
+                                      thread cost more occupancy than they buy */
+#endif
 #define C2_TW 128
 #define C2_TH 8                    /* rows in flight per CTA (one per warp) */
 #define C2_ROWS 40                 /* rows per CTA: each warp walks C2_ROWS / C2_TH of them */
@@ -399,9 +484,15 @@ __device__ __forceinline__ void vm_flow_unit_t(const uint8_t *__restrict__ fg, c
             const float fi = (float)i;
             const float2 fl[4] = {{f01.x, f01.y}, {f01.z, f01.w}, {f23.x, f23.y}, {f23.z, f23.w}};
             VmFlowPx px[4];
+#if C2_GROUP == 1
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 px[k] = vm_flow_px<HAS_FWD>(fg32, ff, h, w, i, j + k, fi, fj + (float)k, fl[k], flags);
+#else
+#pragma unroll
+            for (int g = 0; g < 4; g += C2_GROUP)
+                vm_flow_pxn<HAS_FWD, C2_GROUP>(fg32, ff, h, w, i, j + g, fi, fj + (float)g, fl + g, px + g, flags);
+#endif
             if (PACKED) {
                 uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<uint2 *>(out_bgr) + fbase + p);
                 op[0] = make_uint4(px[0].bgr, vm_pack_alpha<PACKED>(px[0]), px[1].bgr, vm_pack_alpha<PACKED>(px[1]));

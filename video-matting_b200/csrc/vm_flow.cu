@@ -149,8 +149,11 @@ extern "C" int vm_composite(const void *fg, int fg_dtype, const void *bg, int bg
 // ---------------------------------------------------------------------------------------
 // (C2_* tile constants, vm_alpha_f32, vm_pack_alpha and the unit body vm_flow_unit live in vm_common.cuh)
 
+#ifndef C2_MINB
+#define C2_MINB 5                  /* CTAs of 256 threads per SM (48 registers); see C2_GROUP in vm_common.cuh */
+#endif
 template <bool HAS_FWD, int PACKED>
-__global__ void __launch_bounds__(256, 5)
+__global__ void __launch_bounds__(256, C2_MINB)
 k_flow_warp_mask_bgra(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd,
                       const float2 *__restrict__ fwd, int h, int w, int tiles_x, int tiles_y,
                       uint8_t *__restrict__ out_bgr, float *__restrict__ out_alpha,
