@@ -25,8 +25,15 @@ H, W, CLIP, NCTRL = 1080, 1920, 64, 5
 BYTES_PER_PX = {"c4": 39, "c2": 27}
 # dram__bytes_read.sum + dram__bytes_write.sum of the four kernels of one 64-frame launch, from the ncu
 # --set full capture summarised in profiles/ (None until measured for the current kernels)
-TRAFFIC_PER_LAUNCH = 8758900480
+TRAFFIC_PER_LAUNCH = 8486719488
 TRAFFIC_SOURCE = "profiles/r01_lean_traffic.txt"
+# the same capture per kernel (spline, tile boxes, flow stage, resampling), bytes per 64-frame launch
+STAGE_TRAFFIC = [600568960, 133293312, 3683009920, 4069848192]
+# what binds each stage: the spline stage has no HBM traffic to speak of, it is bound by the
+# float64 pipe - 10.85 DP instructions per (coarse point, control point) evaluation (ncu instruction
+# histogram), one DP instruction per 2 cycles and SM sub-partition
+STAGE_BOUND = ["fp64 pipe", "latency", "hbm", "hbm + instruction issue"]
+DP_PER_EVAL = 10.85
 METRIC = "1080p frames/s (warp+TPS+composite)"
 WORKLOAD = ("C4 1080p: flow warp + fwd/bwd occlusion mask + TPS (25 control points, fresh grid per frame) "
             "+ composite, BGRA uint8 in, float32x4 out, clip of 64 frames per GPU per step")
@@ -230,9 +237,14 @@ def run_ours(args):
              "k_flow_warp_mask_bgra<1,2> (flow warp + consistency mask)", "k_lean_fine<1,4> (resampling + composite)"]
     # algorithmic bytes each stage moves per pixel (SURVEY 8d layouts; intermediates are not algorithmic)
     stage_bpp = [0, 0, 8 + 8 + 4, 3 + 16]
-    stages = [{"kernel": nm, "ms": ms_k, "share_of_step": ms_k / sum(stage_ms),
-               "algorithmic_GBps": (bpp * H * W * CLIP / (ms_k / 1e3) / 1e9) if bpp else None}
-              for nm, ms_k, bpp in zip(names, stage_ms, stage_bpp)]
+    stages = [{"kernel": nm, "ms": ms_k, "share_of_step": ms_k / sum(stage_ms), "bound": bound,
+               "algorithmic_GBps": (bpp * H * W * CLIP / (ms_k / 1e3) / 1e9) if bpp else None,
+               "dram_GBps": tr / (ms_k / 1e3) / 1e9, "dram_frac_of_peak": tr / (ms_k / 1e3) / 1e9 / peak}
+              for nm, ms_k, bpp, tr, bound in zip(names, stage_ms, stage_bpp, STAGE_TRAFFIC, STAGE_BOUND)]
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    sm_hz = (((clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)) * 1e6
+    evals = CLIP * (H // 2) * (W // 2) * NCTRL * NCTRL
+    stages[0]["fp64_pipe_frac"] = (evals / 32 * DP_PER_EVAL) / ((stage_ms[0] / 1e3) * sm_count * 4 * 0.5 * sm_hz)
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
