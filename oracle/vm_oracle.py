@@ -1,8 +1,11 @@
 """CPU oracle for the video-matting hot path.  TEST INFRASTRUCTURE ONLY.
 
 This module is the checker, never the product: only ``tests/``, ``__graft_entry__.smoke()``
-and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.  Nothing
-under ``video-matting_b200/`` imports it and the product path has no CPU fallback.
+and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it (the
+measurement helpers under ``scripts/`` and ``bench.py`` also take their seeded synthetic inputs
+from the generators at the end of this file and time its functions as CPU baselines - never as
+the thing shipped).  Nothing under ``video-matting_b200/`` imports it and the product path has
+no CPU fallback.
 
 It is a NumPy restatement of the per-frame pipeline of the reference
 (``/root/reference/{flow,tps,augmentation,reader}.py``) *including* the arithmetic of the
