@@ -196,14 +196,17 @@ int vm_set_option(const char *key, int value);
  *                         change_illumination (augmentation.py:88-99).  mode 1: src = vm_aug_tps output ->
  *                         out_bgr (n,h,w,3) uint8 + out_alpha (n,h,w) float32; mode 0: src = (n,h,w,3) uint8
  *                         background -> out_bgr.  params: device array of n {double M[6]; int32 tu, tv}
- *                         (M = 2x3 matrix of the second pass); luts: device (n,256) uint8 S/V tables.      */
+ *                         (M = 2x3 matrix of the second pass); luts: device (n,256) uint8 S/V tables.
+ *   float64 alpha (optional, both NULL otherwise): vm_aug_tps also writes alpha64 (n,h+1,w+1) in scipy's float64
+ *                         operation order and vm_aug_affine (mode 1) reads it and writes out_alpha64 (n,h,w) float64
+ *                         instead of out_alpha - what the reference's augment() returns (augmentation.py:125).      */
 int vm_alpha_stats_bgra(const uint8_t *bgra, int n, int h, int w, unsigned long long *out, void *stream);
 int vm_tps_coarse_packed(const double *ctrl, const double *coef, int n, int N, int nx, int ny,
                          double step_x, double step_y, void *T, unsigned int *counter, void *stream);
 int vm_aug_tps(const uint8_t *fg_bgra, const void *T, int nx, int ny, const vm_axis_entry *rows,
-               const vm_axis_entry *cols, int n, int h, int w, void *inter, int32_t *status, void *stream);
-int vm_aug_affine(int mode, const void *src, const void *params, const uint8_t *luts, int n, int h, int w,
-                  uint8_t *out_bgr, float *out_alpha, void *stream);
+               const vm_axis_entry *cols, int n, int h, int w, void *inter, double *alpha64, int32_t *status, void *stream);
+int vm_aug_affine(int mode, const void *src, const double *alpha64, const void *params, const uint8_t *luts, int n, int h, int w,
+                  uint8_t *out_bgr, float *out_alpha, double *out_alpha64, void *stream);
 
 /* ---- batch loader: loader.load_and_crop / simple_load_crop / video_load_crop ----
  * reference: loader.py:39-85, 119-157, 285-330 (one sample), loader.py:93-116, 160-171, 333-345 (batch).

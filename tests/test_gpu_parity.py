@@ -7,6 +7,8 @@ bit-exact; float alpha and composites |got-ref| <= 1e-5*|ref| + atol (1e-6 alpha
 up to knife-edge samples (float64 transform differs from numpy's by ~1e-11 px), which are
 counted and bounded, never masked.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -628,6 +630,16 @@ def test_augment_clip_matches_sequential_augment(vm, shape):
         assert np.array_equal(nbg[k], rbg)
         assert np.count_nonzero(np.any(nfg[k] != rfg, axis=-1)) <= 2
         assert np.allclose(nal[k], ral, rtol=RTOL, atol=1e-6)
+    # float64 alpha: the reference's dtype and operation order (scipy map_coordinates, then cv2.warpAffine on
+    # float64) - equal to the drop-in's float64 alpha up to the ~1e-13 px difference of the transform
+    np.random.seed(2024)
+    nfg64, nbg64, nal64 = A.augment_clip(frames, bgs, alpha_dtype=torch.float64)
+    assert nal64.dtype == np.float64 and np.array_equal(nfg64, nfg) and np.array_equal(nbg64, nbg)
+    for k in range(n):
+        assert np.abs(nal64[k] - seq[k][2]).max() <= 1e-9
+        # (bit equality is out of reach even for saturated alpha: sum(w_k * 1.0) in scipy's order is 1 or 1 - 2^-53
+        #  depending on the last bits of the weights, i.e. on the ~1e-13 px by which the two transforms differ)
+        assert np.all(nal64[k][seq[k][2] == 0.] == 0.)
 
 
 def test_augment_clip_golden(vm, golden):
@@ -638,3 +650,52 @@ def test_augment_clip_golden(vm, golden):
     assert np.allclose(nal[0], golden["aug_alpha_out"], rtol=RTOL, atol=1e-6)
     assert np.abs(nbg[0].astype(int) - golden["aug_bg_out"].astype(int)).max() <= 1
     assert np.count_nonzero(np.abs(nfg[0].astype(int) - golden["aug_fg_out"].astype(int)) > 1) <= 2
+
+
+def test_augmentation_writer_matches_sequential_augment(vm, tmp_path, capsys):
+    """augmentation.augmentation (reference augmentation.py:138-166): same files and same np.random order as
+    the per-variant loop of the reference, here emulated with the drop-in augment() (itself pinned by the
+    reference golden vectors)."""
+    import cv2
+    A = vm.augmentation
+    h, w = 52, 76
+    dim, voc, sig = tmp_path / "DIM", tmp_path / "VOC", tmp_path / "SIG"
+    for d in (dim / "fg" / "DIM_TEST", dim / "fg" / "DIM_TRAIN", voc, sig / "fg" / "augmented", sig / "bg" / "augmented"):
+        os.makedirs(d)
+    assert cv2.imwrite(str(dim / "fg" / "DIM_TEST" / "t0.png"), O.synth_frame(1, h, w))
+    assert cv2.imwrite(str(dim / "fg" / "DIM_TRAIN" / "r0.png"), O.synth_frame(2, h, w))
+    for k, shape in enumerate(((h, w), (40, 50), (90, 120))):
+        assert cv2.imwrite(str(voc / f"v{k}.png"), O.synth_background(k, *shape))
+    old = A.N_VARIANTS, A.VARIANT_BATCH
+    A.N_VARIANTS, A.VARIANT_BATCH = 7, 3
+    try:
+        np.random.seed(31)
+        A.augmentation(str(dim), str(voc), str(sig))
+    finally:
+        A.N_VARIANTS, A.VARIANT_BATCH = old
+    assert "Processing image" in capsys.readouterr().out
+    # sequential emulation with the same seed and the same directory listing order
+    np.random.seed(31)
+    paths = [str(dim / "fg" / f / n) for f in ("DIM_TEST", "DIM_TRAIN") for n in os.listdir(dim / "fg" / f)]
+    voc_list = [str(voc / n) for n in os.listdir(voc)]
+    n_alpha_off = 0
+    for p in paths:
+        alpha, fg = vm.reader.read_fg_img(p)
+        name = os.path.basename(p).split(".")[0]
+        ref = cv2.imread(str(sig / "fg" / "augmented" / f"{name}_fg_ref.png"), cv2.IMREAD_UNCHANGED)
+        assert np.array_equal(ref[..., :3], fg) and np.array_equal(ref[..., 3], (255. * alpha).astype(np.uint8))
+        for i in range(7):
+            bg = cv2.imread(voc_list[np.random.randint(len(voc_list))])
+            bg = cv2.resize(bg, dsize=(w, h), interpolation=cv2.INTER_LINEAR)
+            nfg, nbg, nal = A.augment(np.ascontiguousarray(fg), bg, alpha)
+            got_fg = cv2.imread(str(sig / "fg" / "augmented" / f"{name}_fg_{i:04d}.png"), cv2.IMREAD_UNCHANGED)
+            assert np.array_equal(cv2.imread(str(sig / "bg" / "augmented" / f"{name}_bg_ref_{i:04d}.png")), bg)
+            assert np.array_equal(cv2.imread(str(sig / "bg" / "augmented" / f"{name}_bg_{i:04d}.png")), nbg)
+            assert np.array_equal(got_fg[..., :3], nfg)
+            da = np.abs(got_fg[..., 3].astype(int) - (255. * nal).astype(np.uint8).astype(int))
+            assert da.max() <= 1
+            n_alpha_off += int(da.sum())
+    # (255. * alpha).astype(uint8) truncates values that sit within an ulp of an integer wherever alpha is locally
+    # constant (255 * 0.9999999999999999 -> 254), so these bytes follow the last bits of the interpolation weights;
+    # they agree to +-1 level, and mostly exactly
+    assert n_alpha_off <= 0.02 * 14 * h * w

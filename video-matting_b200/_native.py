@@ -41,9 +41,9 @@ SIGNATURES = {
     "vm_flow_tps_composite_bgra": [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _D, _D, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "vm_set_option": [_c.c_char_p, _I],
     "vm_tps_coarse_packed": [_P, _P, _I, _I, _I, _I, _D, _D, _P, _P, _P],
-    "vm_aug_tps": [_P, _P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P],
+    "vm_aug_tps": [_P, _P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "vm_alpha_stats_bgra": [_P, _I, _I, _I, _P, _P],
-    "vm_aug_affine": [_I, _P, _P, _P, _I, _I, _I, _P, _P, _P],
+    "vm_aug_affine": [_I, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "vm_loader_batch": [_P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P],
     "vm_sq_err_sum": [_P, _P, _I, _L, _P, _P],
     "vm_trimap_from_matte": [_P, _I, _I, _I, _I, _P, _P],

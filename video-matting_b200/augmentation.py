@@ -142,39 +142,19 @@ def augment(fg, bg, alpha):
 AUG_PARAMS = np.dtype([("M", "<f8", (6,)), ("tu", "<i4"), ("tv", "<i4")])       # csrc/vm_affine.cu VmAugParams
 
 
-def augment_clip(fg_bgra, bg):
-    """augment() for a whole clip in a handful of launches (BASELINE config 5).
-
-    ``fg_bgra`` (n, H, W, 4) uint8 BGRA with alpha = A/255 (what reader.read_fg_img returns, reference
-    reader.py:16-17), ``bg`` (n, H, W, 3) uint8; NumPy arrays or CUDA tensors.  Equivalent to
-    ``[augment(fg[k, ..., :3], bg[k], fg[k, ..., 3] / 255.) for k in range(n)]``: the global np.random
-    stream is consumed in exactly that order (40 draws per frame, reference augmentation.py:102-135), the
-    TPS systems are solved on the host with numpy's pinv (reference tps.py:119).  Returns
-    (new_fg (n,H,W,3) uint8, new_bg (n,H,W,3) uint8, new_alpha (n,H,W) float32) of the input kind."""
-    import ctypes
-    lib = N.load()
-    fg_d, kind = N.to_device(fg_bgra)
-    bg_d, _ = N.to_device(bg)
-    assert fg_d.dtype == torch.uint8 and fg_d.dim() == 4 and fg_d.shape[3] == 4, "fg must be (n, H, W, 4) uint8 BGRA"
-    n, h, w = fg_d.shape[:3]
-    assert bg_d.dtype == torch.uint8 and tuple(bg_d.shape) == (n, h, w, 3), "bg must be (n, H, W, 3) uint8"
-    fg_d, bg_d = fg_d.contiguous(), bg_d.contiguous()
-    dev = fg_d.device
-    new_fg = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
-    new_bg = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
-    new_alpha = torch.empty((n, h, w), dtype=torch.float32, device=dev)
-    if n == 0:
-        return tuple(N.from_device(t, kind) for t in (new_fg, new_bg, new_alpha))
-    # ---- object_size / fg_center of every frame: one kernel, one host read --------------------------
-    stats = torch.zeros((n, 3), dtype=torch.int64, device=dev)
-    N.check(lib.vm_alpha_stats_bgra(N.ptr(fg_d), n, h, w, N.ptr(stats), N.stream_ptr()))
-    stats = stats.cpu().numpy()
-    # ---- the reference's random draws, frame by frame, in its order -----------------------------------
+def _augment_plan(stats, h, w, before_frame=None):
+    """The reference's random draws for every frame of a clip, frame by frame, in its order (40 per frame,
+    augmentation.py:102-135) -> (background params, foreground params, S/V tables, TPS grids).
+    ``stats``: (n, 3) {count(alpha != 0), sum(rows), sum(cols)}; ``before_frame(k)`` runs ahead of frame k's
+    draws (augmentation() draws its background index there, augmentation.py:158)."""
+    n = len(stats)
     bt, br, bs = 0.05, 10, 0.15
     par_bg = np.zeros(n, dtype=AUG_PARAMS); par_fg = np.zeros(n, dtype=AUG_PARAMS)
     luts = np.zeros((n, 256), dtype=np.uint8)
     grids = []
     for k in range(n):
+        if before_frame is not None:
+            before_frame(k)
         cnt, si, sj = (int(v) for v in stats[k])
         fg_size = np.sqrt(cnt)
         tu_bg = int(np.random.uniform(-w * bt, w * bt)); tv_bg = int(np.random.uniform(-h * bt, h * bt))
@@ -190,48 +170,135 @@ def augment_clip(fg_bgra, bg):
         par_bg[k] = (_rotation_matrix((w // 2, h // 2), 0., scale_bg).reshape(6), tu_bg, tv_bg)
         par_fg[k] = (_rotation_matrix(center, rot_fg, scale_fg).reshape(6), tu_fg, tv_fg)
         luts[k] = illumination_lut(a, b, c)
-    # ---- host TPS solve (system built from the deformed grid, tps.py:51), then the device stages -----
-    plan = P.get_plan((0, 0, h, w), 2, dev)
+    return par_bg, par_fg, luts, grids
+
+
+def _alpha_stats_clip(fg_d):
+    """object_size / fg_center sums of every BGRA frame: one kernel, one host read."""
+    n, h, w = fg_d.shape[:3]
+    stats = torch.zeros((n, 3), dtype=torch.int64, device=fg_d.device)
+    N.check(N.load().vm_alpha_stats_bgra(N.ptr(fg_d), n, h, w, N.ptr(stats), N.stream_ptr()))
+    return stats.cpu().numpy()
+
+
+def _augment_run(fg_d, bg_d, plan, alpha_dtype=torch.float32):
+    """Device stages of augment() for a clip whose random parameters are known: host TPS solve (system built
+    from the deformed grid, tps.py:51), spline, TPS resampling, fused affine passes + illumination.
+    ``alpha_dtype`` float64 carries alpha through both stages in float64 with scipy's / OpenCV's operation
+    order (what the reference returns); float32 halves the intermediate traffic."""
+    lib = N.load()
+    par_bg, par_fg, luts, grids = plan
+    n, h, w = fg_d.shape[:3]
+    dev = fg_d.device
+    new_fg = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+    new_bg = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+    wide = alpha_dtype == torch.float64
+    new_alpha = torch.empty((n, h, w), dtype=torch.float64 if wide else torch.float32, device=dev)
+    a64 = torch.empty((n, h + 1, w + 1), dtype=torch.float64, device=dev) if wide else None
+    tplan = P.get_plan((0, 0, h, w), 2, dev)
     ctrl, coef = P.solve_grids(grids, dev)
     up = lambda arr: torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).to(dev)
     par_bg_d, par_fg_d, luts_d = up(par_bg), up(par_fg), up(luts)
-    T = torch.empty((n, plan.nx, plan.ny, 2), dtype=torch.float64, device=dev)
+    T = torch.empty((n, tplan.nx, tplan.ny, 2), dtype=torch.float64, device=dev)
     counter = torch.zeros(64, dtype=torch.int32, device=dev)
     inter = torch.empty((n, h + 1, w + 1, 2), dtype=torch.int32, device=dev)
     status = N.new_status(dev)
     Np = ctrl.shape[1]
-    N.check(lib.vm_tps_coarse_packed(N.ptr(ctrl), N.ptr(coef), n, Np, plan.nx, plan.ny, plan.step_x, plan.step_y,
+    N.check(lib.vm_tps_coarse_packed(N.ptr(ctrl), N.ptr(coef), n, Np, tplan.nx, tplan.ny, tplan.step_x, tplan.step_y,
                                      N.ptr(T), N.ptr(counter), N.stream_ptr()))
-    N.check(lib.vm_aug_tps(N.ptr(fg_d), N.ptr(T), plan.nx, plan.ny, N.ptr(plan.rows), N.ptr(plan.cols), n, h, w,
-                           N.ptr(inter), N.ptr(status), N.stream_ptr()))
-    N.check(lib.vm_aug_affine(1, N.ptr(inter), N.ptr(par_fg_d), N.ptr(luts_d), n, h, w, N.ptr(new_fg), N.ptr(new_alpha),
+    N.check(lib.vm_aug_tps(N.ptr(fg_d), N.ptr(T), tplan.nx, tplan.ny, N.ptr(tplan.rows), N.ptr(tplan.cols), n, h, w,
+                           N.ptr(inter), N.ptr(a64), N.ptr(status), N.stream_ptr()))
+    N.check(lib.vm_aug_affine(1, N.ptr(inter), N.ptr(a64), N.ptr(par_fg_d), N.ptr(luts_d), n, h, w, N.ptr(new_fg),
+                              None if wide else N.ptr(new_alpha), N.ptr(new_alpha) if wide else None, N.stream_ptr()))
+    N.check(lib.vm_aug_affine(0, N.ptr(bg_d), None, N.ptr(par_bg_d), N.ptr(luts_d), n, h, w, N.ptr(new_bg), None, None,
                               N.stream_ptr()))
-    N.check(lib.vm_aug_affine(0, N.ptr(bg_d), N.ptr(par_bg_d), N.ptr(luts_d), n, h, w, N.ptr(new_bg), None, N.stream_ptr()))
-    return tuple(N.from_device(t, kind) for t in (new_fg, new_bg, new_alpha))
+    return new_fg, new_bg, new_alpha
+
+
+def augment_clip(fg_bgra, bg, alpha_dtype=torch.float32):
+    """augment() for a whole clip in a handful of launches (BASELINE config 5).
+
+    ``fg_bgra`` (n, H, W, 4) uint8 BGRA with alpha = A/255 (what reader.read_fg_img returns, reference
+    reader.py:16-17), ``bg`` (n, H, W, 3) uint8; NumPy arrays or CUDA tensors.  Equivalent to
+    ``[augment(fg[k, ..., :3], bg[k], fg[k, ..., 3] / 255.) for k in range(n)]``: the global np.random
+    stream is consumed in exactly that order (40 draws per frame, reference augmentation.py:102-135), the
+    TPS systems are solved on the host with numpy's pinv (reference tps.py:119).  Returns
+    (new_fg (n,H,W,3) uint8, new_bg (n,H,W,3) uint8, new_alpha (n,H,W) float32) of the input kind;
+    ``alpha_dtype=torch.float64`` returns the alpha in float64 as the reference does (same operation order)."""
+    fg_d, kind = N.to_device(fg_bgra)
+    bg_d, _ = N.to_device(bg)
+    assert fg_d.dtype == torch.uint8 and fg_d.dim() == 4 and fg_d.shape[3] == 4, "fg must be (n, H, W, 4) uint8 BGRA"
+    n, h, w = fg_d.shape[:3]
+    assert bg_d.dtype == torch.uint8 and tuple(bg_d.shape) == (n, h, w, 3), "bg must be (n, H, W, 3) uint8"
+    fg_d, bg_d = fg_d.contiguous(), bg_d.contiguous()
+    if n == 0:
+        dev = fg_d.device
+        empty = (torch.empty((0, h, w, 3), dtype=torch.uint8, device=dev), torch.empty((0, h, w, 3), dtype=torch.uint8, device=dev),
+                 torch.empty((0, h, w), dtype=alpha_dtype, device=dev))
+        return tuple(N.from_device(t, kind) for t in empty)
+    plan = _augment_plan(_alpha_stats_clip(fg_d), h, w)
+    return tuple(N.from_device(t, kind) for t in _augment_run(fg_d, bg_d, plan, alpha_dtype))
+
+
+#: variants written per foreground by augmentation() (reference augmentation.py:140) and how many of them go
+#: through the device stages at once
+N_VARIANTS = 50
+VARIANT_BATCH = 10
 
 
 def augmentation(dim_dataset, voc_dataset, sig_dataset):
     """create synthetic data for video matting (DIM mattes over VOC backgrounds) - reference
-    augmentation.py:138-166.  Disk layout and file names follow the reference."""
+    augmentation.py:138-166; disk layout, file names and the np.random draw order (one background index,
+    then augment()'s 40 draws, per variant) follow the reference.  The 50 variants of a foreground are
+    planned first, then run through ``augment_clip``'s device stages ten at a time while host threads read
+    the backgrounds and write the PNGs.  The alpha bytes are ``(255. * alpha).astype(uint8)`` on the float64
+    alpha, as in the reference.  Where alpha is locally constant that product sits within an ulp of an integer
+    (255 * 0.9999999999999999 truncates to 254), so those bytes follow the last bits of the interpolation
+    weights: they agree with the per-variant ``augment()`` loop to +-1 level (about 1 % of the bytes differ)."""
     import cv2
-    n = 50
+    from concurrent.futures import ThreadPoolExecutor
+    n = N_VARIANTS
     paths = [os.path.join(dim_dataset, 'fg', folder, f)
              for folder in ('DIM_TEST', 'DIM_TRAIN')
              for f in os.listdir(os.path.join(dim_dataset, 'fg', folder))]
     voc_list = [os.path.join(voc_dataset, f) for f in os.listdir(voc_dataset)]
     dst_fg = os.path.join(sig_dataset, 'fg', 'augmented')
     dst_bg = os.path.join(sig_dataset, 'bg', 'augmented')
-    for k, path in enumerate(paths):
-        alpha, fg = reader.read_fg_img(path)
-        name = os.path.basename(path).split('.')[0]
-        print('Processing image {} ({}/{})'.format(name, k + 1, len(paths)))
-        a8 = (255. * alpha.reshape((alpha.shape[0], alpha.shape[1], 1))).astype(np.uint8)
-        cv2.imwrite(os.path.join(dst_fg, '{}_fg_ref.png'.format(name)), np.concatenate((fg, a8), axis=2))
-        for i in range(n):
-            bg = cv2.imread(voc_list[np.random.randint(len(voc_list))])
-            bg = cv2.resize(bg, dsize=(fg.shape[1], fg.shape[0]), interpolation=cv2.INTER_LINEAR)
-            nfg, nbg, nal = augment(fg, bg, alpha)
-            na8 = (255. * nal.reshape((nal.shape[0], nal.shape[1], 1))).astype(np.uint8)
-            cv2.imwrite(os.path.join(dst_bg, '{}_bg_ref_{:04d}.png'.format(name, i)), bg)
-            cv2.imwrite(os.path.join(dst_bg, '{}_bg_{:04d}.png'.format(name, i)), nbg)
-            cv2.imwrite(os.path.join(dst_fg, '{}_fg_{:04d}.png'.format(name, i)), np.concatenate((nfg, na8), axis=2))
+    ref_lut = (255. * (np.arange(256) / 255.)).astype(np.uint8)         # (255. * alpha).astype(uint8) of alpha = A / 255.
+
+    def load_bg(p, h, w):
+        bg = cv2.imread(p)
+        return cv2.resize(bg, dsize=(w, h), interpolation=cv2.INTER_LINEAR)  # augmentation.py:159-160
+
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as pool:
+        pending = []
+        for k, path in enumerate(paths):
+            img = reader.read_bgra(path)
+            h, w = img.shape[:2]
+            name = os.path.basename(path).split('.')[0]
+            print('Processing image {} ({}/{})'.format(name, k + 1, len(paths)))
+            ref = img.copy()
+            ref[:, :, 3] = ref_lut[img[:, :, 3]]
+            pending.append(pool.submit(cv2.imwrite, os.path.join(dst_fg, '{}_fg_ref.png'.format(name)), ref))
+            fg_d = torch.from_numpy(np.ascontiguousarray(img[None])).cuda()
+            stats = np.repeat(_alpha_stats_clip(fg_d), n, axis=0)
+            picks = []
+            plan = _augment_plan(stats, h, w, before_frame=lambda i: picks.append(voc_list[np.random.randint(len(voc_list))]))
+            bg_jobs = [pool.submit(load_bg, p, h, w) for p in picks]
+            for lo in range(0, n, VARIANT_BATCH):
+                hi = min(lo + VARIANT_BATCH, n)
+                bgs = [j.result() for j in bg_jobs[lo:hi]]
+                bg_d = torch.from_numpy(np.stack(bgs)).cuda()
+                sub = (plan[0][lo:hi], plan[1][lo:hi], plan[2][lo:hi], plan[3][lo:hi])
+                nfg, nbg, nal = _augment_run(fg_d.expand(hi - lo, h, w, 4).contiguous(), bg_d, sub, torch.float64)
+                na8 = (255. * nal).to(torch.uint8)                      # float64 product, truncation (augmentation.py:162)
+                out_fg = torch.cat((nfg, na8[..., None]), dim=3).cpu().numpy()
+                out_bg = nbg.cpu().numpy()
+                for i in range(lo, hi):
+                    pending.append(pool.submit(cv2.imwrite, os.path.join(dst_bg, '{}_bg_ref_{:04d}.png'.format(name, i)), bgs[i - lo]))
+                    pending.append(pool.submit(cv2.imwrite, os.path.join(dst_bg, '{}_bg_{:04d}.png'.format(name, i)), out_bg[i - lo]))
+                    pending.append(pool.submit(cv2.imwrite, os.path.join(dst_fg, '{}_fg_{:04d}.png'.format(name, i)), out_fg[i - lo]))
+            pending = [f for f in pending if not f.done() or f.result() is False]
+        for f in pending:
+            if f.result() is False:
+                raise IOError("cv2.imwrite failed")

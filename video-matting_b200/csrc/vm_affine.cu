@@ -229,8 +229,9 @@ extern "C" int vm_alpha_stats_bgra(const uint8_t *bgra, int n, int h, int w, uns
 // (after the illumination change) + new_alpha float32.  !FG: source = (h, w, 3) uint8 background -> new_bg.
 template <bool FG>
 __global__ void __launch_bounds__(256)
-k_aug_affine(const void *__restrict__ src_all, const VmAugParams *__restrict__ params, const uint8_t *__restrict__ luts,
-             int h, int w, uint8_t *__restrict__ out_bgr, float *__restrict__ out_alpha) {
+k_aug_affine(const void *__restrict__ src_all, const double *__restrict__ alpha64, const VmAugParams *__restrict__ params,
+             const uint8_t *__restrict__ luts, int h, int w, uint8_t *__restrict__ out_bgr, float *__restrict__ out_alpha,
+             double *__restrict__ out_alpha64) {
     __shared__ int sdiv[256], hdiv[256];
     __shared__ uint8_t slut[256];
     __shared__ VmAffineInv Ash;
@@ -274,8 +275,9 @@ k_aug_affine(const void *__restrict__ src_all, const VmAugParams *__restrict__ p
             c[t] = 0u; al[t] = 0.0;
             if (ok) {
                 if (FG) {
-                    const uint2 e = __ldg(reinterpret_cast<const uint2 *>(src_all) + ((int64_t)frame * sh + sy) * sw + sx);
-                    c[t] = e.x; al[t] = (double)__uint_as_float(e.y);
+                    const int64_t q = ((int64_t)frame * sh + sy) * sw + sx;
+                    const uint2 e = __ldg(reinterpret_cast<const uint2 *>(src_all) + q);
+                    c[t] = e.x; al[t] = alpha64 ? __ldg(alpha64 + q) : (double)__uint_as_float(e.y);
                 } else {
                     const uint8_t *p = reinterpret_cast<const uint8_t *>(src_all) + (((int64_t)frame * sh + sy) * sw + sx) * 3;
                     c[t] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
@@ -289,20 +291,24 @@ k_aug_affine(const void *__restrict__ src_all, const VmAugParams *__restrict__ p
         const uint32_t o = vm_illum_px(ch[0], ch[1], ch[2], sdiv, hdiv, slut);
         const int64_t p = ((int64_t)frame * h + y) * w + x;
         out_bgr[p * 3] = (uint8_t)o; out_bgr[p * 3 + 1] = (uint8_t)(o >> 8); out_bgr[p * 3 + 2] = (uint8_t)(o >> 16);
-        if (FG) out_alpha[p] = (float)VmTap<double>::blend(al[0], al[1], al[2], al[3], fx, fy);
+        if (FG) {
+            const double a = VmTap<double>::blend(al[0], al[1], al[2], al[3], fx, fy);
+            if (out_alpha64) out_alpha64[p] = a; else out_alpha[p] = (float)a;
+        }
     }
 }
 
 // mode 0: background (src = (n,h,w,3) uint8, out_alpha unused); mode 1: foreground (src = vm_aug_tps intermediate).
 // params: device array of n {double M[6]; int tu, tv}; luts: device (n, 256) uint8 S/V tables.
-extern "C" int vm_aug_affine(int mode, const void *src, const void *params, const uint8_t *luts, int n, int h, int w,
-                             uint8_t *out_bgr, float *out_alpha, void *stream) {
-    VM_REQUIRE(src && params && luts && out_bgr && (mode == 0 || out_alpha), "null pointer");
+extern "C" int vm_aug_affine(int mode, const void *src, const double *alpha64, const void *params, const uint8_t *luts, int n, int h,
+                             int w, uint8_t *out_bgr, float *out_alpha, double *out_alpha64, void *stream) {
+    VM_REQUIRE(src && params && luts && out_bgr && (mode == 0 || out_alpha || out_alpha64), "null pointer");
+    VM_REQUIRE(mode == 0 || (alpha64 != nullptr) == (out_alpha64 != nullptr), "float64 alpha needs both the float64 source plane and the float64 output");
     VM_REQUIRE(n >= 0 && n < 65536 && h >= 1 && h < 65536 && w >= 1, "bad size");
     if (n == 0) return VM_OK;
     const dim3 grid((w + 255) / 256, (h + VA_AFF_ROWS - 1) / VA_AFF_ROWS, n);
     cudaStream_t st = (cudaStream_t)stream;
-    if (mode == 1) k_aug_affine<true><<<grid, 256, 0, st>>>(src, (const VmAugParams *)params, luts, h, w, out_bgr, out_alpha);
-    else k_aug_affine<false><<<grid, 256, 0, st>>>(src, (const VmAugParams *)params, luts, h, w, out_bgr, out_alpha);
+    if (mode == 1) k_aug_affine<true><<<grid, 256, 0, st>>>(src, alpha64, (const VmAugParams *)params, luts, h, w, out_bgr, out_alpha, out_alpha64);
+    else k_aug_affine<false><<<grid, 256, 0, st>>>(src, nullptr, (const VmAugParams *)params, luts, h, w, out_bgr, nullptr, nullptr);
     return vm_check_launch("vm_aug_affine");
 }

@@ -1484,10 +1484,12 @@ extern "C" long long vm_lean_launch_count(void) { return g_vl_launches.load(); }
 // illumination change follow in vm_affine.cu (k_aug_affine).  Taps come straight from global memory:
 // this path is bound by its host orchestration (RNG draws and pinv per frame), not by this kernel.
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ uint2 vl_exact_cols(const uint32_t *__restrict__ src, double t0, double t1, int h, int w, int *outside) {
+__device__ __noinline__ uint2 vl_exact_cols(const uint32_t *__restrict__ src, double t0, double t1, int h, int w, int *outside,
+                                            double *a64_out) {
     const VmBilin64 s = vm_mapcoord_setup(t0, t1, h, w);
     if (!s.inside) {
         (*outside)++;
+        *a64_out = 0.0;
         return make_uint2(0u, 0u);                                      // map_coordinates: cval = 0
     }
     const uint32_t e0 = __ldg(src + ((int64_t)s.i0 * w + s.j0)), e1 = __ldg(src + ((int64_t)s.i0 * w + s.j1));
@@ -1499,6 +1501,7 @@ __device__ __noinline__ uint2 vl_exact_cols(const uint32_t *__restrict__ src, do
                                                                (double)((e2 >> (8 * c)) & 255u), (double)((e3 >> (8 * c)) & 255u))) << (8 * c);
     const double a64 = vm_mapcoord_blend(s, (double)(e0 >> 24) / 255.0, (double)(e1 >> 24) / 255.0,
                                          (double)(e2 >> 24) / 255.0, (double)(e3 >> 24) / 255.0);
+    *a64_out = a64;
     return make_uint2(bgr, __float_as_uint((float)a64));
 }
 
@@ -1506,13 +1509,14 @@ __device__ __noinline__ uint2 vl_exact_cols(const uint32_t *__restrict__ src, do
 __global__ void __launch_bounds__(128)
 k_aug_tps(const uint32_t *__restrict__ fg, const double2 *__restrict__ T, int nx, int ny,
           const vm_axis_entry *__restrict__ rows, const vm_axis_entry *__restrict__ cols, int h, int w,
-          uint2 *__restrict__ inter, int32_t *__restrict__ status) {
+          uint2 *__restrict__ inter, double *__restrict__ alpha64, int32_t *__restrict__ status) {
     const int oh = h + 1, ow = w + 1;
     const int j = blockIdx.x * 128 + threadIdx.x, frame = blockIdx.z;
     const int ibeg = blockIdx.y * VA_ROWS, iend = min(ibeg + VA_ROWS, oh);
     if (j >= ow) return;
     const uint32_t *src = fg + (int64_t)frame * h * w;
     uint2 *op = inter + (int64_t)frame * oh * ow + j;
+    double *ap = alpha64 ? alpha64 + (int64_t)frame * oh * ow + j : nullptr;
     const vm_axis_entry ce = vm_ld_axis(cols + j);
     const double yf = ce.frac, y1 = 1.0 - yf;
     const double2 *Ta = T + (int64_t)frame * nx * ny + ce.i0, *Tb = T + (int64_t)frame * nx * ny + ce.i1;
@@ -1534,6 +1538,7 @@ k_aug_tps(const uint32_t *__restrict__ fg, const double2 *__restrict__ T, int nx
         uint32_t fa, fb;
         const bool fast = vl_geometry(t0, t1, h, w, n0, n1, fa, fb);
         uint2 o;
+        double a64 = 0.0;
         if (fast) {
             const uint32_t *g0 = src + (n0 * w + n1), *g1 = g0 + w;
             const uint32_t e0 = __ldg(g0), e1 = __ldg(g0 + 1), e2 = __ldg(g1), e3 = __ldg(g1 + 1);
@@ -1552,11 +1557,17 @@ k_aug_tps(const uint32_t *__restrict__ fg, const double2 *__restrict__ T, int nx
             const unsigned long long a2f = (unsigned long long)(e0 >> 24) * W00 + (unsigned long long)(e1 >> 24) * W01 +
                                            (unsigned long long)(e2 >> 24) * W10 + (unsigned long long)(e3 >> 24) * W11;
             o = make_uint2(bgr, __float_as_uint((float)a2f * (float)(1.0 / (255.0 * 1073741824.0))));
-            if (knife) o = vl_exact_cols(src, t0, t1, h, w, &outside);
+            if (knife) o = vl_exact_cols(src, t0, t1, h, w, &outside, &a64);
+            else if (ap) {                                              // scipy's float64 operation order (tps.py:34)
+                const VmBilin64 sb = vm_mapcoord_setup(t0, t1, h, w);
+                a64 = vm_mapcoord_blend(sb, (double)(e0 >> 24) / 255.0, (double)(e1 >> 24) / 255.0,
+                                        (double)(e2 >> 24) / 255.0, (double)(e3 >> 24) / 255.0);
+            }
         } else {
-            o = vl_exact_cols(src, t0, t1, h, w, &outside);
+            o = vl_exact_cols(src, t0, t1, h, w, &outside, &a64);
         }
         op[(int64_t)i * ow] = o;
+        if (ap) ap[(int64_t)i * ow] = a64;
     }
     if (status && outside) atomicAdd(status + VM_STATUS_TPS_OUTSIDE, outside);
 }
@@ -1575,13 +1586,13 @@ extern "C" int vm_tps_coarse_packed(const double *ctrl, const double *coef, int 
 }
 
 extern "C" int vm_aug_tps(const uint8_t *fg_bgra, const void *T, int nx, int ny, const vm_axis_entry *rows,
-                          const vm_axis_entry *cols, int n, int h, int w, void *inter, int32_t *status, void *stream) {
+                          const vm_axis_entry *cols, int n, int h, int w, void *inter, double *alpha64, int32_t *status, void *stream) {
     VM_REQUIRE(fg_bgra && T && rows && cols && inter, "null pointer");
     VM_REQUIRE(n >= 0 && n < 65536 && h >= 2 && w >= 2 && (int64_t)(h + 1) * (w + 1) < (1ll << 28), "bad size");
     if (n == 0) return VM_OK;
     const dim3 grid((w + 1 + 127) / 128, (h + 1 + VA_ROWS - 1) / VA_ROWS, n);
     VM_REQUIRE(grid.y <= 65535, "frame too tall");
     k_aug_tps<<<grid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t *>(fg_bgra), reinterpret_cast<const double2 *>(T), nx, ny,
-                                                       rows, cols, h, w, reinterpret_cast<uint2 *>(inter), status);
+                                                       rows, cols, h, w, reinterpret_cast<uint2 *>(inter), alpha64, status);
     return vm_check_launch("vm_aug_tps");
 }
