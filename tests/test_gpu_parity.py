@@ -699,3 +699,29 @@ def test_augmentation_writer_matches_sequential_augment(vm, tmp_path, capsys):
     # constant (255 * 0.9999999999999999 -> 254), so these bytes follow the last bits of the interpolation weights;
     # they agree to +-1 level, and mostly exactly
     assert n_alpha_off <= 0.02 * 14 * h * w
+
+
+# ------------------------------------------------------------------ BASELINE config 1 (real test images)
+
+def test_config1_window_real_images(vm, capsys):
+    """BASELINE config 1 on a window of the reference's own frames (tests/golden/make_c1_golden.py: in0063 warped
+    onto in0062 with DIS stand-in flows, consistency mask, composite onto sea.jpg), through the drop-in functions
+    and through the fused C2 entry point."""
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1_golden.npz")) as z:
+        c1 = {k: z[k] for k in z.files}
+    fg = c1["fg63_bgra"]
+    alpha, bgr = fg[..., 3] / 255., np.ascontiguousarray(fg[..., :3])
+    wa = vm.flow.warp_img(alpha, c1["backward"])
+    assert wa.dtype == np.float64 and np.array_equal(wa, c1["warp_alpha"])
+    wb = vm.flow.warp_bgr(bgr, c1["backward"])
+    assert np.array_equal(wb, c1["warp_bgr"])
+    ca = vm.flow.correct_alpha(c1["backward"], c1["forward"], wa)
+    assert ca is wa and np.array_equal(ca, c1["corrected"])
+    assert str(tuple(c1["forward"].shape)) in capsys.readouterr().out
+    cmp_ = vm.reader.create_composite_image(wb, c1["bg"], ca)
+    assert close(cmp_, c1["composite"], 1e-5)
+    # fused: one pass over the BGRA frame
+    ob, oa, st = vm.pipeline.flow_warp_mask(dev(fg[None]), dev(c1["backward"][None]), dev(c1["forward"][None]))
+    assert np.array_equal(ob[0].cpu().numpy(), c1["warp_bgr"])
+    assert close(oa[0].cpu().numpy(), c1["corrected"], 1e-6)
+    assert int(st[2]) == int((c1["corrected"] != c1["warp_alpha"]).sum()) and int(st[0]) == 0 and int(st[1]) == 0

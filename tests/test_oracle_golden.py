@@ -187,3 +187,25 @@ def test_bgr2hsv_vs_cv2_exhaustive_slice():
         g, r = np.meshgrid(v, v)
         bgr = np.stack([np.full_like(g, b), g, r], -1)
         assert np.array_equal(O.bgr2hsv_u8(bgr), cv2.cvtColor(bgr, cv2.COLOR_BGR2HSV))
+
+
+# ---- BASELINE config 1 on the reference's own test images (tests/golden/make_c1_golden.py) ----------------
+
+@pytest.fixture(scope="module")
+def c1():
+    with np.load(os.path.join(ROOT, "tests", "golden", "c1_golden.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def test_config1_window_oracle(c1):
+    """in0063 warped onto in0062 with DIS stand-in flows, consistency mask, composite onto sea.jpg: the oracle
+    against the unmodified reference on a window of the real frames."""
+    fg = c1["fg63_bgra"]
+    alpha, bgr = fg[..., 3] / 255., np.ascontiguousarray(fg[..., :3])
+    wa = O.warp_img(alpha, c1["backward"])
+    assert np.array_equal(wa, c1["warp_alpha"])
+    assert np.array_equal(O.warp_bgr(bgr, c1["backward"]), c1["warp_bgr"])
+    ca = O.correct_alpha(c1["backward"], c1["forward"], wa.copy())
+    assert np.array_equal(ca, c1["corrected"]) and int((ca != wa).sum()) > 0
+    assert np.array_equal(O.create_composite_image(c1["warp_bgr"], c1["bg"], ca), c1["composite"])
+    assert c1["mae"][1] < 0.2 * c1["mae"][0]          # recorded at native resolution by the generator
