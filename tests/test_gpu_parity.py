@@ -724,4 +724,6 @@ def test_config1_window_real_images(vm, capsys):
     ob, oa, st = vm.pipeline.flow_warp_mask(dev(fg[None]), dev(c1["backward"][None]), dev(c1["forward"][None]))
     assert np.array_equal(ob[0].cpu().numpy(), c1["warp_bgr"])
     assert close(oa[0].cpu().numpy(), c1["corrected"], 1e-6)
-    assert int(st[2]) == int((c1["corrected"] != c1["warp_alpha"]).sum()) and int(st[0]) == 0 and int(st[1]) == 0
+    mask = O.occlusion_mask(c1["backward"], c1["forward"])
+    assert np.array_equal(c1["corrected"] == 0, (c1["warp_alpha"] == 0) | mask)
+    assert int(st[2]) == int(mask.sum()) and int(st[0]) == 0 and int(st[1]) == 0
