@@ -726,4 +726,6 @@ def test_config1_window_real_images(vm, capsys):
     assert close(oa[0].cpu().numpy(), c1["corrected"], 1e-6)
     mask = O.occlusion_mask(c1["backward"], c1["forward"])
     assert np.array_equal(c1["corrected"] == 0, (c1["warp_alpha"] == 0) | mask)
-    assert int(st[2]) == int(mask.sum()) and int(st[0]) == 0 and int(st[1]) == 0
+    assert int(st[0]) == 0 and int(st[1]) == 0
+    m_d, st_m = vm.pipeline.occlusion_mask(dev(c1["backward"]), dev(c1["forward"]))
+    assert np.array_equal(m_d.cpu().numpy().astype(bool), mask) and int(st_m[2]) == int(mask.sum())
