@@ -133,8 +133,8 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's banner off stdout: rank 0 prints ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner (env or nccl.conf) off stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     vm = ge.load_package()
     P = vm.pipeline
