@@ -133,9 +133,19 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner (env or nccl.conf) off stdout: ONE JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to stdout when the communicator is created (NCCL_DEBUG=WARN/VERSION on this
+        # pool): send fd 1 to stderr while that happens, so that rank 0's stdout is the ONE JSON line of the contract
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     vm = ge.load_package()
     P = vm.pipeline
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
