@@ -181,3 +181,32 @@ def test_u16_quirk_closed_form_is_the_reference_expression():
     with np.errstate(all="ignore"):
         literal = (((v16 + np.uint16(1)) / 256.) - 1)
     assert np.array_equal(closed, (np.trunc(literal).astype(np.int64) & 0xFF).astype(np.uint8))
+
+
+def test_plan_random_geometries_stay_in_bounds_and_match_oracle(vm):
+    """Descriptor-driven reads must never leave the staged rectangles: 150 random image / background / output
+    sizes (padding on either axis, all crop types, the 2x area branch) through the host planner, the window
+    emulation and the oracle."""
+    rng = np.random.default_rng(2025)
+    for trial in range(150):
+        fh, fw = int(rng.integers(2, 700)), int(rng.integers(2, 700))
+        bh, bw = int(rng.integers(1, 400)), int(rng.integers(1, 400))
+        size = (int(rng.choice([32, 48, 160, 240, 320])), int(rng.choice([32, 48, 160, 240, 320])))
+        fg = rng.integers(0, 256, size=(fh, fw, 4), dtype=np.uint8)
+        bg = rng.integers(0, 256, size=(bh, bw, 3), dtype=np.uint8)
+        np.random.seed(trial)
+        fgv, bgv = vm.loader._plan_sample(fh, fw, bh, bw, size)
+        for img, v in ((fg, fgv), (bg, bgv)):
+            (r0, r1, c0, c1), v2 = vm.loader._touched(v, img.shape[0], img.shape[1])
+            assert 0 <= r0 < r1 <= img.shape[0] and 0 <= c0 < c1 <= img.shape[1]
+            # every canvas cell of the window that holds image data maps inside the staged rectangle
+            rows = np.arange(int(v2["win_h"])) + int(v2["wi"])
+            cols = np.arange(int(v2["win_w"])) + int(v2["wj"])
+            rr = rows[(rows >= int(v2["vi0"])) & (rows < int(v2["vi1"]))] - int(v2["vi0"]) + int(v2["si"])
+            cc = cols[(cols >= int(v2["vj0"])) & (cols < int(v2["vj1"]))] - int(v2["vj0"]) + int(v2["sj"])
+            if rr.size and cc.size:                       # the kernel reads only where row AND column hold image data
+                assert rr.min() >= 0 and rr.max() < r1 - r0 and cc.min() >= 0 and cc.max() < c1 - c0
+        if trial % 5 == 0:
+            ref = LO.simple_sample(fg, bg, size, np.random.RandomState(trial))
+            assert np.array_equal(LO.resize_linear_f64(view_window(fg[..., :3], fgv), size), ref[3])
+            assert np.array_equal(LO.resize_linear_f64(view_window(bg, bgv), size) - LO.VGG_MEAN, ref[1])
