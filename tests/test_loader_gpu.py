@@ -244,3 +244,33 @@ def test_device_batch_equals_file_batch(vm, lgold, tmp_path):
     assert got["warped"] is None
     assert np.array_equal(torch.cat((got["cmp"], got["bg"]), 3).cpu().numpy(), ref[0])
     assert np.array_equal(got["label"].cpu().numpy(), ref[1]) and np.array_equal(got["fg"].cpu().numpy(), ref[2])
+
+
+def test_device_batch_random_geometries_vs_oracle(vm):
+    """40 random foreground / background / output sizes (padding on either axis, every crop type, area and linear
+    resize, mirror) through vm_loader_batch against the oracle with the same np.random seed."""
+    import torch
+    L = vm.loader
+    rng = np.random.default_rng(77)
+    for trial in range(40):
+        fh, fw = int(rng.integers(2, 700)), int(rng.integers(2, 700))
+        bh, bw = int(rng.integers(1, 300)), int(rng.integers(1, 300))
+        size = (int(rng.choice([32, 48, 160, 240, 320])), int(rng.choice([32, 48, 160, 240, 320])))
+        fg = rng.integers(0, 256, size=(fh, fw, 4), dtype=np.uint8)
+        prev = rng.integers(0, 256, size=(fh, fw, 4), dtype=np.uint8)
+        bg = rng.integers(0, 256, size=(bh, bw, 3), dtype=np.uint8)
+        flo = (rng.normal(0, 6, size=(fh, fw, 2))).astype(np.float32)
+        video = trial % 2 == 0
+        np.random.seed(trial)
+        got = L.device_batch([torch.from_numpy(fg).cuda()], [torch.from_numpy(bg).cuda()], size,
+                             prev=[torch.from_numpy(prev).cuda()] if video else None,
+                             flow=[torch.from_numpy(flo).cuda()] if video else None)
+        r = np.random.RandomState(trial)
+        if video:
+            ref = LO.video_sample(fg, bg, prev, flo, size, r)
+            names = ("cmp", "bg", "label", "warped", "fg")
+        else:
+            ref = LO.simple_sample(fg, bg, size, r)
+            names = ("cmp", "bg", "label", "fg")
+        for name, rv in zip(names, ref):
+            close(got[name][0].cpu().numpy(), rv, f"trial {trial} {name} ({fh}x{fw}, bg {bh}x{bw}, out {size})")
