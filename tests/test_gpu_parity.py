@@ -729,3 +729,53 @@ def test_config1_window_real_images(vm, capsys):
     assert int(st[0]) == 0 and int(st[1]) == 0
     m_d, st_m = vm.pipeline.occlusion_mask(dev(c1["backward"]), dev(c1["forward"]))
     assert np.array_equal(m_d.cpu().numpy().astype(bool), mask) and int(st_m[2]) == int(mask.sum())
+
+
+def test_fused_c4_cuda_graph_replay(vm):
+    """The fused C4 entry point is capturable (no allocation, no synchronisation, no host round trip inside the
+    library): a captured launch sequence replayed on new input values gives the eager result, and for small
+    frames - where the four launches are latency bound - the replay is not slower than eager launches."""
+    P = vm.pipeline
+    h, w, n = 120, 160, 4
+    frames, fb, ff, grids, bgs = _lean_case(h, w, n, 5)
+    ctrl, coef = P.solve_grids(grids)
+    fg_d, fb_d, ff_d, bg_d = dev(frames), dev(fb), dev(ff), dev(bgs)
+    plan = P.get_plan((0, 0, h, w), 2, fg_d.device)
+    out = torch.empty((n, h, w, 4), dtype=torch.float32, device="cuda")
+    status = vm._native.new_status()
+    ref, _ = P.flow_tps_composite(fg_d, fb_d, ff_d, bg_d, ctrl, coef, plan=plan)          # also warms the library up
+    scratch = torch.empty(int(vm._native.load().vm_fused_scratch_bytes(n, h, w)) + 512, dtype=torch.uint8, device="cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        P.flow_tps_composite(fg_d, fb_d, ff_d, bg_d, ctrl, coef, plan=plan, out=out, scratch=scratch, status=status)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        P.flow_tps_composite(fg_d, fb_d, ff_d, bg_d, ctrl, coef, plan=plan, out=out, scratch=scratch, status=status)
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    # new values in the captured buffers: frames rolled by one, result must follow
+    fg_d.copy_(torch.roll(fg_d, 1, dims=0)); fb_d.copy_(torch.roll(fb_d, 1, dims=0)); ff_d.copy_(torch.roll(ff_d, 1, dims=0))
+    bg_d.copy_(torch.roll(bg_d, 1, dims=0)); ctrl.copy_(torch.roll(ctrl, 1, dims=0)); coef.copy_(torch.roll(coef, 1, dims=0))
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, torch.roll(ref, 1, dims=0))
+
+    def timed(fn, iters=200):
+        for _ in range(20):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+    t_eager = timed(lambda: P.flow_tps_composite(fg_d, fb_d, ff_d, bg_d, ctrl, coef, plan=plan, out=out, scratch=scratch, status=status))
+    t_graph = timed(g.replay)
+    print(f"C4 {n} x {h}x{w}: eager {t_eager * 1e3:.1f} us per call, graph replay {t_graph * 1e3:.1f} us")
+    assert t_graph <= 1.25 * t_eager
