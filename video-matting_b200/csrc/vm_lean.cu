@@ -1255,7 +1255,7 @@ int vm_lean_set_option(const char *key, int value) {
     if (!strcmp(key, "lean_persist") && value >= 0 && value <= 1) { g_vl_persist = value; return VM_OK; }
     if (!strcmp(key, "lean_sub") && value >= 0 && value <= 4096) { g_vl_sub = value; return VM_OK; }
     if (!strcmp(key, "lean_box_cap") && value >= 0 && value <= 16384) { g_vl_box_cap = value; return VM_OK; }
-    if (!strcmp(key, "lean_minb") && (value == 2 || value == 3 || value == 4 || value == 6 || value == 8)) { g_vl_minb = value; return VM_OK; }
+    if (!strcmp(key, "lean_minb") && (value >= 2 && value <= 6 || value == 8)) { g_vl_minb = value; return VM_OK; }
     if (!strcmp(key, "lean_fine_rows") && value >= 1 && value <= 256) { g_vl_fine_rows = value; return VM_OK; }
     if (!strcmp(key, "lean_floors") && (value == 0 || value == 1)) { g_vl_floors = value; return VM_OK; }
     return VM_ERR_ARG;
@@ -1439,8 +1439,8 @@ int vm_lean_launch(int mode, const uint8_t *fg, const float *backward, const flo
                 if (mode != 0) VL_FINE_P(1); else VL_FINE_P(0);
 #undef VL_FINE_P
             }
-            else if (mode != 0) { if (g_vl_minb == 8) VL_FINE(1, 8); else if (g_vl_minb == 6) VL_FINE(1, 6); else if (g_vl_minb == 4) VL_FINE(1, 4); else if (g_vl_minb == 3) VL_FINE(1, 3); else VL_FINE(1, 2); }
-            else           { if (g_vl_minb == 8) VL_FINE(0, 8); else if (g_vl_minb == 6) VL_FINE(0, 6); else if (g_vl_minb == 4) VL_FINE(0, 4); else if (g_vl_minb == 3) VL_FINE(0, 3); else VL_FINE(0, 2); }
+            else if (mode != 0) { if (g_vl_minb == 8) VL_FINE(1, 8); else if (g_vl_minb == 6) VL_FINE(1, 6); else if (g_vl_minb == 5) VL_FINE(1, 5); else if (g_vl_minb == 4) VL_FINE(1, 4); else if (g_vl_minb == 3) VL_FINE(1, 3); else VL_FINE(1, 2); }
+            else           { if (g_vl_minb == 8) VL_FINE(0, 8); else if (g_vl_minb == 6) VL_FINE(0, 6); else if (g_vl_minb == 5) VL_FINE(0, 5); else if (g_vl_minb == 4) VL_FINE(0, 4); else if (g_vl_minb == 3) VL_FINE(0, 3); else VL_FINE(0, 2); }
 #undef VL_FINE
             g_vl_launches += 1;
             rc = vm_check_launch(what);
