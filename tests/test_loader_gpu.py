@@ -274,3 +274,40 @@ def test_device_batch_random_geometries_vs_oracle(vm):
             names = ("cmp", "bg", "label", "fg")
         for name, rv in zip(names, ref):
             close(got[name][0].cpu().numpy(), rv, f"trial {trial} {name} ({fh}x{fw}, bg {bh}x{bw}, out {size})")
+
+
+def test_generate_trimaps_and_create_list(vm, tmp_path):
+    D = vm.data
+    src, dst = tmp_path / "fg", tmp_path / "trimap"
+    os.makedirs(src); os.makedirs(dst)
+    frames = {"a.png": O.synth_frame(1, 40, 56), "b.png": O.synth_frame(2, 40, 56), "c.png": O.synth_frame(3, 33, 47)}
+    for name, fr in frames.items():
+        assert cv2.imwrite(str(src / name), fr)
+    assert cv2.imwrite(str(dst / "b.png"), np.zeros((40, 56), np.uint8))          # existing targets are skipped (data.py:80-81)
+    D.generate_trimaps(str(src), str(dst))
+    for name, fr in frames.items():
+        got = cv2.imread(str(dst / name), cv2.IMREAD_UNCHANGED)
+        if name == "b.png":
+            assert not got.any()
+        else:
+            assert np.array_equal(got, LO.trimap_from_matte(fr[..., 3] / 255.))
+    # create_list: 100 random backgrounds per foreground, one np.random.randint(size=100) call each (data.py:87-107)
+    root = tmp_path / "root"
+    for d in (root / "fg" / "S", root / "trimap" / "S", root / "VOC_bg"):
+        os.makedirs(d)
+    for n in ("x.png", "y.png"):
+        (root / "fg" / "S" / n).write_bytes(b"0"); (root / "trimap" / "S" / n).write_bytes(b"0")
+    for n in ("v0.jpg", "v1.jpg", "v2.jpg"):
+        (root / "VOC_bg" / n).write_bytes(b"0")
+    np.random.seed(5)
+    D.create_list(str(root), str(tmp_path / "list.txt"), "S")
+    lines = (tmp_path / "list.txt").read_text().splitlines()
+    assert len(lines) == 200
+    np.random.seed(5)
+    voc = os.listdir(root / "VOC_bg")
+    fgs = os.listdir(root / "fg" / "S")
+    ids = np.random.randint(0, len(voc), size=100)
+    assert lines[0] == "{} {} {}".format(os.path.join("fg", "S", fgs[0]), os.path.join("trimap", "S", fgs[0]),
+                                         os.path.join("VOC_bg", voc[ids[0]]))
+    entries = vm.loader.get_file_list(str(root), str(tmp_path / "list.txt"))
+    assert len(entries) == 200 and entries[0][0] == os.path.join(str(root), "fg", "S", fgs[0])
