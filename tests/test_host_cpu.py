@@ -138,3 +138,23 @@ def test_clip_sharding_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_batched_augment_plan_is_the_sequential_plan(vm):
+    """One random_sample block for a clip == the reference's 40 uniform() calls per frame, value for value, and
+    leaves np.random in the same state."""
+    A = vm.augmentation
+    for (h, w), n in (((1080, 1920), 9), ((61, 83), 4), ((512, 512), 2)):
+        stats = np.stack([np.array([1000 + 37 * k, (1000 + 37 * k) * (h // 3), (1000 + 37 * k) * (w // 2 + k)]) for k in range(n)])
+        np.random.seed(99)
+        seq = A._augment_plan(stats, h, w, before_frame=lambda k: None)        # a hook forces the frame-by-frame path
+        after_seq = np.random.random_sample()
+        np.random.seed(99)
+        bat = A._augment_plan(stats, h, w)
+        assert np.random.random_sample() == after_seq
+        for name, x, y in zip(("bg params", "fg params", "luts"), seq[:3], bat[:3]):
+            assert x.tobytes() == y.tobytes(), name
+        for (g0, d0), (g1, d1) in zip(seq[3], bat[3]):
+            assert np.array_equal(g0, g1) and np.array_equal(d0, d1)
+    with pytest.raises(ValueError):
+        A._augment_plan(np.array([[5, 1, 1], [0, 0, 0]]), 64, 64)

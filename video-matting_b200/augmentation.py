@@ -152,6 +152,8 @@ def _augment_plan(stats, h, w, before_frame=None):
     par_bg = np.zeros(n, dtype=AUG_PARAMS); par_fg = np.zeros(n, dtype=AUG_PARAMS)
     luts = np.zeros((n, 256), dtype=np.uint8)
     grids = []
+    if before_frame is None and n > 1:
+        return _augment_plan_batched(stats, h, w)
     for k in range(n):
         if before_frame is not None:
             before_frame(k)
@@ -170,6 +172,53 @@ def _augment_plan(stats, h, w, before_frame=None):
         par_bg[k] = (_rotation_matrix((w // 2, h // 2), 0., scale_bg).reshape(6), tu_bg, tv_bg)
         par_fg[k] = (_rotation_matrix(center, rot_fg, scale_fg).reshape(6), tu_fg, tv_fg)
         luts[k] = illumination_lut(a, b, c)
+    return par_bg, par_fg, luts, grids
+
+
+def _augment_plan_batched(stats, h, w, n_grid=5):
+    """_augment_plan for a whole clip with ONE call into the generator: the legacy ``RandomState.uniform(lo, hi)``
+    is ``lo + (hi - lo) * random_sample()``, one double per draw, so the (n, 40) block of ``random_sample`` holds
+    exactly the doubles the frame-by-frame calls would consume, in their order, and the same expression gives the
+    same values (checked bit for bit against the sequential plan in tests/test_host_cpu.py)."""
+    n = len(stats)
+    bt, br, bs = 0.05, 10, 0.15
+    bound = min(w, h) * 0.05
+    rows = (h / (n_grid - 1)) * np.arange(n_grid)
+    cols = (w / (n_grid - 1)) * np.arange(n_grid)
+    grid = np.transpose([np.repeat(rows, n_grid), np.tile(cols, n_grid)])
+    need = np.stack([(grid[:, 1] > 0.) & (grid[:, 1] < w), (grid[:, 0] > 0.) & (grid[:, 0] < h)], axis=1)
+    ng = int(need.sum())
+    per = 3 + ng + 7
+    u = np.random.random_sample((n, per))
+    uni = lambda lo, hi, x: lo + (hi - lo) * x
+    cnt = stats[:, 0].astype(np.int64)
+    if (cnt == 0).any():
+        raise ValueError("cannot convert float NaN to integer")           # int(np.mean([])) in fg_center
+    fg_size = np.sqrt(cnt)
+    tu_bg = np.trunc(uni(-w * bt, w * bt, u[:, 0])).astype(np.int64)
+    tv_bg = np.trunc(uni(-h * bt, h * bt, u[:, 1])).astype(np.int64)
+    scale_bg = uni(1., 1. + bs, u[:, 2])
+    draws = uni(-bound, bound, u[:, 3:3 + ng])
+    o = 3 + ng
+    tu_fg = np.trunc(uni(-fg_size * bt, fg_size * bt, u[:, o])).astype(np.int64)
+    tv_fg = np.trunc(uni(-fg_size * bt, fg_size * bt, u[:, o + 1])).astype(np.int64)
+    rot_fg = uni(-br, br, u[:, o + 2])
+    scale_fg = uni(1., 1. + bs, u[:, o + 3])
+    a, b, c = uni(0.95, 1.05, u[:, o + 4]), uni(0.7, 1.3, u[:, o + 5]), uni(-0.07, 0.07, u[:, o + 6])
+    par_bg = np.zeros(n, dtype=AUG_PARAMS); par_fg = np.zeros(n, dtype=AUG_PARAMS)
+    luts = np.zeros((n, 256), dtype=np.uint8)
+    grids = []
+    for k in range(n):
+        flat = np.zeros(need.shape)
+        flat[need] = draws[k]
+        moved = grid.copy()
+        moved[:, 1] += flat[:, 0]
+        moved[:, 0] += flat[:, 1]
+        grids.append((grid, moved))
+        center = (int(int(stats[k, 2]) / int(cnt[k])), int(int(stats[k, 1]) / int(cnt[k])))
+        par_bg[k] = (_rotation_matrix((w // 2, h // 2), 0., scale_bg[k]).reshape(6), tu_bg[k], tv_bg[k])
+        par_fg[k] = (_rotation_matrix(center, rot_fg[k], scale_fg[k]).reshape(6), tu_fg[k], tv_fg[k])
+        luts[k] = illumination_lut(a[k], b[k], c[k])
     return par_bg, par_fg, luts, grids
 
 
