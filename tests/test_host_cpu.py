@@ -158,3 +158,22 @@ def test_batched_augment_plan_is_the_sequential_plan(vm):
             assert np.array_equal(g0, g1) and np.array_equal(d0, d1)
     with pytest.raises(ValueError):
         A._augment_plan(np.array([[5, 1, 1], [0, 0, 0]]), 64, 64)
+
+
+def test_stacked_kernel_matrices_bit_equal_to_per_frame(vm):
+    P, A = vm.pipeline, vm.augmentation
+    np.random.seed(3)
+    for (h, w), n in (((1080, 1920), 5), ((2160, 3840), 5), ((512, 512), 4), ((61, 83), 3)):
+        pts = np.stack([A.deform_grid(h, w, n)[1] for _ in range(33)])
+        L = P._tps_kernel_matrices(pts)
+        ref = np.stack([P._tps_kernel_matrix(p) for p in pts])
+        assert L.tobytes() == ref.tobytes()
+    grids = [A.deform_grid(1080, 1920) for _ in range(40)]
+    P._stacked_kernel_ok[0] = None
+    a = P._solve_chunk(grids[:16])            # first stack of the process: checked against the per-frame build
+    assert P._stacked_kernel_ok[0] is True
+    b = P._solve_chunk(grids[:16])
+    P._stacked_kernel_ok[0] = False
+    c = P._solve_chunk(grids[:16])
+    P._stacked_kernel_ok[0] = True
+    assert a.tobytes() == b.tobytes() == c.tobytes()

@@ -259,10 +259,44 @@ def tps_warp(src, coarse, plan, out_hw=None, status=None):
     return dst
 
 
+_stacked_kernel_ok = [None]      # None: not checked yet in this process
+
+
+def _tps_kernel_matrices(points):
+    """_tps_kernel_matrix for a stack (m, N, 2) of control-point sets with the same element-wise expressions.
+    numpy's sqrt / log loops are expected to give the same value for an element wherever it sits in an array; that
+    is verified once per process on the first stack (bit for bit against the per-frame function), and the per-frame
+    function is used from then on if it ever fails."""
+    pts = np.asarray(points, dtype=np.float64)
+    m, n = pts.shape[:2]
+    d0 = pts[:, :, None, 0] - pts[:, None, :, 0]
+    d1 = pts[:, :, None, 1] - pts[:, None, :, 1]
+    r = np.sqrt(d0 ** 2 + d1 ** 2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        K = (r ** 2) * np.where(r < 1e-100, 0, np.log(r))
+    L = np.zeros((m, n + 3, n + 3))
+    L[:, :n, :n] = K
+    L[:, :n, n] = 1.0
+    L[:, :n, n + 1:] = pts
+    L[:, n:, :n] = np.transpose(L[:, :n, n:], (0, 2, 1))
+    return L
+
+
+def _kernel_stack(chunk):
+    if _stacked_kernel_ok[0] is not False:
+        L = _tps_kernel_matrices(np.stack([np.asarray(d, dtype=np.float64) for (_, d) in chunk]))
+        if _stacked_kernel_ok[0] is None:
+            ref = np.stack([_tps_kernel_matrix(d) for (_, d) in chunk])
+            _stacked_kernel_ok[0] = bool(L.tobytes() == ref.tobytes())
+            return ref
+        return L
+    return np.stack([_tps_kernel_matrix(d) for (_, d) in chunk])
+
+
 def _solve_chunk(chunk):
     """np.dot(np.linalg.pinv(L), V) for a list of (grid, deformed grid) pairs: numpy's stacked pinv runs
     the same LAPACK call per matrix as the reference's per-frame call (bit-identical, checked in the tests)."""
-    L = np.stack([_tps_kernel_matrix(d) for (_, d) in chunk])
+    L = _kernel_stack(chunk)
     V = np.zeros((len(chunk), L.shape[1], 2))
     for k, (g, _) in enumerate(chunk):
         g = np.asarray(g, dtype=np.float64)
