@@ -630,6 +630,9 @@ def test_augment_clip_matches_sequential_augment(vm, shape):
         assert np.array_equal(nbg[k], rbg)
         assert np.count_nonzero(np.any(nfg[k] != rfg, axis=-1)) <= 2
         assert np.allclose(nal[k], ral, rtol=RTOL, atol=1e-6)
+    np.random.seed(2024)
+    again = A.augment_clip(frames, bgs, stats=A.alpha_stats(frames))          # precomputed statistics: same result
+    assert all(np.array_equal(x, y) for x, y in zip(again, (nfg, nbg, nal)))
     # float64 alpha: the reference's dtype and operation order (scipy map_coordinates, then cv2.warpAffine on
     # float64) - equal to the drop-in's float64 alpha up to the ~1e-13 px difference of the transform
     np.random.seed(2024)

@@ -264,7 +264,16 @@ def _augment_run(fg_d, bg_d, plan, alpha_dtype=torch.float32):
     return new_fg, new_bg, new_alpha
 
 
-def augment_clip(fg_bgra, bg, alpha_dtype=torch.float32):
+def alpha_stats(fg_bgra):
+    """(n, 3) int64 {count(alpha != 0), sum(rows), sum(cols)} of a BGRA clip - what object_size / fg_center need
+    (augmentation.py:10-21).  Pass it to ``augment_clip(..., stats=...)`` when the same foregrounds are augmented
+    repeatedly: the call then has no device-to-host synchronisation and its host work overlaps the kernels of the
+    previous call."""
+    fg_d, _ = N.to_device(fg_bgra)
+    return _alpha_stats_clip(fg_d.contiguous())
+
+
+def augment_clip(fg_bgra, bg, alpha_dtype=torch.float32, stats=None):
     """augment() for a whole clip in a handful of launches (BASELINE config 5).
 
     ``fg_bgra`` (n, H, W, 4) uint8 BGRA with alpha = A/255 (what reader.read_fg_img returns, reference
@@ -273,7 +282,8 @@ def augment_clip(fg_bgra, bg, alpha_dtype=torch.float32):
     stream is consumed in exactly that order (40 draws per frame, reference augmentation.py:102-135), the
     TPS systems are solved on the host with numpy's pinv (reference tps.py:119).  Returns
     (new_fg (n,H,W,3) uint8, new_bg (n,H,W,3) uint8, new_alpha (n,H,W) float32) of the input kind;
-    ``alpha_dtype=torch.float64`` returns the alpha in float64 as the reference does (same operation order)."""
+    ``alpha_dtype=torch.float64`` returns the alpha in float64 as the reference does (same operation order);
+    ``stats=alpha_stats(fg_bgra)`` skips the per-call alpha reduction and its host synchronisation."""
     fg_d, kind = N.to_device(fg_bgra)
     bg_d, _ = N.to_device(bg)
     assert fg_d.dtype == torch.uint8 and fg_d.dim() == 4 and fg_d.shape[3] == 4, "fg must be (n, H, W, 4) uint8 BGRA"
@@ -285,7 +295,7 @@ def augment_clip(fg_bgra, bg, alpha_dtype=torch.float32):
         empty = (torch.empty((0, h, w, 3), dtype=torch.uint8, device=dev), torch.empty((0, h, w, 3), dtype=torch.uint8, device=dev),
                  torch.empty((0, h, w), dtype=alpha_dtype, device=dev))
         return tuple(N.from_device(t, kind) for t in empty)
-    plan = _augment_plan(_alpha_stats_clip(fg_d), h, w)
+    plan = _augment_plan(_alpha_stats_clip(fg_d) if stats is None else np.asarray(stats), h, w)
     return tuple(N.from_device(t, kind) for t in _augment_run(fg_d, bg_d, plan, alpha_dtype))
 
 
