@@ -8,7 +8,11 @@ over one clip per rank; clips are independent, so ranks share nothing (weak scal
 collective on the data path; torch.distributed only for the barrier and the max-over-ranks).
 
     python bench.py --gpus N --steps K --warmup W            # ours
-    python bench.py --impl reference --gpus N ...            # CPU restatement (oracle) arm
+    python bench.py --impl reference --gpus N ...            # the reference's own CPU implementation
+
+Besides the contract's keys the line carries: `value_with_solve` (fresh TPS grids every step, solved on the
+host by a worker pool while the previous step's kernels run), `configs` (the other BASELINE.json configs, short
+device-timed runs), and in `e2e` the copy-only ceiling of the same byte volume.
 """
 import argparse
 import json
@@ -22,18 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 H, W, CLIP, NCTRL = 1080, 1920, 64, 5
-BYTES_PER_PX = {"c4": 39, "c2": 27}
-# dram__bytes_read.sum + dram__bytes_write.sum of the four kernels of one 64-frame launch, from the ncu
-# --set full capture summarised in profiles/ (None until measured for the current kernels)
-TRAFFIC_PER_LAUNCH = 8486719488
-TRAFFIC_SOURCE = "profiles/r01_lean_traffic.txt"
-# the same capture per kernel (spline, tile boxes, flow stage, resampling), bytes per 64-frame launch
-STAGE_TRAFFIC = [600568960, 133293312, 3683009920, 4069848192]
-# what binds each stage: the spline stage has no HBM traffic to speak of, it is bound by the
-# float64 pipe - 10.85 DP instructions per (coarse point, control point) evaluation (ncu instruction
-# histogram), one DP instruction per 2 cycles and SM sub-partition
-STAGE_BOUND = ["fp64 pipe", "latency", "hbm", "hbm + instruction issue"]
-DP_PER_EVAL = 10.85
+BYTES_PER_PX = {"c4": 39, "c3": 23, "c2": 27, "c5": 17}
 METRIC = "1080p frames/s (warp+TPS+composite)"
 WORKLOAD = ("C4 1080p: flow warp + fwd/bwd occlusion mask + TPS (25 control points, fresh grid per frame) "
             "+ composite, BGRA uint8 in, float32x4 out, clip of 64 frames per GPU per step")
@@ -45,6 +38,15 @@ def measured_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic():
+    """DRAM bytes of the kernels of one 64-frame launch from the committed ncu --set full summary."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 # ------------------------------------------------------------------------- clocks sampling
@@ -87,8 +89,61 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # "under load" = samples in the upper half of the observed range (idle samples before/after excluded)
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------- host placement
+
+def _cpulist(text):
+    out = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        out.extend(range(int(a), int(b or a) + 1))
+    return out
+
+
+def _gpu_numa_node(torch, idx):
+    try:
+        pr = torch.cuda.get_device_properties(idx)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            return int(f.read())
+    except Exception:
+        return -1
+
+
+def place_rank(torch, local, world):
+    """Pin this rank to its own slice of the host cores - those of its GPU's NUMA node when sysfs tells, split
+    among the ranks whose GPUs sit on the same node - so that N ranks do not oversubscribe one another and
+    pinned buffers are allocated NUMA-locally.  Returns a description for the bench line."""
+    try:
+        avail = sorted(os.sched_getaffinity(0))
+    except Exception:
+        return {"cores": None}
+    nodes = [_gpu_numa_node(torch, g) for g in range(world)] if world > 1 else [_gpu_numa_node(torch, local)]
+    node = nodes[local] if world > 1 else nodes[0]
+    cores = avail
+    if node >= 0:
+        try:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                local_cores = [c for c in _cpulist(f.read()) if c in avail]
+            if local_cores:
+                cores = local_cores
+        except Exception:
+            node = -1
+    if world > 1:
+        peers = [g for g in range(world) if nodes[g] == node] if node >= 0 else list(range(world))
+        k, share = peers.index(local), len(peers)
+        per = max(1, len(cores) // share)
+        mine = cores[k * per:(k + 1) * per] or cores
+        try:
+            os.sched_setaffinity(0, mine)
+            cores = mine
+        except Exception:
+            pass
+    return {"cores": len(cores), "numa_node": node}
 
 
 # ------------------------------------------------------------------------- synthetic inputs
@@ -114,8 +169,19 @@ def make_clip(torch, seed, n, h, w, device):
     return fg.contiguous(), fb.float().contiguous(), ff.float().contiguous(), bg.contiguous()
 
 
-def make_grids(O, seed, n, h, w):
-    return [O.synth_grids(seed * 1000 + k, h, w, NCTRL) for k in range(n)]
+def make_grids(vm, seed, n, h, w, n_ctrl=NCTRL):
+    """n (regular grid, deformed grid) pairs: np.random.seed(s); augmentation.deform_grid(h, w, n_ctrl) -
+    the reference's own generator (augmentation.py:24-41, the product's host copy of it), SURVEY 8d."""
+    import numpy as np
+    state = np.random.get_state()
+    try:
+        out = []
+        for k in range(n):
+            np.random.seed(seed * 1000 + k)
+            out.append(vm.augmentation.deform_grid(h, w, n_ctrl))
+        return out
+    finally:
+        np.random.set_state(state)
 
 
 # ------------------------------------------------------------------------------- our arm
@@ -130,6 +196,8 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device - this path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    placement = place_rank(torch, local, world)
+    torch.set_num_threads(1)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -147,33 +215,9 @@ def run_ours(args):
             os.dup2(saved, 1)
             os.close(saved)
     vm = ge.load_package()
-    P = vm.pipeline
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import vm_oracle as O       # input-grid generator + cpu_baseline checker leg only
-
-    fg, fb, ff, bg = make_clip(torch, 1234 + rank, CLIP, H, W, dev)
-    grids = make_grids(O, rank + 1, CLIP, H, W)
-    ctrl, coef = P.solve_grids(grids, dev)
-    plan = P.get_plan((0, 0, H, W), 2, dev)
-    out = torch.empty((CLIP, H, W, 4), dtype=torch.float32, device=dev)
-    status = vm._native.new_status(dev)
-    lib = vm._native.load()
-    scratch = torch.empty(lib.vm_fused_scratch_bytes(CLIP, H, W), dtype=torch.uint8, device=dev)
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    marks = []
-
-    def step(timed):
-        e1, e2 = ev(), ev()
-        e1.record()
-        vm._native.check(lib.vm_flow_tps_composite_bgra(
-            fg.data_ptr(), fb.data_ptr(), ff.data_ptr(), bg.data_ptr(), bg.shape[0], ctrl.data_ptr(),
-            coef.data_ptr(), NCTRL * NCTRL, plan.nx, plan.ny, plan.step_x, plan.step_y, plan.rows.data_ptr(),
-            plan.cols.data_ptr(), CLIP, H, W, out.data_ptr(), scratch.data_ptr(), status.data_ptr(),
-            torch.cuda.current_stream().cuda_stream))
-        e2.record()
-        if timed:
-            marks.append((e1, e2))
+    P, Nt = vm.pipeline, vm._native
+    lib = Nt.load()
+    peak, peak_src = measured_peak()
 
     def barrier():
         torch.cuda.synchronize()
@@ -181,20 +225,46 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([float(x)], device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    solve_workers = max(1, min(8, (placement.get("cores") or os.cpu_count() or 2) - 1))
+    pool = P.SolverPool(solve_workers)
+
+    fg, fb, ff, bg = make_clip(torch, 1234 + rank, CLIP, H, W, dev)
+    n_sets = 4
+    grid_sets = [make_grids(vm, 10 * rank + 1 + s, CLIP, H, W) for s in range(n_sets)]
+    grids = grid_sets[0]
+    ctrl, coef = P.solve_grids(grids, dev, pool=pool)
+    plan = P.get_plan((0, 0, H, W), 2, dev)
+    out = torch.empty((CLIP, H, W, 4), dtype=torch.float32, device=dev)
+    status = Nt.new_status(dev)
+    scratch = torch.empty(lib.vm_fused_scratch_bytes(CLIP, H, W), dtype=torch.uint8, device=dev)
+
+    def launch(c, k):
+        Nt.check(lib.vm_flow_tps_composite_bgra(
+            fg.data_ptr(), fb.data_ptr(), ff.data_ptr(), bg.data_ptr(), bg.shape[0], c.data_ptr(),
+            k.data_ptr(), NCTRL * NCTRL, plan.nx, plan.ny, plan.step_x, plan.step_y, plan.rows.data_ptr(),
+            plan.cols.data_ptr(), CLIP, H, W, out.data_ptr(), scratch.data_ptr(), status.data_ptr(),
+            torch.cuda.current_stream().cuda_stream))
+
+    marks = []
+
+    def step(timed):
+        e1, e2 = ev(), ev()
+        e1.record()
+        launch(ctrl, coef)
+        e2.record()
+        if timed:
+            marks.append((e1, e2))
+
     for _ in range(args.warmup):
         step(False)
-    # per-stage durations of one (untimed) step, CUDA events recorded inside the library on the launch stream
-    import ctypes
-    vm._native.set_option("lean_timing", 1)
-    stage_ms = []
-    for _ in range(3):
-        step(False)
-        torch.cuda.synchronize()
-        buf = (ctypes.c_float * 4)()
-        vm._native.check(lib.vm_lean_stage_ms(ctypes.cast(buf, ctypes.c_void_p)))
-        stage_ms.append(list(buf))
-    vm._native.set_option("lean_timing", 0)
-    stage_ms = [statistics.median(col) for col in zip(*stage_ms)]
+    stage_info = kernel_stages(vm, lib, step, torch)
     launches0 = lib.vm_lean_launch_count()
     sampler = ClockSampler(str(torch.cuda.get_device_properties(local).uuid)) if rank == 0 else None
     barrier()
@@ -207,56 +277,88 @@ def run_ours(args):
     t1.record()
     barrier()
     launches = int(lib.vm_lean_launch_count() - launches0)
-    ms = t0.elapsed_time(t1)
-    tms = torch.tensor([ms], device=dev)
-    if dist is not None:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_total = float(tms.item())
+    ms_total = max_over_ranks(t0.elapsed_time(t1))
     frames = world * CLIP * args.steps
     value = frames / (ms_total / 1e3)
     k_ms = statistics.mean(a.elapsed_time(b) for (a, b) in marks)
+    ref_out = out.clone() if CLIP * H * W * 16 < 3e9 else None
+
+    # ---- the same loop with FRESH grids every step: the host solve of step s+1 (worker pool) overlaps the
+    # kernels of step s; coefficients go up through pinned memory on the launch stream -----------------------
+    ws_steps = max(4, min(args.steps, 40))
+    pin = [(torch.empty((CLIP, NCTRL * NCTRL, 2), dtype=torch.float64).pin_memory(),
+            torch.empty((CLIP, NCTRL * NCTRL + 3, 2), dtype=torch.float64).pin_memory()) for _ in range(2)]
+    dbuf = [(torch.empty_like(ctrl), torch.empty_like(coef)) for _ in range(2)]
+    consumed = [ev(), ev()]
+    barrier()
+    w0 = time.perf_counter()
+    s0, s1 = ev(), ev()
+    handle = pool.submit(grid_sets[0])
+    solve_wait = 0.0
+    s0.record()
+    for s in range(ws_steps):
+        tw = time.perf_counter()
+        c_h, k_h = pool.collect(handle)
+        solve_wait += time.perf_counter() - tw
+        if s + 1 < ws_steps:
+            handle = pool.submit(grid_sets[(s + 1) % n_sets])
+        b = s & 1
+        if s >= 2:
+            consumed[b].synchronize()                      # the pinned / device pair of step s-2 is free again
+        pin[b][0].copy_(torch.from_numpy(c_h)); pin[b][1].copy_(torch.from_numpy(k_h))
+        dbuf[b][0].copy_(pin[b][0], non_blocking=True); dbuf[b][1].copy_(pin[b][1], non_blocking=True)
+        launch(dbuf[b][0], dbuf[b][1])
+        consumed[b].record()
+    s1.record()
+    barrier()
+    ws_ms = max_over_ranks(s0.elapsed_time(s1))
+    ws_wall = max_over_ranks(time.perf_counter() - w0)
+    value_with_solve = world * CLIP * ws_steps / (max(ws_ms / 1e3, 0.0) or ws_wall)
 
     # ---- e2e: same clip from pinned host memory through the public host API ----------------
     e2e_steps = max(1, min(args.steps, 3))
     host = [t.cpu().pin_memory() for t in (fg, fb, ff)]
     bg_h = bg[torch.arange(CLIP) % bg.shape[0]].cpu().pin_memory()
     out_h = torch.empty((CLIP, H, W, 4), dtype=torch.float32).pin_memory()
-    P.flow_tps_composite_host(host[0], host[1], host[2], bg_h, grids, out=out_h)      # warm-up
+    P.flow_tps_composite_host(host[0], host[1], host[2], bg_h, grids, out=out_h, pool=pool)      # warm-up
     barrier()
     w0 = time.perf_counter()
     for _ in range(e2e_steps):
-        P.flow_tps_composite_host(host[0], host[1], host[2], bg_h, grids, out=out_h)
+        P.flow_tps_composite_host(host[0], host[1], host[2], bg_h, grids, out=out_h, pool=pool)
     barrier()
-    e2e_s = time.perf_counter() - w0
+    e2e_s = max_over_ranks(time.perf_counter() - w0)
     clocks = sampler.stop() if sampler else None     # sampled over the device-timed steps and the end-to-end steps
-    te = torch.tensor([e2e_s], device=dev)
-    if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
     runner = next(iter(P._runners.values()))
-    e2e = {"value": world * CLIP * e2e_steps / float(te.item()), "unit": "frames/s",
-           "h2d_bytes_per_step": int(runner.h2d_bytes), "d2h_bytes_per_step": int(runner.d2h_bytes),
-           "steps": e2e_steps, "note": "pinned host clip -> H2D -> kernels -> D2H float32x4, TPS solve on host included"}
-    same = bool(torch.equal(out_h.to(dev), out))
+    h2d, d2h, solve_s = int(runner.h2d_bytes), int(runner.d2h_bytes), float(runner.solve_s)
+    same = bool(torch.equal(out_h.to(dev), ref_out)) if ref_out is not None else None
+    # copy-only ceiling: the same H2D / D2H volume through the same three streams, no solve, no kernels
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        runner.run(host[0], host[1], host[2], bg_h, grids, out_h, kernels=False)
+        torch.cuda.current_stream().synchronize()
+    barrier()
+    copy_s = max_over_ranks(time.perf_counter() - w0)
+    e2e = {"value": world * CLIP * e2e_steps / e2e_s, "unit": "frames/s",
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+           "copy_only_value": world * CLIP * e2e_steps / copy_s,
+           "frac_of_copy_only": copy_s / e2e_s,
+           "h2d_GBps_per_rank": h2d * e2e_steps / e2e_s / 1e9, "d2h_GBps_per_rank": d2h * e2e_steps / e2e_s / 1e9,
+           "copy_only_h2d_GBps_per_rank": h2d * e2e_steps / copy_s / 1e9,
+           "solve_ms_per_step": 1e3 * solve_s, "solve_workers": solve_workers, "host_placement": placement,
+           "note": "pinned host clip -> H2D -> kernels -> D2H float32x4, TPS solve on host (worker pool) included; "
+                   "copy_only_value = the same copies without solve and kernels, same streams, all ranks at once"}
+    del host, bg_h, out_h, ref_out
+    cfgs = bench_configs(vm, torch, dev, rank, world, barrier, max_over_ranks, peak, pool)
+    pool.close()
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-    peak, peak_src = measured_peak()
     alg = BYTES_PER_PX["c4"] * H * W * CLIP
     ach = alg / (k_ms / 1e3) / 1e9
-    names = ["k_lean_coarse<25> (TPS on the coarse grid, float64)", "k_lean_boxes<1> (source box per tile)",
-             "k_flow_warp_mask_bgra<1,2> (flow warp + consistency mask)", "k_lean_fine<1,4> (resampling + composite)"]
-    # algorithmic bytes each stage moves per pixel (SURVEY 8d layouts; intermediates are not algorithmic)
-    stage_bpp = [0, 0, 8 + 8 + 4, 3 + 16]
-    stages = [{"kernel": nm, "ms": ms_k, "share_of_step": ms_k / sum(stage_ms), "bound": bound,
-               "algorithmic_GBps": (bpp * H * W * CLIP / (ms_k / 1e3) / 1e9) if bpp else None,
-               "dram_GBps": tr / (ms_k / 1e3) / 1e9, "dram_frac_of_peak": tr / (ms_k / 1e3) / 1e9 / peak}
-              for nm, ms_k, bpp, tr, bound in zip(names, stage_ms, stage_bpp, STAGE_TRAFFIC, STAGE_BOUND)]
-    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
-    sm_hz = (((clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)) * 1e6
-    evals = CLIP * (H // 2) * (W // 2) * NCTRL * NCTRL
-    stages[0]["fp64_pipe_frac"] = (evals / 32 * DP_PER_EVAL) / ((stage_ms[0] / 1e3) * sm_count * 4 * 0.5 * sm_hz)
+    traffic = load_traffic()
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -264,63 +366,260 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "height": H, "width": W, "frames_per_step_per_gpu": CLIP,
                    "control_points": NCTRL * NCTRL, "sharding": f"clip-sharded replicas x{world}, no collective",
                    "l2": "inputs+outputs 4.8 GB per step >> 126 MB L2 (no flush needed)"},
-        "roofline": {"bound": "hbm",
-                     "kernel": "vm_flow_tps_composite_bgra = k_lean_coarse + k_lean_boxes + k_flow_warp_mask_bgra + "
-                               "k_lean_fine, timed as one unit (39 B/px is defined for the whole pipeline); the "
-                               "dominant kernel is k_lean_fine, see stages",
-                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": TRAFFIC_PER_LAUNCH,
-                     "traffic_source": TRAFFIC_SOURCE,
+        "value_with_solve": value_with_solve,
+        "with_solve": {"steps": ws_steps, "solve_cores": solve_workers, "ratio_to_value": value_with_solve / value,
+                       "host_wait_ms_per_step": 1e3 * solve_wait / ws_steps,
+                       "note": "fresh deform_grid per frame and step; np.linalg.pinv systems (reference tps.py:113-119) solved by "
+                               f"{solve_workers} worker processes per rank while the previous step's kernels run"},
+        "roofline": {"bound": "hbm", "kernel": stage_info["kernel"],
+                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": traffic.get("traffic_per_launch"), "traffic_source": traffic.get("source"),
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms,
-                     "step_frac": alg / ((ms_total / args.steps) / 1e3) / 1e9 / peak, "stages": stages},
+                     "step_frac": alg / ((ms_total / args.steps) / 1e3) / 1e9 / peak, "stages": stage_info["stages"]},
         "e2e": e2e, "e2e_matches_device_path": same,
+        "configs": cfgs,
         "gpu_launches": launches, "clocks": clocks,
         "status_words": [int(v) for v in status.cpu()],
     }
     if world == 1:
-        line["cpu_baseline"] = cpu_baseline(O, frames=4)
+        line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
 
+def kernel_stages(vm, lib, step, torch):
+    """Per-kernel durations of one (untimed) step from CUDA events recorded inside the library on the launch
+    stream, with the committed ncu DRAM traffic of each kernel beside them."""
+    import ctypes
+    Nt = vm._native
+    peak, _ = measured_peak()
+    traffic = load_traffic()
+    names = traffic.get("kernels") or ["k_lean_coarse<25> (TPS on the coarse grid, float64)", "k_lean_boxes<1> (source box per tile)",
+                                       "k_flow_warp_mask_bgra<1,2> (flow warp + consistency mask)",
+                                       "k_lean_fine<1,4> (resampling + composite)"]
+    try:
+        Nt.set_option("lean_timing", 1)
+        rows = []
+        for _ in range(3):
+            step(False)
+            torch.cuda.synchronize()
+            buf = (ctypes.c_float * 4)()
+            Nt.check(lib.vm_lean_stage_ms(ctypes.cast(buf, ctypes.c_void_p)))
+            rows.append(list(buf))
+        stage_ms = [statistics.median(col) for col in zip(*rows)]
+    except Exception as e:          # noqa: BLE001 - stage timing is diagnostic only
+        return {"kernel": "vm_flow_tps_composite_bgra", "stages": [{"error": str(e)}]}
+    finally:
+        Nt.set_option("lean_timing", 0)
+    stage_bpp = traffic.get("stage_algorithmic_bpp") or [0, 0, 20, 19]
+    stage_tr = traffic.get("stage_traffic") or [None] * len(stage_ms)
+    total = sum(stage_ms) or 1.0
+    stages = []
+    for nm, ms_k, bpp, tr in zip(names, stage_ms, stage_bpp, stage_tr):
+        if ms_k <= 0:
+            continue
+        rec = {"kernel": nm, "ms": ms_k, "share_of_step": ms_k / total,
+               "algorithmic_GBps": (bpp * H * W * CLIP / (ms_k / 1e3) / 1e9) if bpp else None}
+        if tr:
+            rec["dram_GBps"] = tr / (ms_k / 1e3) / 1e9
+            rec["dram_frac_of_peak"] = rec["dram_GBps"] / peak
+        stages.append(rec)
+    return {"kernel": traffic.get("kernel_note") or
+            "vm_flow_tps_composite_bgra, timed as one unit (39 B/px is defined for the whole pipeline); see stages",
+            "stages": stages}
+
+
+def bench_configs(vm, torch, dev, rank, world, barrier, max_over_ranks, peak, pool, iters=5):
+    """The other BASELINE.json configs, device-resident, short runs (3 warm-up + `iters` timed launches each,
+    CUDA events, max over ranks): C2 1080p x 64, C3 512^2 x 256 (16 control points), C4 4K x 16 per GPU
+    (config 4 = 256 frames clip-sharded: 16 clips of 16 frames, each rank times its share), C5 augment_clip."""
+    import numpy as np
+    P, Nt = vm.pipeline, vm._native
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    out = []
+
+    def timed(fn, n_it=iters):
+        for _ in range(3):
+            fn()
+        barrier()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(n_it):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / n_it
+
+    def rec(name, which, h, w, n, ms, extra=None):
+        bpp = BYTES_PER_PX[which]
+        gbs = bpp * h * w * n / (ms / 1e3) / 1e9
+        r = {"config": name, "height": h, "width": w, "frames_per_launch_per_gpu": n, "ms": ms,
+             "fps": world * n / (ms / 1e3), "algorithmic_bytes_per_px": bpp, "frac": gbs / peak}
+        r.update(extra or {})
+        out.append(r)
+
+    try:
+        h, w, n = 1080, 1920, 64
+        fg, fb, ff, bg = make_clip(torch, 77 + rank, n, h, w, dev)
+        st = Nt.new_status(dev)
+        ob = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+        oa = torch.empty((n, h, w), dtype=torch.float32, device=dev)
+        rec("C2 flow warp + fwd/bwd mask, 1080p x 64", "c2", h, w, n,
+            timed(lambda: P.flow_warp_mask(fg, fb, ff, out_bgr=ob, out_alpha=oa, status=st)))
+        del ob, oa
+        # C5: augmentation.augment_clip on the same clip (host RNG plan + pinv per frame included, alpha statistics reused)
+        bgn = bg[torch.arange(n) % bg.shape[0]].contiguous()
+        stats = vm.augmentation.alpha_stats(fg)
+        np.random.seed(1 + rank)
+        barrier()
+        for _ in range(2):
+            vm.augmentation.augment_clip(fg, bgn, stats=stats)
+        barrier()
+        t = time.perf_counter()
+        for _ in range(iters):
+            vm.augmentation.augment_clip(fg, bgn, stats=stats)
+        barrier()
+        ms5 = 1e3 * max_over_ranks(time.perf_counter() - t) / iters
+        rec("C5 augmentation.augment_clip (RNG plan + host pinv + TPS + 2 affine passes + illumination), 1080p x 64, wall clock",
+            "c5", h, w, n, ms5, {"host_bound": True})
+        del fg, fb, ff, bg, bgn
+        torch.cuda.empty_cache()
+
+        h, w, n = 512, 512, 256
+        fg, fb, ff, bg = make_clip(torch, 78 + rank, n, h, w, dev)
+        ctrl, coef = P.solve_grids(make_grids(vm, 500 + rank, n, h, w, 4), dev, pool=pool)
+        o = torch.empty((n, h, w, 4), dtype=torch.float32, device=dev)
+        rec("C3 TPS (16 control points) + composite, 512x512 x 256", "c3", h, w, n,
+            timed(lambda: P.tps_composite(fg, bg, ctrl, coef, out=o, status=st)))
+        del fg, fb, ff, bg, o
+        torch.cuda.empty_cache()
+
+        h, w, n = 2160, 3840, 16
+        fg, fb, ff, bg = make_clip(torch, 79 + rank, n, h, w, dev)
+        ctrl, coef = P.solve_grids(make_grids(vm, 600 + rank, n, h, w, 5), dev, pool=pool)
+        o = torch.empty((n, h, w, 4), dtype=torch.float32, device=dev)
+        rec("C4 flow warp + mask + TPS + composite, 4K, clips of 16 frames (config 4: 256 frames clip-sharded over the ranks)",
+            "c4", h, w, n, timed(lambda: P.flow_tps_composite(fg, fb, ff, bg, ctrl, coef, out=o, status=st)),
+            {"equivalent_1080p_fps": None})
+        out[-1]["equivalent_1080p_fps"] = out[-1]["fps"] * 4
+        out[-1]["seconds_for_256_frames"] = 256 / out[-1]["fps"]
+        del fg, fb, ff, bg, o
+        torch.cuda.empty_cache()
+    except Exception as e:          # noqa: BLE001 - the headline must still be printed
+        out.append({"error": repr(e)})
+    return out
+
+
 # --------------------------------------------------------------- CPU baseline / reference arm
 
-def _cpu_frame(seed):
+def _synth_host_frame(seed):
+    """One synthetic 1080p frame, flows, grids and background on the host (SURVEY 8d generators)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import vm_oracle as O
-    fgf = O.synth_frame(seed, H, W)
-    b, f = O.synth_flows(seed, H, W)
-    g = O.synth_grids(seed, H, W, NCTRL)
-    bgf = O.synth_background(seed, H, W)
+    return (O.synth_frame(seed, H, W),) + tuple(O.synth_flows(seed, H, W)) + (O.synth_grids(seed, H, W, NCTRL),
+                                                                              O.synth_background(seed, H, W))
+
+
+def _load_reference():
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import refshim
+    return refshim.load(("reader", "flow", "tps", "augmentation"))
+
+
+def _reference_frame(seed, threads=None):
+    """The C4 pipeline of SURVEY 8d through the UNMODIFIED reference functions (baseline/_ref): warp_bgr,
+    warp_img, correct_alpha (the shipped pure-Python loop), warp_image(thin=grids) twice, create_composite_image.
+    Returns (seconds, seconds spent in correct_alpha)."""
+    import contextlib
+    import io
+    import numpy as np
+    import cv2
+    if threads is not None:
+        cv2.setNumThreads(threads)
+    R = _load_reference()
+    fgf, fb, ff, grids, bgf = _synth_host_frame(seed)
+    alpha, bgr = fgf[..., 3] / 255., np.ascontiguousarray(fgf[..., :3])
+    params = ((0, 0), 0., 1., (W // 2, H // 2))
     t = time.perf_counter()
-    O.pipeline_c4(fgf, b, f, g, bgf)
-    return time.perf_counter() - t
+    b = R["flow"].warp_bgr(bgr, fb)
+    a = R["flow"].warp_img(alpha, fb)
+    tc = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        a = R["flow"].correct_alpha(fb, ff, a)
+    tc = time.perf_counter() - tc
+    b2 = R["augmentation"].warp_image(b, params, thin=grids)
+    a2 = R["augmentation"].warp_image(a, params, thin=grids)
+    R["reader"].create_composite_image(b2, bgf, a2)
+    return time.perf_counter() - t, tc
 
 
-def cpu_baseline(O, frames=2):
-    """Oracle (NumPy restatement of the reference pipeline) on this box's host, one process."""
-    secs = [_cpu_frame(10 + k) for k in range(frames)]
+def _port_frame(seed):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import vm_oracle as O
+    fgf, fb, ff, grids, bgf = _synth_host_frame(seed)
+    t = time.perf_counter()
+    O.pipeline_c4(fgf, fb, ff, grids, bgf)
+    return time.perf_counter() - t, 0.0
+
+
+def _have_reference():
+    try:
+        _load_reference()
+        return True
+    except Exception:
+        return False
+
+
+def cpu_baseline():
+    """Rank 0, N=1: the reference AS SHIPPED (one process, cv2's default thread pool) on one synthetic 1080p frame
+    when baseline/_ref is present, else the oracle port on four frames."""
+    if _have_reference():
+        import cv2
+        secs, tc = _reference_frame(10)
+        return {"value": 1.0 / secs, "unit": "frames/s", "cores": int(cv2.getNumThreads()), "kind": "reference",
+                "sample": "1 synthetic 1080p frame through the unmodified reference modules (baseline/_ref via the A.0 shim), "
+                          "one process, cv2 default threads; correct_alpha (pure-Python loop, flow.py:41-48) took "
+                          f"{tc:.1f} s = {1e6 * tc / (H * W):.2f} us/px of {secs:.1f} s"}
+    frames = 4
+    secs = [_port_frame(10 + k)[0] for k in range(frames)]
     return {"value": frames / sum(secs), "unit": "frames/s", "cores": 1, "kind": "port",
             "sample": f"{frames} synthetic 1080p frames through oracle.pipeline_c4 (vectorised NumPy restatement; "
-                      "the shipped reference adds a pure-Python per-pixel loop in correct_alpha, ~10 us/px)"}
+                      "baseline/_ref absent)"}
+
+
+def _ref_worker(seed):
+    return _reference_frame(seed, threads=1)
 
 
 def run_reference(args):
+    """The reference's own CPU implementation with all host cores: one process per core (cv2.setNumThreads(1)),
+    one 1080p frame per process and step; before that, two frames as shipped (one process,
+    cv2's default pool).  Bounded to ~4 minutes whatever --steps says."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    workers = max(1, min(cores, 32))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    workers = max(1, min(cores, 64))
+    use_ref = _have_reference()
+    fn = _ref_worker if use_ref else _port_frame
+    kind = "reference" if use_ref else "port"
+    shipped = None
+    if use_ref:
+        import cv2
+        rows = [_reference_frame(20 + k) for k in range(2)]
+        secs, tc = sum(r[0] for r in rows), sum(r[1] for r in rows)
+        shipped = {"frames": 2, "fps": 2 / secs, "s_per_frame": secs / 2, "cv2_threads": int(cv2.getNumThreads()),
+                   "correct_alpha_s_per_frame": tc / 2, "correct_alpha_us_per_px": 1e6 * tc / 2 / (H * W)}
     ctx = mp.get_context("spawn")
     times = []
-    # bounded sample: every step is `workers` frames (one per process); at most ~150 s of wall clock in total
-    budget_s, t_start = 150.0, time.perf_counter()
-    warm = min(args.warmup, 1)
+    budget_s, t_start = 170.0, time.perf_counter()
+    warm = 0 if use_ref else min(args.warmup, 1)         # a reference step is ~25 s of pure Python: nothing to warm up
     with ctx.Pool(workers) as pool:
         for s in range(warm + args.steps):
             t = time.perf_counter()
-            pool.map(_cpu_frame, [1000 * s + k for k in range(workers)])
+            pool.map(fn, [1000 * s + k for k in range(workers)])
             dt = time.perf_counter() - t
             if s >= warm:
                 times.append(dt)
@@ -329,15 +628,17 @@ def run_reference(args):
     total = sum(times)
     steps_run = len(times)
     value = workers * steps_run / total
+    sample = (f"{workers} synthetic 1080p frames per step, one per worker process with cv2.setNumThreads(1) (host has {cores} usable cores); "
+              + ("unmodified reference modules from baseline/_ref (flow.warp_bgr / warp_img / correct_alpha as shipped, "
+                 "augmentation.warp_image(thin=grids) x2, reader.create_composite_image)" if use_ref else
+                 "oracle.pipeline_c4 = NumPy restatement (baseline/_ref absent)"))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s",
             "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": steps_run, "steps_requested": args.steps,
             "warmup": warm, "ms_per_step": 1e3 * total / steps_run, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 in / f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "height": H, "width": W, "frames_per_step": workers},
-            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": workers, "kind": "port",
-                             "sample": f"{workers} 1080p frames per step, one per worker process (host has {cores} cores); "
-                                       "oracle.pipeline_c4 = NumPy restatement of the reference pipeline (the Python "
-                                       "reference and its cv2/scipy wheels cannot be compiled into oracle/_ref)"},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": workers, "kind": kind, "sample": sample,
+                             "as_shipped": shipped},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 

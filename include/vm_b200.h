@@ -103,12 +103,21 @@ int vm_tps_warp(const void *src, int dtype, int channels, int sh, int sw,
                 const double *coarse, int nx, int ny,
                 const vm_axis_entry *rows, const vm_axis_entry *cols,
                 int oh, int ow, void *dst, int32_t *status, void *stream);
+/* Same with the `interpolation_order` argument of tps.warp_images (tps.py:14,34): 1 = bilinear (above),
+ * 0 = nearest neighbour as scipy does it: cval 0 outside [0, n-1], else the sample at floor(t + 1/2). */
+int vm_tps_warp_order(const void *src, int dtype, int channels, int sh, int sw,
+                      const double *coarse, int nx, int ny,
+                      const vm_axis_entry *rows, const vm_axis_entry *cols,
+                      int oh, int ow, void *dst, int32_t *status, int order, void *stream);
 
 /* scipy.ndimage.map_coordinates(order=1, mode='constant', cval=0) with an explicit transform
  * (tps.py:34 when approximate_grid is None/1): t0/t1 (oh, ow) float64 row / column coords.  */
 int vm_map_coordinates(const void *src, int dtype, int channels, int sh, int sw,
                        const double *t0, const double *t1, int oh, int ow, void *dst,
                        int32_t *status, void *stream);
+int vm_map_coordinates_order(const void *src, int dtype, int channels, int sh, int sw,
+                             const double *t0, const double *t1, int oh, int ow, void *dst,
+                             int32_t *status, int order, void *stream);
 
 /* ---- cv2.warpAffine (INTER_LINEAR, BORDER_CONSTANT 0), legacy fixed-point path -----------
  * reference: augmentation.py:59-62.  M is the forward 2x3 matrix (row-major, 6 doubles,

@@ -364,13 +364,27 @@ def map_coordinates_linear(img, t0, t1):
     return v.astype(img.dtype)
 
 
+def map_coordinates_nearest(img, t0, t1):
+    """scipy.ndimage.map_coordinates(order=0, mode='constant', cval=0) (tps.py:34 with interpolation_order=0,
+    "if 0 then use nearest-neighbor", tps.py:22): outside [0, n-1] -> 0, else the sample at floor(t + 1/2)
+    (probed against scipy 1.18: 0.5 -> 1, 1.5 -> 2, 2.5 -> 3, -1e-4 -> cval, n-1+1e-7 -> cval)."""
+    img = np.asarray(img)
+    H, W = img.shape
+    with np.errstate(invalid='ignore'):
+        inside = (t0 >= 0) & (t0 <= H - 1) & (t1 >= 0) & (t1 <= W - 1)
+    i = np.floor(np.where(inside, t0, 0.) + 0.5).astype(np.int64)
+    j = np.floor(np.where(inside, t1, 0.) + 0.5).astype(np.int64)
+    return np.where(inside, img[i, j], 0).astype(img.dtype)
+
+
 def tps_warp_images(from_points, to_points, images, output_region, interpolation_order=1,
                     approximate_grid=2):
-    """tps.py:14-34 (linear interpolation, region (0,0,h,w))."""
+    """tps.py:14-34 (nearest or linear interpolation, region (0,0,h,w))."""
     x_min, y_min, h, w = output_region
-    assert x_min == 0 and y_min == 0 and interpolation_order == 1
+    assert x_min == 0 and y_min == 0 and interpolation_order in (0, 1)
     (t0, t1), _, _ = tps_inverse_transform(from_points, to_points, h, w, approximate_grid)
-    return [map_coordinates_linear(im, t0, t1) for im in images]
+    fn = map_coordinates_linear if interpolation_order == 1 else map_coordinates_nearest
+    return [fn(im, t0, t1) for im in images]
 
 
 # --------------------------------------------------------------------------------------

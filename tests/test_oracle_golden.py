@@ -5,6 +5,7 @@ Bars: uint8 outputs, masks, .flo parse bit-exact; float alpha / comp
 |got-ref| <= 1e-5*|ref| + 1e-6; change_illumination +-1 LSB.
 """
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -209,3 +210,71 @@ def test_config1_window_oracle(c1):
     assert np.array_equal(ca, c1["corrected"]) and int((ca != wa).sum()) > 0
     assert np.array_equal(O.create_composite_image(c1["warp_bgr"], c1["bg"], ca), c1["composite"])
     assert c1["mae"][1] < 0.2 * c1["mae"][0]          # recorded at native resolution by the generator
+
+
+# ---- BASELINE config 1 at NATIVE resolution, 500 x 1200 (tests/golden/make_c1_full_golden.py) -----------------
+
+def load_c1_full():
+    """Fixture of make_c1_full_golden.py -> dict with the decoded inputs added (decoded with cv2 only:
+    the product / oracle readers are what the tests check)."""
+    import hashlib
+    with np.load(os.path.join(ROOT, "tests", "golden", "c1_full_golden.npz")) as z:
+        c = {k: z[k] for k in z.files}
+    c["backward"] = c["backward_q16"].astype(np.float32) / 16.0
+    c["forward"] = c["forward_q16"].astype(np.float32) / 16.0
+    c["sha"] = lambda a: np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+    return c
+
+
+def test_config1_native_oracle():
+    """The oracle against the unmodified reference on the whole 500 x 1200 frames: bit-exact outputs by
+    digest, the composite on the stored sub-grid."""
+    import cv2
+    c = load_c1_full()
+    sha = c["sha"]
+    img16 = cv2.imdecode(c["in0063_png"], cv2.IMREAD_UNCHANGED)
+    assert img16.dtype == np.uint16 and img16.shape == (500, 1200, 4)
+    alpha, bgr = O.split_fg(O.fg_from_uint16(img16))
+    bgr = np.ascontiguousarray(bgr)
+    assert np.array_equal(sha(bgr), c["sha_fg63"]) and np.array_equal(sha(alpha), c["sha_alpha63"])
+    jpg = cv2.imdecode(c["sea_jpg"], cv2.IMREAD_COLOR)
+    bg = cv2.resize(jpg, dsize=(1200, 500), interpolation=cv2.INTER_LINEAR)          # host call of the reference (reader.py:41)
+    assert np.array_equal(sha(bg), c["sha_bg"])
+    wa = O.warp_img(alpha, c["backward"])
+    assert np.array_equal(sha(wa), c["sha_warp_alpha"])
+    wb = O.warp_bgr(bgr, c["backward"])
+    assert np.array_equal(sha(wb), c["sha_warp_bgr"]) and int(wb.astype(np.int64).sum()) == int(c["sum_warp_bgr"][0])
+    ca = O.correct_alpha(c["backward"], c["forward"], wa.copy())
+    assert int((ca != wa).sum()) == int(c["n_masked"][0])
+    assert np.array_equal(sha(ca), c["sha_corrected"])
+    cmp_ = O.create_composite_image(wb, bg, ca)
+    assert np.array_equal(cmp_[::3, ::3].astype(np.float32), c["composite_sub"])
+    assert cmp_.sum() == c["sum_composite"][0]
+
+
+def test_tps_order0_oracle_vs_scipy_and_reference():
+    """interpolation_order=0 (tps.py:22,34): the oracle's nearest-neighbour rule against scipy itself on
+    knife-edge coordinates, and against the unmodified reference's tps.warp_images when it is importable."""
+    from scipy import ndimage
+    rng = np.random.default_rng(3)
+    img8 = rng.integers(0, 256, (23, 31), dtype=np.uint8)
+    img64 = rng.random((23, 31))
+    t0 = rng.uniform(-2, 25, (40, 50))
+    t1 = rng.uniform(-2, 33, (40, 50))
+    t0[:6, :8] = np.array([-0.5, -1e-9, 0.0, 0.5, 1.5, 2.5, 22.0, 22.0000001])[None, :]
+    t1[:6, :8] = np.array([0.5, 1.5, 2.5, 29.5, 30.0, 30.0000001])[:, None]
+    for img in (img8, img64):
+        ref = ndimage.map_coordinates(img, [t0, t1], order=0)
+        assert np.array_equal(O.map_coordinates_nearest(img, t0, t1), ref)
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import refshim
+    if refshim.reference_dir() is None:
+        pytest.skip("reference modules not available")
+    tps = refshim.load(("tps",))["tps"]
+    h, w = 61, 83
+    grid, dgrid = O.synth_grids(9, h, w, 4)
+    img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    for order in (0, 1):
+        ref = tps.warp_images(grid, dgrid, [img, img / 255.], (0, 0, h, w), interpolation_order=order)
+        got = O.tps_warp_images(grid, dgrid, [img, img / 255.], (0, 0, h, w), interpolation_order=order)
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])

@@ -31,6 +31,8 @@ SIGNATURES = {
     "vm_tps_upsample": [_P, _I, _I, _P, _P, _I, _I, _P, _P],
     "vm_tps_warp": [_P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _I, _I, _P, _P, _P],
     "vm_map_coordinates": [_P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P],
+    "vm_tps_warp_order": [_P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P],
+    "vm_map_coordinates_order": [_P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P],
     "vm_warp_affine": [_P, _I, _I, _I, _I, _P, _I, _I, _P, _P],
     "vm_change_illumination": [_P, _L, _D, _D, _D, _P, _P],
     "vm_illumination_lut": [_P, _L, _P, _P, _P],

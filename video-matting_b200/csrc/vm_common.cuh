@@ -198,6 +198,9 @@ __device__ __forceinline__ double vm_mapcoord_blend(const VmBilin64 &s, double s
     return v;
 }
 
+// scipy order 0 (nearest): index floor(t + 1/2) of an in-range coordinate (0 <= t <= n - 1)
+__device__ __forceinline__ int vm_nearest(double t) { return (int)floor(t + 0.5); }
+
 __device__ __forceinline__ uint8_t vm_round_half_up_u8(double v) {
     const double r = floor(v + 0.5);
     return (uint8_t)(r < 0.0 ? 0 : (r > 255.0 ? 255 : (int)r));

@@ -167,7 +167,7 @@ template <typename T, int C>
 __global__ void __launch_bounds__(256)
 k_tps_warp(const T *__restrict__ src, int sh, int sw, const double *__restrict__ coarse, int nx, int ny,
            const vm_axis_entry *__restrict__ rows, const vm_axis_entry *__restrict__ cols,
-           int oh, int ow, T *__restrict__ dst, int32_t *__restrict__ status) {
+           int oh, int ow, T *__restrict__ dst, int32_t *__restrict__ status, int order) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
     if (j >= ow || i >= oh) return;
     double t0, t1;
@@ -178,6 +178,12 @@ k_tps_warp(const T *__restrict__ src, int sh, int sw, const double *__restrict__
 #pragma unroll
         for (int c = 0; c < C; ++c) o[c] = T(0);
         if (status) atomicAdd(status + VM_STATUS_TPS_OUTSIDE, 1);
+        return;
+    }
+    if (order == 0) {                       // scipy order 0: the sample at floor(t + 1/2), no arithmetic on the value
+        const T *pn = src + ((int64_t)vm_nearest(t0) * sw + vm_nearest(t1)) * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) o[c] = __ldg(pn + c);
         return;
     }
     const T *p00 = src + ((int64_t)s.i0 * sw + s.j0) * C, *p01 = src + ((int64_t)s.i0 * sw + s.j1) * C;
@@ -195,11 +201,19 @@ extern "C" int vm_tps_warp(const void *src, int dtype, int channels, int sh, int
                            const double *coarse, int nx, int ny, const vm_axis_entry *rows,
                            const vm_axis_entry *cols, int oh, int ow, void *dst, int32_t *status,
                            void *stream) {
+    return vm_tps_warp_order(src, dtype, channels, sh, sw, coarse, nx, ny, rows, cols, oh, ow, dst, status, 1, stream);
+}
+
+extern "C" int vm_tps_warp_order(const void *src, int dtype, int channels, int sh, int sw,
+                                 const double *coarse, int nx, int ny, const vm_axis_entry *rows,
+                                 const vm_axis_entry *cols, int oh, int ow, void *dst, int32_t *status,
+                                 int order, void *stream) {
     VM_REQUIRE(src && coarse && rows && cols && dst, "null pointer");
+    VM_REQUIRE(order == 0 || order == 1, "interpolation order must be 0 or 1");
     VM_REQUIRE(sh >= 1 && sw >= 1 && oh >= 1 && ow >= 1 && oh < 65536, "bad size");
     dim3 grid((ow + 255) / 256, oh);
     cudaStream_t st = (cudaStream_t)stream;
-#define VM_TW(T, C) k_tps_warp<T, C><<<grid, 256, 0, st>>>((const T *)src, sh, sw, coarse, nx, ny, rows, cols, oh, ow, (T *)dst, status)
+#define VM_TW(T, C) k_tps_warp<T, C><<<grid, 256, 0, st>>>((const T *)src, sh, sw, coarse, nx, ny, rows, cols, oh, ow, (T *)dst, status, order)
     if (dtype == VM_U8 && channels == 1) VM_TW(uint8_t, 1);
     else if (dtype == VM_U8 && channels == 3) VM_TW(uint8_t, 3);
     else if (dtype == VM_U8 && channels == 4) VM_TW(uint8_t, 4);
@@ -215,7 +229,7 @@ template <typename T, int C>
 __global__ void __launch_bounds__(256)
 k_map_coordinates(const T *__restrict__ src, int sh, int sw, const double *__restrict__ t0p,
                   const double *__restrict__ t1p, int oh, int ow, T *__restrict__ dst,
-                  int32_t *__restrict__ status) {
+                  int32_t *__restrict__ status, int order) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
     if (j >= ow || i >= oh) return;
     const int64_t q = (int64_t)i * ow + j;
@@ -225,6 +239,12 @@ k_map_coordinates(const T *__restrict__ src, int sh, int sw, const double *__res
 #pragma unroll
         for (int c = 0; c < C; ++c) o[c] = T(0);
         if (status) atomicAdd(status + VM_STATUS_TPS_OUTSIDE, 1);
+        return;
+    }
+    if (order == 0) {
+        const T *pn = src + ((int64_t)vm_nearest(t0p[q]) * sw + vm_nearest(t1p[q])) * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) o[c] = __ldg(pn + c);
         return;
     }
     const T *p00 = src + ((int64_t)s.i0 * sw + s.j0) * C, *p01 = src + ((int64_t)s.i0 * sw + s.j1) * C;
@@ -241,11 +261,18 @@ k_map_coordinates(const T *__restrict__ src, int sh, int sw, const double *__res
 extern "C" int vm_map_coordinates(const void *src, int dtype, int channels, int sh, int sw,
                                   const double *t0, const double *t1, int oh, int ow, void *dst,
                                   int32_t *status, void *stream) {
+    return vm_map_coordinates_order(src, dtype, channels, sh, sw, t0, t1, oh, ow, dst, status, 1, stream);
+}
+
+extern "C" int vm_map_coordinates_order(const void *src, int dtype, int channels, int sh, int sw,
+                                        const double *t0, const double *t1, int oh, int ow, void *dst,
+                                        int32_t *status, int order, void *stream) {
     VM_REQUIRE(src && t0 && t1 && dst, "null pointer");
+    VM_REQUIRE(order == 0 || order == 1, "interpolation order must be 0 or 1");
     VM_REQUIRE(sh >= 1 && sw >= 1 && oh >= 1 && ow >= 1 && oh < 65536, "bad size");
     dim3 grid((ow + 255) / 256, oh);
     cudaStream_t st = (cudaStream_t)stream;
-#define VM_MC(T, C) k_map_coordinates<T, C><<<grid, 256, 0, st>>>((const T *)src, sh, sw, t0, t1, oh, ow, (T *)dst, status)
+#define VM_MC(T, C) k_map_coordinates<T, C><<<grid, 256, 0, st>>>((const T *)src, sh, sw, t0, t1, oh, ow, (T *)dst, status, order)
     if (dtype == VM_U8 && channels == 1) VM_MC(uint8_t, 1);
     else if (dtype == VM_U8 && channels == 3) VM_MC(uint8_t, 3);
     else if (dtype == VM_F64 && channels == 1) VM_MC(double, 1);

@@ -117,8 +117,9 @@ def alpha_stats(alpha):
     return out
 
 
-def map_coordinates(src, t0, t1, status=None):
-    """scipy.ndimage.map_coordinates(src, [t0, t1], order=1) - reference tps.py:34."""
+def map_coordinates(src, t0, t1, status=None, order=1):
+    """scipy.ndimage.map_coordinates(src, [t0, t1], order=order) - reference tps.py:34; order 1 (bilinear) or
+    0 (nearest: the sample at floor(t + 1/2), 0 outside [0, n-1])."""
     lib = N.load()
     src = src.contiguous()
     t0 = t0.to(torch.float64).contiguous()
@@ -126,8 +127,8 @@ def map_coordinates(src, t0, t1, status=None):
     ch = 1 if src.dim() == 2 else src.shape[2]
     oh, ow = t0.shape
     dst = torch.empty((oh, ow) if src.dim() == 2 else (oh, ow, ch), dtype=src.dtype, device=src.device)
-    N.check(lib.vm_map_coordinates(N.ptr(src), N.dtype_code(src), ch, src.shape[0], src.shape[1], N.ptr(t0),
-                                   N.ptr(t1), oh, ow, N.ptr(dst), N.ptr(status), N.stream_ptr()))
+    N.check(lib.vm_map_coordinates_order(N.ptr(src), N.dtype_code(src), ch, src.shape[0], src.shape[1], N.ptr(t0),
+                                         N.ptr(t1), oh, ow, N.ptr(dst), N.ptr(status), int(order), N.stream_ptr()))
     return dst
 
 
@@ -135,33 +136,11 @@ def map_coordinates(src, t0, t1, status=None):
 # thin-plate spline: host solve + device evaluation
 # ----------------------------------------------------------------------------------------
 
-def _tps_kernel_matrix(points):
-    """L = [[K, P], [P^T, 0]], K_ab = U(|P_a - P_b|), U(r) = r^2 log r (reference tps.py:78-98).
-    The expression order is the reference's so that L - and therefore numpy's truncated
-    pseudo-inverse of it - is bit-identical."""
-    pts = np.asarray(points, dtype=np.float64)
-    n = len(pts)
-    d0 = np.subtract.outer(pts[:, 0], pts[:, 0])
-    d1 = np.subtract.outer(pts[:, 1], pts[:, 1])
-    r = np.sqrt(d0 ** 2 + d1 ** 2)
-    with np.errstate(divide="ignore", invalid="ignore"):
-        K = (r ** 2) * np.where(r < 1e-100, 0, np.log(r))
-    L = np.zeros((n + 3, n + 3))
-    L[:n, :n] = K
-    L[:n, n] = 1.0
-    L[:n, n + 1:] = pts
-    L[n:, :n] = L[:n, n:].T
-    return L
+from .hostpool import vm_tps_host as _host
 
-
-def tps_solve(src_points, dst_points):
-    """Spline coefficients (N+3, 2) mapping src_points onto dst_points: numpy's own
-    ``dot(pinv(L), V)`` (reference tps.py:113-119) - called, not re-implemented, because the
-    rcond=1e-15 truncation is active for 1080p/4K grids."""
-    dst = np.asarray(dst_points, dtype=np.float64)
-    V = np.zeros((len(dst) + 3, 2))
-    V[:len(dst)] = dst
-    return np.dot(np.linalg.pinv(_tps_kernel_matrix(src_points)), V)
+_tps_kernel_matrix = _host.tps_kernel_matrix
+tps_solve = _host.tps_solve
+SolverPool = _host.SolverPool
 
 
 def axis_table(lo, hi, steps):
@@ -243,79 +222,33 @@ def tps_transform(coarse, plan):
     return out
 
 
-def tps_warp(src, coarse, plan, out_hw=None, status=None):
+def tps_warp(src, coarse, plan, out_hw=None, status=None, order=1):
     """Fused up-sample + map_coordinates of one image (reference tps.warp_images, one entry)."""
     lib = N.load()
     src = src.contiguous()
     if plan.approximate_grid == 1:
-        return map_coordinates(src, coarse[0], coarse[1], status)
+        return map_coordinates(src, coarse[0], coarse[1], status, order)
     ch = 1 if src.dim() == 2 else src.shape[2]
     oh, ow = out_hw if out_hw is not None else (plan.out_h, plan.out_w)
     assert oh <= plan.out_h and ow <= plan.out_w
     dst = torch.empty((oh, ow) if src.dim() == 2 else (oh, ow, ch), dtype=src.dtype, device=src.device)
-    N.check(lib.vm_tps_warp(N.ptr(src), N.dtype_code(src), ch, src.shape[0], src.shape[1], N.ptr(coarse),
-                            plan.nx, plan.ny, N.ptr(plan.rows), N.ptr(plan.cols), oh, ow, N.ptr(dst),
-                            N.ptr(status), N.stream_ptr()))
+    N.check(lib.vm_tps_warp_order(N.ptr(src), N.dtype_code(src), ch, src.shape[0], src.shape[1], N.ptr(coarse),
+                                  plan.nx, plan.ny, N.ptr(plan.rows), N.ptr(plan.cols), oh, ow, N.ptr(dst),
+                                  N.ptr(status), int(order), N.stream_ptr()))
     return dst
 
 
-_stacked_kernel_ok = [None]      # None: not checked yet in this process
+_tps_kernel_matrices = _host.tps_kernel_matrices
+_stacked_kernel_ok = _host._stacked_kernel_ok      # same list object: tests flip it
+_solve_chunk = _host.solve_chunk
 
 
-def _tps_kernel_matrices(points):
-    """_tps_kernel_matrix for a stack (m, N, 2) of control-point sets with the same element-wise expressions.
-    numpy's sqrt / log loops are expected to give the same value for an element wherever it sits in an array; that
-    is verified once per process on the first stack (bit for bit against the per-frame function), and the per-frame
-    function is used from then on if it ever fails."""
-    pts = np.asarray(points, dtype=np.float64)
-    m, n = pts.shape[:2]
-    d0 = pts[:, :, None, 0] - pts[:, None, :, 0]
-    d1 = pts[:, :, None, 1] - pts[:, None, :, 1]
-    r = np.sqrt(d0 ** 2 + d1 ** 2)
-    with np.errstate(divide="ignore", invalid="ignore"):
-        K = (r ** 2) * np.where(r < 1e-100, 0, np.log(r))
-    L = np.zeros((m, n + 3, n + 3))
-    L[:, :n, :n] = K
-    L[:, :n, n] = 1.0
-    L[:, :n, n + 1:] = pts
-    L[:, n:, :n] = np.transpose(L[:, :n, n:], (0, 2, 1))
-    return L
-
-
-def _kernel_stack(chunk):
-    if _stacked_kernel_ok[0] is not False:
-        L = _tps_kernel_matrices(np.stack([np.asarray(d, dtype=np.float64) for (_, d) in chunk]))
-        if _stacked_kernel_ok[0] is None:
-            ref = np.stack([_tps_kernel_matrix(d) for (_, d) in chunk])
-            _stacked_kernel_ok[0] = bool(L.tobytes() == ref.tobytes())
-            return ref
-        return L
-    return np.stack([_tps_kernel_matrix(d) for (_, d) in chunk])
-
-
-def _solve_chunk(chunk):
-    """np.dot(np.linalg.pinv(L), V) for a list of (grid, deformed grid) pairs: numpy's stacked pinv runs
-    the same LAPACK call per matrix as the reference's per-frame call (bit-identical, checked in the tests)."""
-    L = _kernel_stack(chunk)
-    V = np.zeros((len(chunk), L.shape[1], 2))
-    for k, (g, _) in enumerate(chunk):
-        g = np.asarray(g, dtype=np.float64)
-        V[k, :len(g)] = g
-    Li = np.linalg.pinv(L)
-    return np.stack([np.dot(Li[k], V[k]) for k in range(len(chunk))])
-
-
-def solve_grids(grids, device=None):
+def solve_grids(grids, device=None, pool=None):
     """Host solve for a batch of (regular grid, deformed grid) pairs as used by
     augmentation.warp_image(..., thin=grids): the system is built from the DEFORMED grid and maps
-    back onto the regular one (reference tps.py:51).  Returns CUDA (ctrl, coef)."""
-    grids = list(grids)
-    ctrl = np.stack([np.asarray(d, dtype=np.float64) for (_, d) in grids])
-    same = len({len(d) for (_, d) in grids}) == 1
-    if same:
-        coef = np.concatenate([_solve_chunk(grids[i:i + 16]) for i in range(0, len(grids), 16)])
-    else:
-        coef = np.stack([tps_solve(d, g) for (g, d) in grids])
+    back onto the regular one (reference tps.py:51).  ``pool``: a SolverPool to spread the solves over
+    host cores.  Returns CUDA (ctrl, coef)."""
+    ctrl, coef = pool.solve(grids) if pool is not None else _host.solve_many(grids)
     dev = torch.device(device if device is not None else "cuda")
     return torch.from_numpy(ctrl).to(dev), torch.from_numpy(coef).to(dev)
 
@@ -369,11 +302,12 @@ _scratch_cache = {}
 def _fused_scratch(lib, n, plan, scratch, device):
     """Workspace of the fused entry points: the packed flow-warped intermediate of the split
     pipeline (a few frames, L2 resident) or the coarse transform of the gather variant.  One
-    buffer per device is cached; work on one stream at a time per device or pass ``scratch``."""
+    buffer per (device, stream) is cached, so calls on different streams never share a workspace."""
     h, w = plan.region[2], plan.region[3]
     need = max(int(lib.vm_fused_scratch_bytes(n, h, w)), 256)
     if scratch is None or scratch.numel() * scratch.element_size() < need:
-        key = (device.index if device.index is not None else torch.cuda.current_device())
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        key = (idx, torch.cuda.current_stream(idx).cuda_stream)      # one workspace per (device, stream): no races
         cached = _scratch_cache.get(key)
         if cached is None or cached.numel() < need:
             cached = torch.empty(need, dtype=torch.uint8, device=device)
@@ -486,16 +420,24 @@ class HostClipRunner:
     def _as_tensor(x):
         return x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
 
-    def run(self, fg, backward, forward, bg, grids, out):
+    def run(self, fg, backward, forward, bg, grids, out, pool=None, kernels=True):
         """fg (n,H,W,4) u8, flows (n,H,W,2) f32, bg (n,H,W,3) u8 host arrays/tensors, ``grids``
-        a list of n (grid, deformed grid) pairs, ``out`` a host (n,H,W,4) float32 buffer."""
+        a list of n (grid, deformed grid) pairs, ``out`` a host (n,H,W,4) float32 buffer.
+        ``pool``: a SolverPool - the whole clip's TPS systems are then solved by its worker processes while
+        the first chunks are on the wire; otherwise each chunk is solved in this thread (stacked pinv,
+        bit-identical to the per-frame call).  ``kernels=False`` skips solve and kernels: the copy-only
+        ceiling of the same byte volume (bench.py reports it beside the end-to-end rate)."""
+        import time
         fg, backward, forward, bg, out = map(self._as_tensor, (fg, backward, forward, bg, out))
         n = fg.shape[0]
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.solve_s = 0.0
         cur = torch.cuda.current_stream(self.device)
         for s in (self.s_in, self.s_run, self.s_out):
             s.wait_stream(cur)
+        handle = pool.submit(grids) if (pool is not None and kernels) else None
+        ctrl_all = coef_all = None
         for ci, lo in enumerate(range(0, n, self.chunk)):
             hi = min(lo + self.chunk, n)
             m = hi - lo
@@ -507,18 +449,26 @@ class HostClipRunner:
                     slot[key][:m].copy_(src[lo:hi], non_blocking=True)
                     self.h2d_bytes += src[lo:hi].numel() * src.element_size()
                 slot["loaded"].record(self.s_in)
-            # host TPS solve of this chunk (reference tps.py:113-119) while its frames are on the wire
-            ctrl_h = np.stack([np.asarray(d, dtype=np.float64) for (_, d) in grids[lo:hi]])
-            coef_h = np.stack([tps_solve(d, g) for (g, d) in grids[lo:hi]])
-            self.h2d_bytes += ctrl_h.nbytes + coef_h.nbytes
+            if kernels:
+                # host TPS solve (reference tps.py:113-119) while the frames are on the wire
+                t0 = time.perf_counter()
+                if handle is not None:
+                    if ctrl_all is None:
+                        ctrl_all, coef_all = pool.collect(handle)
+                    ctrl_h, coef_h = ctrl_all[lo:hi], coef_all[lo:hi]
+                else:
+                    ctrl_h, coef_h = _host.solve_many(grids[lo:hi])
+                self.solve_s += time.perf_counter() - t0
+                self.h2d_bytes += ctrl_h.nbytes + coef_h.nbytes
             with torch.cuda.stream(self.s_run):
-                ctrl_d = torch.from_numpy(ctrl_h).to(self.device, non_blocking=True)
-                coef_d = torch.from_numpy(coef_h).to(self.device, non_blocking=True)
                 self.s_run.wait_event(slot["loaded"])
                 if ci >= 2:
                     self.s_run.wait_event(slot["drained"])        # output of chunk ci-2 copied out
-                flow_tps_composite(slot["fg"][:m], slot["fb"][:m], slot["ff"][:m], slot["bg"][:m],
-                                   ctrl_d, coef_d, plan=self.plan, out=slot["out"][:m], status=self.status)
+                if kernels:
+                    ctrl_d = torch.from_numpy(np.ascontiguousarray(ctrl_h)).to(self.device, non_blocking=True)
+                    coef_d = torch.from_numpy(np.ascontiguousarray(coef_h)).to(self.device, non_blocking=True)
+                    flow_tps_composite(slot["fg"][:m], slot["fb"][:m], slot["ff"][:m], slot["bg"][:m],
+                                       ctrl_d, coef_d, plan=self.plan, out=slot["out"][:m], status=self.status)
                 slot["computed"].record(self.s_run)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(slot["computed"])
@@ -533,15 +483,16 @@ class HostClipRunner:
 _runners = {}
 
 
-def flow_tps_composite_host(fg, backward, forward, bg, grids, out=None, chunk=4):
+def flow_tps_composite_host(fg, backward, forward, bg, grids, out=None, chunk=4, pool=None):
     """NumPy/host-tensor front end of the C4 pipeline (H2D, kernels, D2H inside).  Returns the
-    host (n,H,W,4) float32 result; synchronises before returning."""
+    host (n,H,W,4) float32 result; synchronises before returning.  ``pool``: optional SolverPool for the
+    host TPS solves."""
     n, h, w = fg.shape[:3]
     key = (h, w, chunk, torch.cuda.current_device())
     if key not in _runners:
         _runners[key] = HostClipRunner(h, w, chunk)
     if out is None:
         out = torch.empty((n, h, w, 4), dtype=torch.float32).pin_memory()
-    res = _runners[key].run(fg, backward, forward, bg, grids, out)
+    res = _runners[key].run(fg, backward, forward, bg, grids, out, pool=pool)
     torch.cuda.current_stream().synchronize()
     return res

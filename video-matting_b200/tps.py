@@ -31,8 +31,9 @@ def warp_images(from_points, to_points, images, output_region, interpolation_ord
     """Warp ``images`` by the thin-plate spline taking from_points to to_points - reference
     tps.py:14-34.  Returns a list with one warped image per input (same dtype, and the
     (x_max-x_min+1, y_max-y_min+1) shape the reference produces)."""
-    if interpolation_order != 1:
-        raise NotImplementedError("only interpolation_order=1 (the reference's only use) is implemented")
+    if interpolation_order not in (0, 1):
+        # scipy's spline orders 2..5 need its prefilter; the reference only ever passes 1 (and documents 0)
+        raise NotImplementedError("interpolation_order must be 0 (nearest) or 1 (bilinear)")
     N.require_cuda()
     plan = P.get_plan(output_region, approximate_grid)
     coarse = _coarse_for(from_points, to_points, plan)
@@ -43,7 +44,7 @@ def warp_images(from_points, to_points, images, output_region, interpolation_ord
             raise RuntimeError("invalid shape for coordinate array")      # what scipy raises
         if src.dtype not in (torch.uint8, torch.float64, torch.float32):
             raise TypeError(f"unsupported image dtype {src.dtype}")
-        out.append(N.from_device(P.tps_warp(src, coarse, plan), kind))
+        out.append(N.from_device(P.tps_warp(src, coarse, plan, order=interpolation_order), kind))
     return out
 
 
