@@ -265,7 +265,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         step(False)
     stage_info = kernel_stages(vm, lib, step, torch)
-    launches0 = lib.vm_lean_launch_count()
+    launches0 = lib.vm_lean_launch_count() + lib.vm_fuse_launch_count()
     sampler = ClockSampler(str(torch.cuda.get_device_properties(local).uuid)) if rank == 0 else None
     barrier()
     if sampler:
@@ -276,7 +276,7 @@ def run_ours(args):
         step(True)
     t1.record()
     barrier()
-    launches = int(lib.vm_lean_launch_count() - launches0)
+    launches = int(lib.vm_lean_launch_count() + lib.vm_fuse_launch_count() - launches0)
     ms_total = max_over_ranks(t0.elapsed_time(t1))
     frames = world * CLIP * args.steps
     value = frames / (ms_total / 1e3)
@@ -375,7 +375,8 @@ def run_ours(args):
                      "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": traffic.get("traffic_per_launch"), "traffic_source": traffic.get("source"),
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms,
-                     "step_frac": alg / ((ms_total / args.steps) / 1e3) / 1e9 / peak, "stages": stage_info["stages"]},
+                     "step_frac": alg / ((ms_total / args.steps) / 1e3) / 1e9 / peak, "stages": stage_info["stages"],
+                     "single_pass_kernel": stage_info.get("single_pass_kernel")},
         "e2e": e2e, "e2e_matches_device_path": same,
         "configs": cfgs,
         "gpu_launches": launches, "clocks": clocks,
@@ -389,15 +390,20 @@ def run_ours(args):
 
 
 def kernel_stages(vm, lib, step, torch):
-    """Per-kernel durations of one (untimed) step from CUDA events recorded inside the library on the launch
-    stream, with the committed ncu DRAM traffic of each kernel beside them."""
+    """Per-kernel durations of one (untimed) step of the default path (lean split pipeline, four kernels) from CUDA
+    events recorded inside the library on the launch stream, with the committed ncu DRAM traffic of each kernel
+    beside them; and, for comparison, the same step through the single-pass kernel (fused_variant 5: no
+    intermediate in HBM, but slower - DESIGN.md 5f)."""
     import ctypes
-    Nt = vm._native
+    Nt, P = vm._native, vm.pipeline
     peak, _ = measured_peak()
     traffic = load_traffic()
     names = traffic.get("kernels") or ["k_lean_coarse<25> (TPS on the coarse grid, float64)", "k_lean_boxes<1> (source box per tile)",
                                        "k_flow_warp_mask_bgra<1,2> (flow warp + consistency mask)",
                                        "k_lean_fine<1,4> (resampling + composite)"]
+    info = {"kernel": traffic.get("kernel_note") or
+            "vm_flow_tps_composite_bgra = k_lean_coarse + k_lean_boxes + k_flow_warp_mask_bgra + k_lean_fine, timed as one unit "
+            "(39 B/px is defined for the whole pipeline); the dominant kernel is k_lean_fine, see stages", "stages": []}
     try:
         Nt.set_option("lean_timing", 1)
         rows = []
@@ -408,26 +414,43 @@ def kernel_stages(vm, lib, step, torch):
             Nt.check(lib.vm_lean_stage_ms(ctypes.cast(buf, ctypes.c_void_p)))
             rows.append(list(buf))
         stage_ms = [statistics.median(col) for col in zip(*rows)]
+        stage_bpp = traffic.get("stage_algorithmic_bpp") or [0, 0, 20, 19]
+        stage_tr = traffic.get("stage_traffic") or [None] * len(stage_ms)
+        total = sum(stage_ms) or 1.0
+        for nm, ms_k, bpp, tr in zip(names, stage_ms, stage_bpp, stage_tr):
+            rec = {"kernel": nm, "ms": ms_k, "share_of_step": ms_k / total,
+                   "algorithmic_GBps": (bpp * H * W * CLIP / (ms_k / 1e3) / 1e9) if bpp else None}
+            if tr:
+                rec["dram_GBps"] = tr / (ms_k / 1e3) / 1e9
+                rec["dram_frac_of_peak"] = rec["dram_GBps"] / peak
+            info["stages"].append(rec)
     except Exception as e:          # noqa: BLE001 - stage timing is diagnostic only
-        return {"kernel": "vm_flow_tps_composite_bgra", "stages": [{"error": str(e)}]}
+        info["stages"].append({"error": str(e)})
     finally:
         Nt.set_option("lean_timing", 0)
-    stage_bpp = traffic.get("stage_algorithmic_bpp") or [0, 0, 20, 19]
-    stage_tr = traffic.get("stage_traffic") or [None] * len(stage_ms)
-    total = sum(stage_ms) or 1.0
-    stages = []
-    for nm, ms_k, bpp, tr in zip(names, stage_ms, stage_bpp, stage_tr):
-        if ms_k <= 0:
-            continue
-        rec = {"kernel": nm, "ms": ms_k, "share_of_step": ms_k / total,
-               "algorithmic_GBps": (bpp * H * W * CLIP / (ms_k / 1e3) / 1e9) if bpp else None}
-        if tr:
-            rec["dram_GBps"] = tr / (ms_k / 1e3) / 1e9
-            rec["dram_frac_of_peak"] = rec["dram_GBps"] / peak
-        stages.append(rec)
-    return {"kernel": traffic.get("kernel_note") or
-            "vm_flow_tps_composite_bgra, timed as one unit (39 B/px is defined for the whole pipeline); see stages",
-            "stages": stages}
+    try:
+        P.set_fused_variant(5)
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        for _ in range(2):
+            step(False)
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(3):
+            step(False)
+        b.record()
+        torch.cuda.synchronize()
+        ms5 = a.elapsed_time(b) / 3
+        alg = BYTES_PER_PX["c4"] * H * W * CLIP
+        info["single_pass_kernel"] = {"kernel": "k_fuse_c4<25, true, 8> (fused_variant 5: flow warp + mask + TPS + resampling + composite "
+                                      "in one persistent warp-specialised kernel, no intermediate in HBM)", "ms": ms5,
+                                      "frac": alg / (ms5 / 1e3) / 1e9 / peak, "traffic": traffic.get("single_pass_traffic_per_launch"),
+                                      "traffic_source": traffic.get("single_pass_source")}
+    except Exception as e:          # noqa: BLE001
+        info["single_pass_kernel"] = {"error": str(e)}
+    finally:
+        P.set_fused_variant(P.DEFAULT_VARIANT)
+    return info
 
 
 def bench_configs(vm, torch, dev, rank, world, barrier, max_over_ranks, peak, pool, iters=5):

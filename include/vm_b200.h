@@ -46,6 +46,8 @@ extern "C" {
 #define VM_STATUS_TPS_OUTSIDE  3   /* # TPS samples outside [0,n-1] (map_coordinates -> 0) */
 #define VM_STATUS_SLOW_TILES   4   /* # tiles of a fused kernel that took the gather path  */
 #define VM_STATUS_BAD_TABLE    5   /* # tiles skipped: axis tables inconsistent with a /2 grid */
+#define VM_STATUS_NEAR_KNIFE   6   /* # resampled colour samples within 1e-9 of a rounding boundary (SURVEY 8a-6:
+                                      these are the ones a ~1e-11 px transform difference could flip)      */
 
 int         vm_version(void);
 const char *vm_last_error_string(void);
@@ -277,12 +279,15 @@ int vm_trimap_from_matte(const void *matte, int dtype, int n, int h, int w, uint
  * the x86 wrap of -1.0 -> 255.  src: n uint16 elements as decoded (16-byte aligned), dst: n uint8.       */
 int vm_fg_from_u16(const uint16_t *src, int64_t n, uint8_t *dst, void *stream);
 
-/* Measurement hooks of the default fused path (no reference counterpart; used by bench.py).
+/* Measurement hooks of the fused paths (no reference counterpart; used by bench.py).
  * vm_lean_stage_ms: durations in ms of {spline, tile boxes, flow stage, resampling+composite}
- * of the first chunk of the last call made with "lean_timing" = 1 on the current device, after
- * the stream was synchronised.  vm_lean_launch_count: kernels launched so far by that path.  */
+ * of the first chunk of the last call of the lean split pipeline (fused_variant 4, and C3) made with
+ * "lean_timing" = 1 on the current device, after the stream was synchronised.
+ * vm_lean_launch_count / vm_fuse_launch_count: kernels launched so far by the lean pipeline / by the
+ * single-pass C4 kernel (fused_variant 5, the default).                                       */
 int       vm_lean_stage_ms(float *out4);
 long long vm_lean_launch_count(void);
+long long vm_fuse_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,7 @@ if os.environ.get("VM_TILE_H"):
     vm._native.set_option("tile_h", int(os.environ["VM_TILE_H"]))
 dev = torch.device("cuda", 0)
 fg, fb, ff, bg = bench.make_clip(torch, 1234, n, H, W, dev)
-grids = bench.make_grids(O, 1, n, H, W)
+grids = bench.make_grids(vm, 1, n, H, W)
 ctrl, coef = P.solve_grids(grids, dev)
 out = torch.empty((n, H, W, 4), dtype=torch.float32, device=dev)
 ob = torch.empty((n, H, W, 3), dtype=torch.uint8, device=dev)

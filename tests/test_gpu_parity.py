@@ -273,17 +273,25 @@ def test_augment_golden(vm, golden):
 
 # ------------------------------------------------------------------------- fused C3 / C4
 
-VARIANTS = [(4, 32), (3, 32), (0, 32), (2, 64), (2, 32), (1, 32)]   # (fused_variant, tile_h): lean, pipe, split, tiled 64, tiled 32, gather
+VARIANTS = [(5, 32), (4, 32), (3, 32), (0, 32), (2, 64), (2, 32), (1, 32)]   # (fused_variant, tile_h): fuse, lean, pipe, split, tiled 64, tiled 32, gather
 
 
-@pytest.fixture(params=VARIANTS, ids=["lean", "pipe", "split", "tiled64", "tiled32", "gather"])
+@pytest.fixture(params=VARIANTS, ids=["fuse", "lean", "pipe", "split", "tiled64", "tiled32", "gather"])
 def variant(request, vm):
     v, th = request.param
     vm.pipeline.set_fused_variant(v)
     vm._native.set_option("tile_h", th)
     yield request.param
-    vm.pipeline.set_fused_variant(4)
+    vm.pipeline.set_fused_variant(vm.pipeline.DEFAULT_VARIANT)
     vm._native.set_option("tile_h", 32)
+
+
+@pytest.fixture
+def lean(vm):
+    """the lean split pipeline (fused_variant 4) for the tests of its own knobs"""
+    vm.pipeline.set_fused_variant(4)
+    yield
+    vm.pipeline.set_fused_variant(vm.pipeline.DEFAULT_VARIANT)
 
 
 @pytest.mark.parametrize("tag", ["a", "b", "c"])
@@ -339,7 +347,7 @@ def test_fused_degenerate_grid_takes_gather_path(vm):
     try:
         out, st = P.flow_tps_composite(dev(frame[None]), dev(fb[None]), dev(ff[None]), dev(bg[None]), ctrl, coef)
     finally:
-        P.set_fused_variant(4)
+        P.set_fused_variant(P.DEFAULT_VARIANT)
     rc, ra = O.pipeline_c4(frame, fb, ff, (grid, dgrid), bg)
     got = out[0].cpu().numpy()
     assert close(got[..., 3], ra, 1e-6)
@@ -410,7 +418,7 @@ def _lean_case(h, w, n, n_ctrl, seed=300, stretch=1.0):
     return frames, np.stack([f[0] for f in flows]), np.stack([f[1] for f in flows]), grids, bgs
 
 
-def test_lean_partition_independent(vm):
+def test_lean_partition_independent(vm, lean):
     """The result must not depend on how the work is cut: frames per stage round, coarse rows per
     spline unit, resampling occupancy target, and whether a tile's source box is staged in shared
     memory (box capacity 64 entries forces every tile onto the global-gather path)."""
@@ -422,14 +430,14 @@ def test_lean_partition_independent(vm):
     base, st0 = P.flow_tps_composite(*args)
     base3, _ = P.tps_composite(args[0], args[3], ctrl, coef)
     assert int(st0[4]) < 4, "most tiles of a mild grid must take the shared-memory box path"
-    defaults = {"lean_chunk": 64, "lean_rb": 0, "lean_minb": 4, "lean_box_cap": 0, "lean_fine_rows": 8, "lean_persist": 0,
-                "lean_sub": 0, "lean_mega": 0, "lean_overlap": 0, "lean_b1_warps": 16, "lean_b1_dyr": 1, "flow_stage_layout": 0, "lean_floors": 1}
+    defaults = {"lean_chunk": 64, "lean_rb": 0, "lean_minb": 4, "lean_box_cap": 0, "lean_fine_rows": 8, "lean_sub": 0,
+                "lean_b1_warps": 16, "lean_b1_dyr": 1, "flow_stage_layout": 0, "lean_floors": 1,
+                "lean_b1_ctas": 0}
     configs = [{"lean_chunk": 1}, {"lean_chunk": 2}, {"lean_chunk": 3}, {"lean_rb": 4}, {"lean_rb": 16}, {"lean_rb": 32},
                {"lean_sub": 2}, {"lean_minb": 2}, {"lean_minb": 3}, {"lean_fine_rows": 3}, {"lean_fine_rows": 5},
-               {"lean_box_cap": 64}, {"lean_persist": 1}, {"lean_persist": 1, "lean_box_cap": 64}, {"lean_persist": 1, "lean_chunk": 2},
-               {"lean_mega": 1}, {"lean_mega": 1, "lean_chunk": 2}, {"lean_mega": 1, "lean_box_cap": 64},
-               {"lean_overlap": 1, "lean_chunk": 2, "lean_b1_warps": 6}, {"lean_b1_dyr": 0, "lean_b1_warps": 24},
-               {"flow_stage_layout": 1}, {"lean_floors": 0}, {"lean_floors": 0, "lean_box_cap": 64}]
+               {"lean_box_cap": 64}, {"lean_b1_dyr": 0, "lean_b1_warps": 24}, {"lean_b1_warps": 6, "lean_b1_ctas": 40},
+               {"flow_stage_layout": 1}, {"lean_floors": 0}, {"lean_floors": 0, "lean_box_cap": 64},
+               {"lean_chunk": 2, "lean_b1_warps": 8, "lean_box_cap": 64}]
     try:
         for cfg in configs:
             for key, v in cfg.items():
@@ -450,7 +458,7 @@ def test_lean_partition_independent(vm):
 
 
 @pytest.mark.parametrize("n_ctrl", [3, 4, 6, 8])
-def test_lean_control_point_counts_vs_oracle(vm, n_ctrl):
+def test_lean_control_point_counts_vs_oracle(vm, n_ctrl, lean):
     """N = 16 and 25 use the unrolled spline kernels, every other count the run-time one (N <= 64)."""
     h, w, n = 96, 128, 2
     P = vm.pipeline
@@ -464,7 +472,7 @@ def test_lean_control_point_counts_vs_oracle(vm, n_ctrl):
         assert np.count_nonzero(~np.isclose(out[k][..., :3], rc, rtol=RTOL, atol=1e-5)) <= 1
 
 
-def test_lean_stretched_grid_vs_oracle(vm):
+def test_lean_stretched_grid_vs_oracle(vm, lean):
     """30 % displacements: many tiles' source boxes exceed shared memory (gather path) and control points
     come close to coarse grid points (generic spline path); both must still match the oracle."""
     h, w = 256, 320
@@ -479,7 +487,7 @@ def test_lean_stretched_grid_vs_oracle(vm):
     assert int(st[5]) == 0
 
 
-def test_lean_control_point_on_grid_point(vm):
+def test_lean_control_point_on_grid_point(vm, lean):
     """A control point that coincides with a coarse grid point (r = 0: U = 0, tps.py:78-82) and one a hair
     away from it (r^2 below the log table) take the generic spline path of their unit."""
     h, w = 128, 160
@@ -499,7 +507,7 @@ def test_lean_control_point_on_grid_point(vm):
     assert np.count_nonzero(~np.isclose(got[..., :3], rc, rtol=RTOL, atol=1e-5)) <= 1
 
 
-def test_lean_stage_timing_and_launch_count(vm):
+def test_lean_stage_timing_and_launch_count(vm, lean):
     import ctypes
     h, w, n = 128, 192, 3
     P, Nt = vm.pipeline, vm._native

@@ -13,7 +13,7 @@ from . import _build
 
 VM_U8, VM_F32, VM_F64 = 0, 1, 2
 STATUS_WORDS = 8
-STATUS_INDEX_ERR, STATUS_NAN_ERR, STATUS_MASKED, STATUS_TPS_OUTSIDE, STATUS_SLOW_TILES, STATUS_BAD_TABLE = 0, 1, 2, 3, 4, 5
+STATUS_INDEX_ERR, STATUS_NAN_ERR, STATUS_MASKED, STATUS_TPS_OUTSIDE, STATUS_SLOW_TILES, STATUS_BAD_TABLE, STATUS_NEAR_KNIFE = 0, 1, 2, 3, 4, 5, 6
 
 _c = ctypes
 _P, _I, _L, _D = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_double
@@ -52,6 +52,7 @@ SIGNATURES = {
     "vm_fg_from_u16": [_P, _L, _P, _P],
     "vm_lean_stage_ms": [_P],
     "vm_lean_launch_count": [],
+    "vm_fuse_launch_count": [],
 }
 
 _lib = None
@@ -86,6 +87,7 @@ def load(build_if_missing=True):
     lib.vm_last_error_string.restype = _c.c_char_p
     lib.vm_fused_scratch_bytes.restype = _c.c_int64
     lib.vm_lean_launch_count.restype = _c.c_longlong
+    lib.vm_fuse_launch_count.restype = _c.c_longlong
     _lib = lib
     return lib
 

@@ -26,15 +26,13 @@ int vm_launch_flow_stage(const uint8_t *fg, const float *backward, const float *
                          void *packed, int32_t *status, cudaStream_t st, bool raw_ta);     // vm_flow.cu
 
 int g_vl_chunk = 64;         // frames per A/B1/B2 round
-int g_vl_overlap = 0;        // run B1 on a side stream next to stage A
 int g_vl_rb = 0;             // coarse rows per B1 unit (0 = pick on the host)
 int g_vl_fine_rows = 8;      // fine rows per B2 thread
 int g_vl_timing = 0;         // 1: bracket the stages of the first chunk of every call with CUDA events (vm_lean_stage_ms)
 static cudaEvent_t g_vl_tev[64][5];
+static int g_vl_tpair[64][4][2];                  // event indices bracketing {spline, tile boxes, flow stage, resampling}
 static bool g_vl_tev_ok[64];
 static std::atomic<long long> g_vl_launches{0};   // kernels launched by this library's lean path (bench.py "gpu_launches")
-int g_vl_mega = 0;           // 1 (C4 only): flow stage + resampling in one dependency-driven persistent kernel (k_lean_mega)
-int g_vl_persist = 0;        // 1: persistent double-buffered resampling kernel (k_lean_fine_p); 0: one CTA per tile (k_lean_fine)
 int g_vl_sub = 0;            // frames per flow-stage / resampling sub-round inside a round (0: the whole round)
 int g_vl_box_cap = 0;        // source-box entries per B2 tile (0: as many as the occupancy target allows)
 int g_vl_floors = 1;         // 1: the spline stage also writes packed int16 floors of T for the tile-box stage
@@ -44,8 +42,6 @@ __device__ double2 g_vl_tab[VL_TAB_N];
 
 static std::mutex g_vl_mu;
 static bool g_vl_done[64];
-static cudaStream_t g_vl_side[64];
-static cudaEvent_t g_vl_ev_fork[64], g_vl_ev_ready[64][2], g_vl_ev_free[64][2];
 
 static int vl_init(int *dev_out) {
     int dev = 0;
@@ -65,23 +61,24 @@ static int vl_init(int *dev_out) {
             t.x = ldexp(inv, -e);
             t.y = (double)((long double)e * 0.693147180559945309417232121458L - logl((long double)inv));
         }
-    cudaError_t err = cudaMemcpyToSymbol(g_vl_tab, tab, sizeof(tab));
-    if (err == cudaSuccess) {                      // side stream at the highest priority: its persistent CTAs must get their
-        int lo = 0, hi = 0;                        // slice of every SM as soon as CTAs of the caller's stream retire
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        err = cudaStreamCreateWithPriority(&g_vl_side[dev], cudaStreamNonBlocking, hi);
-    }
-    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&g_vl_ev_fork[dev], cudaEventDisableTiming);
-    for (int k = 0; k < 2 && err == cudaSuccess; ++k) {
-        err = cudaEventCreateWithFlags(&g_vl_ev_ready[dev][k], cudaEventDisableTiming);
-        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&g_vl_ev_free[dev][k], cudaEventDisableTiming);
-    }
+    const cudaError_t err = cudaMemcpyToSymbol(g_vl_tab, tab, sizeof(tab));
     if (err != cudaSuccess) {
         vm_set_error("vm_lean: init: %s", cudaGetErrorString(err));
         return VM_ERR_CUDA;
     }
     g_vl_done[dev] = true;
     return VM_OK;
+}
+
+// the log table for other translation units (vm_fuse.cu): make sure it is uploaded / return its device address
+int vl_table_init() { int dev = 0; return vl_init(&dev); }
+const void *vl_table_device() {
+    static void *addr[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    void *&p = addr[dev & 63];
+    if (!p) cudaGetSymbolAddress(&p, g_vl_tab);
+    return p;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -296,6 +293,7 @@ k_lean_coarse(const double *__restrict__ ctrl, const double *__restrict__ coef, 
 
 // rows per unit: minimise (waves of units over the persistent warps) x (rows + set-up cost)
 int g_vl_b1_warps = VL_B1_WARPS;
+int g_vl_b1_ctas = 0;        // persistent CTAs of the spline stage (0: one per SM)
 int g_vl_b1_dyr = 1;         // 1: dy^2 in registers / <= 16 warps per SM; 0: recomputed / <= 24 warps per SM
 
 static int vl_pick_rb(int n, int nx, int ny, int ctas) {
@@ -331,7 +329,7 @@ static int vl_launch_coarse(const double *ctrl, const double *coef, int N, int n
         vm_set_error("vm_lean: cudaMemsetAsync failed");
         return VM_ERR_CUDA;
     }
-    const int ctas = vl_sm_count();
+    const int ctas = g_vl_b1_ctas > 0 ? g_vl_b1_ctas : vl_sm_count();
     const int warps_cta = g_vl_b1_dyr ? (g_vl_b1_warps < VL_B1_WARPS ? g_vl_b1_warps : VL_B1_WARPS) : g_vl_b1_warps;
     const int rb = vl_pick_rb(n, nx, ny, ctas);
     const int nbands = (nx + rb - 1) / rb, ncb = (ny + 31) / 32;
@@ -726,364 +724,118 @@ k_lean_fine(const void *__restrict__ src_all, const uint8_t *__restrict__ bg, in
 }
 
 // ---------------------------------------------------------------------------------------
-// Stage A + stage B2 in one persistent kernel ("mega", option lean_mega, off by default: measured 78 us
-// per frame against 45 us for the separate kernels - CTAs spin on the frame dependency because their
-// progress drifts apart by more than the two-frame lag, and the packed frames still reach DRAM because
-// every frame has its own region, so dirty lines are written back): every CTA walks a fixed,
-// interleaved list of work items - flow-stage units of frame s and resampling tiles of frame s-2 -
-// so the packed intermediate of a frame is consumed from L2 two frames after it was produced and
-// never makes the round trip through HBM.  A tile of frame f waits until all flow-stage units of
-// frame f have been published (release: __threadfence + atomicAdd; acquire: volatile load +
-// __threadfence).  Items are taken in increasing order by every CTA and the units a tile depends on
-// come earlier in the list, so the wait cannot deadlock as long as every CTA of the grid is resident
-// (the host sizes the grid with the occupancy API).
-// ---------------------------------------------------------------------------------------
-#define VL_MEGA_LAG 2
-
-template <bool HAS_FWD>
-__global__ void __launch_bounds__(VL_FW * VL_FS, 4)
-k_lean_mega(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd, const float2 *__restrict__ fwd,
-            uint2 *__restrict__ packed, const uint8_t *__restrict__ bg, int n_bg, int frame0,
-            const double2 *__restrict__ T, int nx, int ny, const vm_axis_entry *__restrict__ rows,
-            const vm_axis_entry *__restrict__ cols, int h, int w, int n, int rpt,
-            const VlTileBox *__restrict__ boxes, float4 *__restrict__ out, int32_t *__restrict__ status,
-            unsigned int *__restrict__ frame_done) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    VlFineSmem &S = *reinterpret_cast<VlFineSmem *>(smem_raw);
-    const int tid = threadIdx.y * VL_FW + threadIdx.x;
-    const int atx = (w + C2_TW - 1) / C2_TW, aty = (h + C2_ROWS - 1) / C2_ROWS, nA = atx * aty;      // flow-stage units per frame
-    const int btx = (w + VL_FW - 1) / VL_FW, bty = (h + VL_FS * rpt - 1) / (VL_FS * rpt), nB = btx * bty;   // tiles per frame
-    const int P = nA + nB;
-    const int64_t total = (int64_t)(n + VL_MEGA_LAG) * P;
-    vl_bar_init(S);
-    uint32_t phase = 0;
-    int outside = 0, slow = 0;
-    for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
-        const int slot = (int)(item / P), k = (int)(item - (int64_t)slot * P);
-        // Bresenham interleave of nA units among P positions
-        const int a_before = (int)(((int64_t)k * nA) / P), a_after = (int)(((int64_t)(k + 1) * nA) / P);
-        if (a_after > a_before) {                                       // ---- flow-stage unit a_before of frame `slot`
-            if (slot >= n) continue;
-            const int ty = a_before / atx, tx = a_before - ty * atx;
-            // the 2-D thread index of this kernel is irrelevant to the unit: it uses threadIdx.x of a 256-thread CTA
-            vm_flow_unit_flat<HAS_FWD>(fg, bwd, fwd, h, w, slot, ty, tx, tid, packed, status);
-            __syncthreads();
-            if (tid == 0) {
-                __threadfence();
-                atomicAdd(frame_done + slot, 1u);
-            }
-        } else {                                                        // ---- resampling tile (k - a_before) of frame slot - LAG
-            const int f = slot - VL_MEGA_LAG;
-            if (f < 0) continue;
-            const int b = k - a_before;
-            const int by = b / btx, bx = b - by * btx;
-            if (tid == 0) {
-                while (*reinterpret_cast<volatile unsigned int *>(frame_done + f) < (unsigned)nA) __nanosleep(200);
-                __threadfence();
-            }
-            __syncthreads();                                            // (also: everybody is done with the previous tile's buffers)
-            const VlTileBox rec = boxes[((int64_t)f * bty + by) * btx + bx];
-            vl_fine_tile<1, true>(S, phase, packed, bg, n_bg, frame0, T, nx, ny, rows, cols, h, w, rpt, rec, f, by, bx, out, outside, slow);
-            __syncthreads();
-        }
-    }
-    if (status) {
-        if (outside) atomicAdd(status + VM_STATUS_TPS_OUTSIDE, outside);
-        if (slow) atomicAdd(status + VM_STATUS_SLOW_TILES, slow);
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// stage B2, persistent variant (default): the same tile work as k_lean_fine, but every CTA walks a
-// contiguous run of 64 x 32 tiles and the bulk async copies of tile i+1 (coarse window, source box,
-// background rows, axis entries) are in flight while tile i is resampled, so no warp waits for DRAM
-// in steady state.  512 threads (64 columns x 8 strips of 4 rows), 2 CTAs per SM, double-buffered
-// box / background / axis entries, single-buffered coarse window (refilled as soon as the tile's
-// column-interpolated rows have been formed).  Everything a tile needs to issue its copies comes from
-// one 32-byte record written by k_lean_recs.
-// ---------------------------------------------------------------------------------------
-#define VL_PS 8                                    // strips per CTA
-#define VL_PR 4                                    // rows per thread and tile
-#define VL_PTH (VL_PS * VL_PR)                     // tile height (32)
-#define VL_PTR (VL_PTH / 2 + 4)                    // coarse rows staged per tile of the persistent kernel (20)
-
-// rmin/bh/cmin/bw: source box (bw = 0: taps from global memory); kr0/nkr/kc0/nkc: coarse window
-// (nkr = 0: axis tables are not monotone windows -> fully generic tile)
-struct __align__(16) VlTileRec { int rmin, bh, cmin, bw, kr0, nkr, kc0, nkc; };
-
-struct __align__(16) VlPSmem {
-    double2 T[VL_PTR * VL_TC];
-    double2 Cs[VL_PTR * VL_FW];
-    unsigned char bgt[2][VL_PTH * VL_FW * 3];
-    vm_axis_entry rows[2][VL_PTH];
-    vm_axis_entry cols[2][VL_FW];
-    VlTileRec rec[2];
-    unsigned long long bar[2];
-    uint2 box[2];                                  // 2 x box_cap entries (dynamic)
-};
-static inline size_t vl_p_smem_bytes(int box_cap) { return sizeof(VlPSmem) + (size_t)(2 * box_cap - 2) * sizeof(uint2); }
-
-template <int SRC>
-__global__ void __launch_bounds__(128)
-k_lean_recs(const double2 *__restrict__ T, int nx, int ny, const vm_axis_entry *__restrict__ rows,
-            const vm_axis_entry *__restrict__ cols, int h, int w, int tiles_x, int tiles_y, int n_tiles,
-            int box_cap, VlTileRec *__restrict__ recs) {
-    constexpr int EPV = 16 / (int)sizeof(typename VlSrc<SRC>::elem);
-    const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (t >= n_tiles) return;
-    const int per = tiles_x * tiles_y;
-    const int frame = t / per, tl = t - frame * per;
-    const int ty = tl / tiles_x, tx = tl - ty * tiles_x;
-    const int I0 = ty * VL_PTH, J0 = tx * VL_FW;
-    const int th = min(VL_PTH, h - I0), tw = min(VL_FW, w - J0);
-    const vm_axis_entry r0 = vm_ld_axis(rows + I0), r1 = vm_ld_axis(rows + I0 + th - 1);
-    const vm_axis_entry c0 = vm_ld_axis(cols + J0), c1 = vm_ld_axis(cols + J0 + tw - 1);
-    const int kr0 = r0.i0, kr1 = max(r1.i1, r1.i0), kc0 = c0.i0, kc1 = max(c1.i1, c1.i0);
-    const int nkr = kr1 - kr0 + 1, nkc = kc1 - kc0 + 1;
-    VlTileRec rec = {0, 0, 0, 0, 0, 0, 0, 0};
-    bool ok = nkr >= 1 && nkc >= 1 && nkr <= VL_PTR && nkc <= VL_TC && kr0 >= 0 && kr1 < nx && kc0 >= 0 && kc1 < ny;
-    if (ok) {                                      // every (i0, i1) of the tile inside the window
-        for (int i = lane; i < th; i += 32) {
-            const vm_axis_entry e = vm_ld_axis(rows + I0 + i);
-            ok = ok && e.i0 >= kr0 && e.i0 <= kr1 && e.i1 >= kr0 && e.i1 <= kr1;
-        }
-        for (int j = lane; j < tw; j += 32) {
-            const vm_axis_entry e = vm_ld_axis(cols + J0 + j);
-            ok = ok && e.i0 >= kc0 && e.i0 <= kc1 && e.i1 >= kc0 && e.i1 <= kc1;
-        }
-    }
-    ok = __all_sync(0xffffffffu, ok);
-    if (ok) {
-        rec.kr0 = kr0; rec.nkr = nkr; rec.kc0 = kc0; rec.nkc = nkc;
-        const int64_t woff = (int64_t)frame * nx * ny + (int64_t)kr0 * ny + kc0;
-        const double2 *Tf = T + woff;
-        const int *F = nullptr;                                          // the record stage reads T itself
-        int rlo = INT_MAX, rhi = INT_MIN, clo = INT_MAX, chi = INT_MIN, bad = 0;
-        if (F && nkr <= VL_TR && nkc <= 64) {                            // packed floors written by the spline stage:
-            const int *Ff = F + woff;                                    // every load of the window is issued before the
-            int v[VL_TR][2];                                             // first one is used (the stage is latency bound)
-#pragma unroll
-            for (int r = 0; r < VL_TR; ++r)
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const int c = lane + 32 * g;
-                    v[r][g] = (r < nkr && c < nkc) ? __ldg(Ff + (int64_t)r * ny + c) : 0x7FFF7FFF;     // 0x7FFF7FFF: no point
-                }
-#pragma unroll
-            for (int r = 0; r < VL_TR; ++r)
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const int x = v[r][g];
-                    if (x == VL_FLOOR_BAD) bad = 1;
-                    else if (x != 0x7FFF7FFF) {
-                        const int f0 = (int)(short)(x & 0xFFFF), f1 = x >> 16;
-                        rlo = min(rlo, f0); rhi = max(rhi, f0); clo = min(clo, f1); chi = max(chi, f1);
-                    }
-                }
-        } else {
-            for (int r = 0; r < nkr; ++r)
-                for (int c = lane; c < nkc; c += 32) {
-                    const double2 v = __ldg(Tf + (int64_t)r * ny + c);
-                    if (!(fabs(v.x) < 1.0e9) || !(fabs(v.y) < 1.0e9)) bad = 1;
-                    else {
-                        const int f0 = __double2int_rd(v.x), f1 = __double2int_rd(v.y);
-                        rlo = min(rlo, f0); rhi = max(rhi, f0); clo = min(clo, f1); chi = max(chi, f1);
-                    }
-                }
-        }
-        rlo = __reduce_min_sync(0xffffffffu, rlo); rhi = __reduce_max_sync(0xffffffffu, rhi);
-        clo = __reduce_min_sync(0xffffffffu, clo); chi = __reduce_max_sync(0xffffffffu, chi);
-        bad = __reduce_max_sync(0xffffffffu, bad);
-        // rows [rmin, rmax] x columns [cmin, cmin + bw) hold every tap of every in-frame fast pixel
-        const int rmin = max(rlo, 0), rmax = min(rhi + 1, h - 1);
-        int cmin = max(clo, 0) & ~(EPV - 1);
-        const int cmax = min(chi + 1, w - 1);
-        const int bh = rmax - rmin + 1;
-        const int bw = (cmax - cmin + 1 + EPV - 1) & ~(EPV - 1);
-        if (cmin + bw > w) cmin = w - bw;
-        if (!bad && bh >= 1 && bw >= EPV && cmin >= 0 && (w & (EPV - 1)) == 0 && bh * bw <= box_cap) {
-            rec.rmin = rmin; rec.bh = bh; rec.cmin = cmin; rec.bw = bw;
-        }
-    }
-    if (lane == 0) recs[t] = rec;
-}
-
-
-template <int SRC>
-__global__ void __launch_bounds__(VL_FW * VL_PS, 2)
-k_lean_fine_p(const void *__restrict__ src_all, const uint8_t *__restrict__ bg, int n_bg, int frame0,
-              const double2 *__restrict__ T, int nx, int ny, const vm_axis_entry *__restrict__ rows,
-              const vm_axis_entry *__restrict__ cols, int h, int w, int tiles_x, int tiles_y, int n_tiles,
-              int tiles_per_cta, int box_cap, const VlTileRec *__restrict__ recs, float4 *__restrict__ out,
-              int32_t *__restrict__ status) {
-    typedef typename VlSrc<SRC>::elem elem;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    VlPSmem &S = *reinterpret_cast<VlPSmem *>(smem_raw);
-    const int x = threadIdx.x, strip = threadIdx.y;
-    const int tid = strip * VL_FW + x;
-    const bool issuer = tid < 32;                                       // warp 0 issues the bulk copies
-    const int t_begin = blockIdx.x * tiles_per_cta, t_end = min(t_begin + tiles_per_cta, n_tiles);
-    if (t_begin >= t_end) return;
-    const uint32_t bar[2] = {vl_smem_u32(&S.bar[0]), vl_smem_u32(&S.bar[1])};
-    const bool bulk_bg = (w & 15) == 0 && (reinterpret_cast<uintptr_t>(bg) & 15) == 0;
-    const bool src_al = (reinterpret_cast<uintptr_t>(src_all) & 15) == 0;
-    const int64_t hw = (int64_t)h * w;
-
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar[0]));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar[1]));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-
-    // tile coordinates as running counters (no division per tile)
-    const int per = tiles_x * tiles_y;
-    int frame = t_begin / per, ty = (t_begin - frame * per) / tiles_x, tx = t_begin - frame * per - ty * tiles_x;
-    int nframe = frame, nty = ty, ntx = tx;                             // coordinates of the tile being prefetched
-    auto advance = [&](int &f, int &yy, int &xx) { if (++xx == tiles_x) { xx = 0; if (++yy == tiles_y) { yy = 0; ++f; } } };
-
-    // issue every bulk copy of tile (f, yy, xx) with record r into buffer b; `with_T`: the coarse window too
-    auto issue = [&](const VlTileRec &r, int f, int yy, int xx, int b, bool with_T, bool rest) {
-        const int I0 = yy * VL_PTH, J0 = xx * VL_FW;
-        const int th = min(VL_PTH, h - I0), tw = min(VL_FW, w - J0);
-        const bool staged = r.nkr > 0;
-        const bool boxed = staged && r.bw > 0 && src_al;
-        const bool bg_sm = staged && bulk_bg && tw == VL_FW;
-        if (rest && tid == 0) {
-            S.rec[b] = r;
-            uint32_t bytes = 0;
-            if (staged) bytes = (uint32_t)(r.nkr * r.nkc * 16) + (uint32_t)((th + tw) * 16) +
-                                (boxed ? (uint32_t)(r.bh * r.bw * (int)sizeof(elem)) : 0u) + (bg_sm ? (uint32_t)(th * VL_FW * 3) : 0u);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar[b]), "r"(bytes) : "memory");
-        }
-        __syncwarp();
-        if (!staged) return;
-        if (rest) {
-            if (tid == 0) {
-                vl_bulk_g2s(vl_smem_u32(S.rows[b]), rows + I0, (uint32_t)(th * 16), bar[b]);
-                vl_bulk_g2s(vl_smem_u32(S.cols[b]), cols + J0, (uint32_t)(tw * 16), bar[b]);
-            }
-            if (boxed) {
-                elem *boxp = reinterpret_cast<elem *>(S.box + (size_t)b * box_cap);
-                const uint32_t row_bytes = (uint32_t)(r.bw * (int)sizeof(elem));
-                const elem *g = reinterpret_cast<const elem *>(src_all) + (int64_t)f * hw + (int64_t)r.rmin * w + r.cmin;
-                for (int k = tid; k < r.bh; k += 32) vl_bulk_g2s(vl_smem_u32(boxp + k * r.bw), g + (int64_t)k * w, row_bytes, bar[b]);
-            }
-            if (bg_sm) {
-                int bgi = frame0 + f;
-                if (bgi >= n_bg) bgi %= n_bg;
-                const uint8_t *g = bg + ((int64_t)bgi * hw + (int64_t)I0 * w + J0) * 3;
-                for (int k = tid; k < th; k += 32) vl_bulk_g2s(vl_smem_u32(S.bgt[b] + k * (VL_FW * 3)), g + (int64_t)k * w * 3, VL_FW * 3, bar[b]);
-            }
-        }
-        if (with_T) {
-            const double2 *g = T + (int64_t)f * nx * ny + (int64_t)r.kr0 * ny + r.kc0;
-            for (int k = tid; k < r.nkr; k += 32) vl_bulk_g2s(vl_smem_u32(S.T + k * VL_TC), g + (int64_t)k * ny, (uint32_t)(r.nkc * 16), bar[b]);
-        }
-    };
-
-    VlTileRec rnext = {0, 0, 0, 0, 0, 0, 0, 0};                          // record of tile t + 1 (warp 0 only)
-    if (issuer) {
-        const VlTileRec r0 = recs[t_begin];
-        issue(r0, frame, ty, tx, 0, true, true);
-        if (t_begin + 1 < t_end) rnext = recs[t_begin + 1];
-    }
-    advance(nframe, nty, ntx);
-
-    int outside = 0, slow = 0;
-    for (int t = t_begin, i = 0; t < t_end; ++t, ++i) {
-        const int b = i & 1;
-        // ---- S0: tile t has landed ---------------------------------------------------------
-        if (issuer) vl_mbar_wait_parity(bar[b], (uint32_t)((i >> 1) & 1));
-        __syncthreads();                                                // also: everybody is done with tile t-1
-        if (!issuer) vl_mbar_wait_parity(bar[b], (uint32_t)((i >> 1) & 1));   // completes at once: orders the async writes
-        const VlTileRec rec = S.rec[b];
-        const int I0 = ty * VL_PTH, J0 = tx * VL_FW;
-        const int th = min(VL_PTH, h - I0), tw = min(VL_FW, w - J0);
-        const bool staged = rec.nkr > 0;
-        // ---- S1: column-interpolated coarse rows -----------------------------------------------
-        if (staged && x < tw) {
-            const vm_axis_entry ce = S.cols[b][x];
-            const double yf = ce.frac, y1 = 1.0 - yf;
-            const double2 *Ta = S.T + (ce.i0 - rec.kc0), *Tb = S.T + (ce.i1 - rec.kc0);
-            for (int k = strip; k < rec.nkr; k += VL_PS) {
-                const VlC c = vl_col_lerp(Ta[k * VL_TC], Tb[k * VL_TC], y1, yf);
-                S.Cs[k * VL_FW + x] = make_double2(c.x, c.y);
-            }
-        }
-        __syncthreads();                                                // Cs complete, S.T free again
-        // ---- S2: prefetch tile t + 1 (its buffer was last read while tile t - 1 was resampled) ---------
-        if (issuer && t + 1 < t_end) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic reads of S.T / buffer b^1 before the async writes
-            issue(rnext, nframe, nty, ntx, b ^ 1, true, true);
-            if (t + 2 < t_end) rnext = recs[t + 2];
-        }
-        // ---- S3: resample + composite the thread's rows ---------------------------------------------
-        const int r_first = strip * VL_PR;
-        const int nrows = min(VL_PR, th - r_first);
-        if (x < tw && nrows > 0) {
-            const elem *src = reinterpret_cast<const elem *>(src_all) + (int64_t)frame * hw;
-            int bgi = frame0 + frame;
-            if (bgi >= n_bg) bgi %= n_bg;
-            const int64_t p0 = (int64_t)(I0 + r_first) * w + J0 + x;
-            const uint8_t *bgp = bg + ((int64_t)bgi * hw + p0) * 3;
-            float4 *op = out + (int64_t)frame * hw + p0;
-            if (!staged) {
-                const vm_axis_entry ce = vm_ld_axis(cols + J0 + x);
-                const double2 *Tf = T + (int64_t)frame * nx * ny;
-                vl_strip_generic<SRC>(src, Tf + ce.i0, Tf + ce.i1, ny, rows + I0 + r_first, ce.frac, bgp, op, nrows, h, w, &outside);
-            } else {
-                const bool boxed = rec.bw > 0 && src_al;
-                const bool bg_sm = bulk_bg && tw == VL_FW;
-                const elem *boxp = reinterpret_cast<const elem *>(S.box + (size_t)b * box_cap);
-                const unsigned char *bgl = S.bgt[b] + (r_first * VL_FW + x) * 3;
-                const double2 *Csj = S.Cs + x;
-                const vm_axis_entry *rp = S.rows[b] + r_first;
-                if (boxed && bg_sm) vl_strip_tile<SRC, true, true>(src, boxp, rec.rmin, rec.cmin, rec.bw, Csj, rec.kr0, rp, bgl, bgp, op, nrows, h, w, &outside);
-                else if (boxed)     vl_strip_tile<SRC, true, false>(src, boxp, rec.rmin, rec.cmin, rec.bw, Csj, rec.kr0, rp, bgl, bgp, op, nrows, h, w, &outside);
-                else                vl_strip_tile<SRC, false, false>(src, boxp, 0, 0, 0, Csj, rec.kr0, rp, bgl, bgp, op, nrows, h, w, &outside);
-            }
-        }
-        if (tid == 0 && !(staged && rec.bw > 0 && src_al)) ++slow;
-        advance(frame, ty, tx);
-        advance(nframe, nty, ntx);
-    }
-    if (status) {
-        if (outside) atomicAdd(status + VM_STATUS_TPS_OUTSIDE, outside);
-        if (slow) atomicAdd(status + VM_STATUS_SLOW_TILES, slow);
-    }
-}
-
-// ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 static inline int64_t vl_align(int64_t v) { return (v + 255) & ~(int64_t)255; }
 
+// scratch of one slot of `m` frames: packed flow-warped frames, coarse transform, packed floors, tile boxes, counter
+struct VlSlot { void *packed; double2 *T; int *F; VlTileBox *boxes; unsigned int *counter; };
+static int64_t vl_slot_bytes(int m, int h, int w) {
+    const int64_t tiles = (int64_t)m * ((w + VL_FW - 1) / VL_FW) * ((h + 3) / 4);     // >= tiles for any rows-per-thread setting
+    const int64_t cp = (int64_t)m * (h / 2 + 1) * (w / 2 + 1);
+    return 256 + vl_align((int64_t)m * h * w * 8) + vl_align(cp * 16) + vl_align(cp * 4) + vl_align(tiles * 16);
+}
+static VlSlot vl_slot_at(unsigned char *base, int m, int h, int w) {
+    const int64_t tiles = (int64_t)m * ((w + VL_FW - 1) / VL_FW) * ((h + 3) / 4);
+    const int64_t cp = (int64_t)m * (h / 2 + 1) * (w / 2 + 1);
+    VlSlot s;
+    s.counter = reinterpret_cast<unsigned int *>(base); base += 256;
+    s.packed = base; base += vl_align((int64_t)m * h * w * 8);
+    s.T = reinterpret_cast<double2 *>(base); base += vl_align(cp * 16);
+    s.F = reinterpret_cast<int *>(base); base += vl_align(cp * 4);
+    s.boxes = reinterpret_cast<VlTileBox *>(base);
+    (void)tiles;
+    return s;
+}
+
 int64_t vm_lean_scratch_bytes(int n, int h, int w) {
     const int m = n < g_vl_chunk ? n : g_vl_chunk;
-    const int64_t tiles = (int64_t)m * ((w + VL_FW - 1) / VL_FW) * ((h + 3) / 4);     // >= tiles for any rows-per-thread setting
-    return 512 + vl_align((int64_t)m * h * w * 8) +
-           (g_vl_overlap ? 2 : 1) * (vl_align((int64_t)m * (h / 2 + 1) * (w / 2 + 1) * 16) + vl_align(tiles * 16)) +
-           vl_align((int64_t)m * 4);
+    return 512 + vl_slot_bytes(m, h, w);
 }
 
 int vm_lean_set_option(const char *key, int value) {
     if (!strcmp(key, "lean_chunk") && value >= 1 && value <= 4096) { g_vl_chunk = value; return VM_OK; }
-    if (!strcmp(key, "lean_overlap") && value >= 0 && value <= 1) { g_vl_overlap = value; return VM_OK; }
     if (!strcmp(key, "lean_rb") && value >= 0 && value <= 64) { g_vl_rb = value; return VM_OK; }
     if (!strcmp(key, "lean_b1_warps") && value >= 1 && value <= VL_B1_WARPS_HI) { g_vl_b1_warps = value; return VM_OK; }
     if (!strcmp(key, "lean_b1_dyr") && value >= 0 && value <= 1) { g_vl_b1_dyr = value; return VM_OK; }
     if (!strcmp(key, "lean_timing") && value >= 0 && value <= 1) { g_vl_timing = value; return VM_OK; }
-    if (!strcmp(key, "lean_mega") && value >= 0 && value <= 1) { g_vl_mega = value; return VM_OK; }
-    if (!strcmp(key, "lean_persist") && value >= 0 && value <= 1) { g_vl_persist = value; return VM_OK; }
     if (!strcmp(key, "lean_sub") && value >= 0 && value <= 4096) { g_vl_sub = value; return VM_OK; }
     if (!strcmp(key, "lean_box_cap") && value >= 0 && value <= 16384) { g_vl_box_cap = value; return VM_OK; }
     if (!strcmp(key, "lean_minb") && (value >= 2 && value <= 6 || value == 8)) { g_vl_minb = value; return VM_OK; }
     if (!strcmp(key, "lean_fine_rows") && value >= 1 && value <= 256) { g_vl_fine_rows = value; return VM_OK; }
     if (!strcmp(key, "lean_floors") && (value == 0 || value == 1)) { g_vl_floors = value; return VM_OK; }
+    if (!strcmp(key, "lean_b1_ctas") && value >= 0 && value <= 4096) { g_vl_b1_ctas = value; return VM_OK; }
     return VM_ERR_ARG;
+}
+
+// geometry shared by the launches of one call
+struct VlCall {
+    int mode, N, nx, ny, n_bg, h, w, rpt, box_cap;
+    double step_x, step_y;
+    const uint8_t *fg, *bg;
+    const float *backward, *forward;
+    const double *ctrl, *coef;
+    const vm_axis_entry *rows, *cols;
+    float *out;
+    int32_t *status;
+    size_t fine_smem;
+    const char *what;
+};
+
+// spline on the coarse grid of frames [f0, f0 + m) into slot `sl`
+static int *vl_floors_ptr(const VlCall &c, const VlSlot &sl, bool floors_in_packed) {
+    return g_vl_floors && c.h <= 32766 && c.w <= 32766 ? (floors_in_packed ? reinterpret_cast<int *>(sl.packed) : sl.F) : nullptr;
+}
+static int vl_enqueue_coarse(const VlCall &c, const VlSlot &sl, int f0, int m, bool floors_in_packed, cudaStream_t st) {
+    g_vl_launches += 1;
+    return vl_launch_coarse(c.ctrl + (int64_t)f0 * c.N * 2, c.coef + (int64_t)f0 * (c.N + 3) * 2, c.N, m, c.nx, c.ny, c.step_x, c.step_y,
+                            sl.T, vl_floors_ptr(c, sl, floors_in_packed), sl.counter, st);
+}
+// source box of every resampling tile of the slot's m frames
+static int vl_enqueue_boxes(const VlCall &c, const VlSlot &sl, int m, bool floors_in_packed, cudaStream_t st) {
+    int *F = vl_floors_ptr(c, sl, floors_in_packed);
+    const dim3 grid((c.w + VL_FW - 1) / VL_FW, (c.h + VL_FS * c.rpt - 1) / (VL_FS * c.rpt), m);
+    const int n_tiles = (int)(grid.x * grid.y * m);
+    if (c.mode != 0) k_lean_boxes<1><<<(n_tiles + 3) / 4, 128, 0, st>>>(sl.T, F, c.nx, c.ny, c.rows, c.cols, c.h, c.w, c.rpt, grid.x, grid.y, n_tiles, c.box_cap, sl.boxes);
+    else             k_lean_boxes<0><<<(n_tiles + 3) / 4, 128, 0, st>>>(sl.T, F, c.nx, c.ny, c.rows, c.cols, c.h, c.w, c.rpt, grid.x, grid.y, n_tiles, c.box_cap, sl.boxes);
+    g_vl_launches += 1;
+    return vm_check_launch("vm_lean box stage");
+}
+
+static int vl_enqueue_flow(const VlCall &c, const VlSlot &sl, int f0, int m, cudaStream_t st) {
+    const int64_t px = (int64_t)c.h * c.w;
+    g_vl_launches += 1;
+    return vm_launch_flow_stage(c.fg + f0 * px * 4, c.backward + f0 * px * 2, (c.mode == 2 && c.forward) ? c.forward + f0 * px * 2 : nullptr,
+                                m, c.h, c.w, sl.packed, c.status, st, true);
+}
+
+// resampling + composite of frames [f0, f0 + m); the slot's T / boxes start at frame `fs` of the slot
+static int vl_enqueue_fine(const VlCall &c, const VlSlot &sl, int f0, int fs, int m, cudaStream_t st) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int64_t px = (int64_t)c.h * c.w;
+    const dim3 block(VL_FW, VL_FS), sgrid((c.w + VL_FW - 1) / VL_FW, (c.h + VL_FS * c.rpt - 1) / (VL_FS * c.rpt), m);
+    const int64_t tiles_per_frame = (int64_t)sgrid.x * sgrid.y;
+    const double2 *Ts = sl.T + (int64_t)fs * c.nx * c.ny;
+    const VlTileBox *bs = sl.boxes + fs * tiles_per_frame;
+    float4 *o4 = reinterpret_cast<float4 *>(c.out) + f0 * px;
+    const void *src = c.mode != 0 ? (const void *)(reinterpret_cast<const uint2 *>(sl.packed) + fs * px) : (const void *)(c.fg + f0 * px * 4);
+    const size_t fine_smem = c.fine_smem;
+#define VL_FINE(S, MB)                                                                                              \
+    do {                                                                                                            \
+        static size_t attr_set[64];                                                                                 \
+        if (attr_set[dev & 63] < fine_smem) {                                                                       \
+            cudaError_t e = cudaFuncSetAttribute(k_lean_fine<S, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fine_smem); \
+            if (e != cudaSuccess) { vm_set_error("vm_lean: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VM_ERR_CUDA; } \
+            attr_set[dev & 63] = fine_smem;                                                                         \
+        }                                                                                                           \
+        k_lean_fine<S, MB><<<sgrid, block, fine_smem, st>>>(src, c.bg, c.n_bg, f0, Ts, c.nx, c.ny, c.rows, c.cols, c.h, c.w, c.rpt, bs, o4, c.status); \
+    } while (0)
+    if (c.mode != 0) { if (g_vl_minb == 8) VL_FINE(1, 8); else if (g_vl_minb == 6) VL_FINE(1, 6); else if (g_vl_minb == 5) VL_FINE(1, 5); else if (g_vl_minb == 4) VL_FINE(1, 4); else if (g_vl_minb == 3) VL_FINE(1, 3); else VL_FINE(1, 2); }
+    else             { if (g_vl_minb == 8) VL_FINE(0, 8); else if (g_vl_minb == 6) VL_FINE(0, 6); else if (g_vl_minb == 5) VL_FINE(0, 5); else if (g_vl_minb == 4) VL_FINE(0, 4); else if (g_vl_minb == 3) VL_FINE(0, 3); else VL_FINE(0, 2); }
+#undef VL_FINE
+    g_vl_launches += 1;
+    return vm_check_launch(c.what);
 }
 
 // mode 0: C3 (no flow stage), 1: flow warp only, 2: flow warp + consistency mask
@@ -1097,184 +849,66 @@ int vm_lean_launch(int mode, const uint8_t *fg, const float *backward, const flo
     VM_REQUIRE(scratch, "scratch workspace (vm_fused_scratch_bytes) required");
     VM_REQUIRE(N >= 1 && N <= VL_MAX_N, "control point count out of range");
     VM_REQUIRE(nx <= h / 2 + 1 && ny <= w / 2 + 1, "coarse grid larger than the scratch layout");
-    const int64_t px = (int64_t)h * w;
-    const int chunk = g_vl_chunk;
+    VlCall c;
+    c.mode = mode; c.N = N; c.nx = nx; c.ny = ny; c.n_bg = n_bg; c.h = h; c.w = w;
+    c.step_x = step_x; c.step_y = step_y; c.fg = fg; c.bg = bg; c.backward = backward; c.forward = forward;
+    c.ctrl = ctrl; c.coef = coef; c.rows = rows; c.cols = cols; c.out = out; c.status = status; c.what = what;
+    c.rpt = g_vl_fine_rows < VL_FROWS_MAX / VL_FS ? g_vl_fine_rows : VL_FROWS_MAX / VL_FS;
+    {
+        const dim3 grid((w + VL_FW - 1) / VL_FW, (h + VL_FS * c.rpt - 1) / (VL_FS * c.rpt), 1);
+        VM_REQUIRE(grid.y <= 65535 && n <= 65535, "too many tiles for one launch");
+    }
+    // shared memory per resampling CTA: 227 KB per SM (1 KB reserved per CTA) split over the occupancy target
+    c.box_cap = g_vl_box_cap;
+    if (c.box_cap <= 0) {
+        const int64_t per_cta = (227 * 1024) / g_vl_minb - 1024 - (int64_t)sizeof(VlFineSmem);
+        c.box_cap = (int)(per_cta / 8) & ~63;
+        if (c.box_cap > 8192) c.box_cap = 8192;
+    }
+    c.fine_smem = vl_fine_smem_bytes(c.box_cap);
     unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
-    unsigned int *counters = reinterpret_cast<unsigned int *>(base);     // one B1 unit counter per chunk parity
-    base += 256;
-    void *packed = base;
-    const int mc = n < chunk ? n : chunk;
-    const int64_t t_bytes = vl_align((int64_t)mc * (h / 2 + 1) * (w / 2 + 1) * 16);
-    const int rpt = g_vl_fine_rows < VL_FROWS_MAX / VL_FS ? g_vl_fine_rows : VL_FROWS_MAX / VL_FS;
-    const int64_t box_bytes = vl_align((int64_t)mc * ((w + VL_FW - 1) / VL_FW) * ((h + 3) / 4) * 16);
-    // two {T, boxes} sets: the spline stage of chunk c+1 runs on the side stream while chunk c is
-    // flow-warped and resampled on the caller's stream (it uses the float64 / shared-memory pipes the
-    // other two stages leave idle)
-    unsigned char *tb0 = base + vl_align((int64_t)mc * px * 8);
-    double2 *Tset[2] = {reinterpret_cast<double2 *>(tb0), reinterpret_cast<double2 *>(tb0 + t_bytes + box_bytes)};
-    VlTileBox *Bset[2] = {reinterpret_cast<VlTileBox *>(tb0 + t_bytes), reinterpret_cast<VlTileBox *>(tb0 + 2 * t_bytes + box_bytes)};
-    unsigned int *frame_done = reinterpret_cast<unsigned int *>(tb0 + (g_vl_overlap ? 2 : 1) * (t_bytes + box_bytes));
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
-    const bool overlap = g_vl_overlap && cap == cudaStreamCaptureStatusNone;
-    if (!g_vl_overlap) { Tset[1] = Tset[0]; Bset[1] = Bset[0]; }       // one set: the scratch only holds one
-    cudaStream_t side = overlap ? g_vl_side[dev] : st;
-    if (overlap) {                                                      // the side stream starts behind the caller's work
-        cudaEventRecord(g_vl_ev_fork[dev], st);
-        cudaStreamWaitEvent(side, g_vl_ev_fork[dev], 0);
-    }
-    const bool timing = g_vl_timing && !overlap && cap == cudaStreamCaptureStatusNone;
+    // ---- one round per chunk of `lean_chunk` frames on the caller's stream: spline, tile boxes, flow stage, resampling
+    const int chunk = g_vl_chunk;
+    const int mc = n < chunk ? n : chunk;
+    const VlSlot sl = vl_slot_at(base, mc, h, w);
+    const bool timing = g_vl_timing && cap == cudaStreamCaptureStatusNone;
     if (timing && !g_vl_tev_ok[dev]) {
         for (int k = 0; k < 5; ++k)
             if (cudaEventCreate(&g_vl_tev[dev][k]) != cudaSuccess) { vm_set_error("vm_lean: cudaEventCreate failed"); return VM_ERR_CUDA; }
         g_vl_tev_ok[dev] = true;
     }
-    const int n_chunks = (n + chunk - 1) / chunk;
-    for (int c = 0; c < n_chunks; ++c) {
-        const int f0 = c * chunk;
+    for (int f0 = 0, ci = 0; f0 < n; f0 += chunk, ++ci) {
         const int m = (n - f0 < chunk) ? n - f0 : chunk;
-        const int par = c & 1;
-        double2 *T = Tset[par];
-        VlTileBox *boxes = Bset[par];
-        const dim3 block(VL_FW, VL_FS), grid((w + VL_FW - 1) / VL_FW, (h + VL_FS * rpt - 1) / (VL_FS * rpt), m);
-        VM_REQUIRE(grid.y <= 65535 && m <= 65535, "too many tiles for one launch");
-        // shared memory per CTA: 227 KB per SM (1 KB reserved per CTA) split over the occupancy target
-        int box_cap = g_vl_box_cap;
-        if (box_cap <= 0) {
-            const int64_t per_cta = (227 * 1024) / g_vl_minb - 1024 - (int64_t)sizeof(VlFineSmem);
-            box_cap = (int)(per_cta / 8) & ~63;
-            if (box_cap > 8192) box_cap = 8192;
-        }
-        const size_t fine_smem = vl_fine_smem_bytes(box_cap);
-        // ---- side stream: spline on the coarse grid + tile boxes of chunk c ---------------------
-        if (overlap && c >= 2) cudaStreamWaitEvent(side, g_vl_ev_free[dev][par], 0);     // set `par` consumed by chunk c-2
-        const bool tev = timing && c == 0;
-        if (tev) cudaEventRecord(g_vl_tev[dev][0], st);
-        // packed floors of T for the tile-box stage: they live at the start of the flow stage's output buffer,
-        // which nobody touches until the box stage is done (not with the spline stage on the side stream,
-        // where the previous round's flow stage may still be writing it)
-        const bool persist = g_vl_persist != 0;
-        int *F = (!overlap && !persist && g_vl_floors && h <= 32766 && w <= 32766) ? reinterpret_cast<int *>(packed) : nullptr;
-        rc = vl_launch_coarse(ctrl + (int64_t)f0 * N * 2, coef + (int64_t)f0 * (N + 3) * 2, N, m, nx, ny, step_x, step_y, T, F,
-                              counters + par * 32, side);
+        const bool tev = timing && ci == 0;
+        auto mark = [&](int k) { if (tev) cudaEventRecord(g_vl_tev[dev][k], st); };
+        if (tev) { const int pr[4][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 4}}; memcpy(g_vl_tpair[dev], pr, sizeof(pr)); }
+        mark(0);
+        // the packed floors of T live at the start of the flow stage's output buffer, which nobody touches until
+        // the box stage is done (same stream)
+        rc = vl_enqueue_coarse(c, sl, f0, m, true, st);
         if (rc != VM_OK) return rc;
-        if (tev) cudaEventRecord(g_vl_tev[dev][1], st);
-        const int ptx = (w + VL_FW - 1) / VL_FW, pty = (h + VL_PTH - 1) / VL_PTH;      // tiling of the persistent kernel
-        // persistent kernel: 2 CTAs per SM share 227 KB; two source-box buffers per CTA
-        int pbox_cap = (int)((((227 * 1024) / 2 - 1024 - (int64_t)sizeof(VlPSmem)) / 16) & ~63);
-        if (g_vl_box_cap > 0 && g_vl_box_cap < pbox_cap) pbox_cap = g_vl_box_cap;
-        VlTileRec *recs = reinterpret_cast<VlTileRec *>(boxes);
-        if (persist) {
-            const int n_tiles = ptx * pty * m;
-            if (mode != 0) k_lean_recs<1><<<(n_tiles + 3) / 4, 128, 0, side>>>(T, nx, ny, rows, cols, h, w, ptx, pty, n_tiles, pbox_cap, recs);
-            else           k_lean_recs<0><<<(n_tiles + 3) / 4, 128, 0, side>>>(T, nx, ny, rows, cols, h, w, ptx, pty, n_tiles, pbox_cap, recs);
-            rc = vm_check_launch("vm_lean tile record stage");
-            if (rc != VM_OK) return rc;
-        } else {
-            const int n_tiles = (int)(grid.x * grid.y * m);
-            if (mode != 0) k_lean_boxes<1><<<(n_tiles + 3) / 4, 128, 0, side>>>(T, F, nx, ny, rows, cols, h, w, rpt, grid.x, grid.y, n_tiles, box_cap, boxes);
-            else           k_lean_boxes<0><<<(n_tiles + 3) / 4, 128, 0, side>>>(T, F, nx, ny, rows, cols, h, w, rpt, grid.x, grid.y, n_tiles, box_cap, boxes);
-            rc = vm_check_launch("vm_lean box stage");
-            if (rc != VM_OK) return rc;
-        }
-        if (overlap) cudaEventRecord(g_vl_ev_ready[dev][par], side);
-        if (tev) cudaEventRecord(g_vl_tev[dev][2], st);
-        g_vl_launches += 2;
-        // ---- caller's stream: flow stage, then resampling + composite, in sub-rounds of `lean_sub` frames
-        // (0 = the whole round): small sub-rounds keep the packed intermediate in L2 between the two kernels
-        if (overlap) cudaStreamWaitEvent(st, g_vl_ev_ready[dev][par], 0);
+        mark(1);
+        rc = vl_enqueue_boxes(c, sl, m, true, st);
+        if (rc != VM_OK) return rc;
+        mark(2);
+        // flow stage, then resampling + composite, in sub-rounds of `lean_sub` frames (0 = the whole round)
         const int sub = (g_vl_sub > 0 && g_vl_sub < m && !tev) ? g_vl_sub : m;
-        const int64_t tiles_per_frame = (int64_t)grid.x * grid.y;
         for (int fs = 0; fs < m; fs += sub) {
             const int ms = (m - fs < sub) ? m - fs : sub;
-            const int ff0 = f0 + fs;
-            const bool mega = g_vl_mega && mode != 0 && !persist && (w & 3) == 0;
-            if (mega) {
-                // flow-stage units and resampling tiles from one interleaved list; every CTA must be resident
-                const float2 *b2 = reinterpret_cast<const float2 *>(backward + ff0 * px * 2);
-                const float2 *f2 = (mode == 2 && forward) ? reinterpret_cast<const float2 *>(forward + ff0 * px * 2) : nullptr;
-                float4 *o4m = reinterpret_cast<float4 *>(out) + ff0 * px;
-                if (cudaMemsetAsync(frame_done, 0, sizeof(unsigned int) * ms, st) != cudaSuccess) { vm_set_error("vm_lean: cudaMemsetAsync failed"); return VM_ERR_CUDA; }
-                int per_sm = 0;
-                cudaError_t e = cudaSuccess;
-#define VL_MEGA(FW)                                                                                                 \
-    do {                                                                                                            \
-        static size_t attr_m[64];                                                                                   \
-        if (attr_m[dev & 63] < fine_smem) {                                                                         \
-            e = cudaFuncSetAttribute(k_lean_mega<FW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fine_smem);   \
-            if (e == cudaSuccess) attr_m[dev & 63] = fine_smem;                                                     \
-        }                                                                                                           \
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lean_mega<FW>, VL_FW * VL_FS, fine_smem); \
-        if (e == cudaSuccess && per_sm >= 1)                                                                        \
-            k_lean_mega<FW><<<per_sm * vl_sm_count(), block, fine_smem, st>>>(fg + ff0 * px * 4, b2, f2, (uint2 *)packed, bg, n_bg, ff0, \
-                Ts0, nx, ny, rows, cols, h, w, ms, rpt, bs0, o4m, status, frame_done);                               \
-    } while (0)
-                const double2 *Ts0 = T + (int64_t)fs * nx * ny;
-                const VlTileBox *bs0 = boxes + fs * tiles_per_frame;
-                if (f2) VL_MEGA(true); else VL_MEGA(false);
-#undef VL_MEGA
-                if (e != cudaSuccess || per_sm < 1) { vm_set_error("vm_lean: mega kernel set-up failed: %s", cudaGetErrorString(e)); return VM_ERR_CUDA; }
-                g_vl_launches += 1;
-                rc = vm_check_launch(what);
-                if (rc != VM_OK) return rc;
-                if (tev) cudaEventRecord(g_vl_tev[dev][3], st);
-                continue;
-            }
             if (mode != 0) {
-                rc = vm_launch_flow_stage(fg + ff0 * px * 4, backward + ff0 * px * 2, (mode == 2 && forward) ? forward + ff0 * px * 2 : nullptr,
-                                          ms, h, w, packed, status, st, true);
+                rc = vl_enqueue_flow(c, sl, f0 + fs, ms, st);           // the sub-round's packed frames start the buffer
                 if (rc != VM_OK) return rc;
-                g_vl_launches += 1;
             }
-            if (tev) cudaEventRecord(g_vl_tev[dev][3], st);
-            const dim3 sgrid(grid.x, grid.y, ms);
-            const double2 *Ts = T + (int64_t)fs * nx * ny;
-            const VlTileBox *bs = boxes + fs * tiles_per_frame;
-            float4 *o4 = reinterpret_cast<float4 *>(out) + ff0 * px;
-#define VL_FINE(S, MB)                                                                                              \
-    do {                                                                                                            \
-        static size_t attr_set[64];                                                                                 \
-        if (attr_set[dev & 63] < fine_smem) {                                                                       \
-            cudaError_t e = cudaFuncSetAttribute(k_lean_fine<S, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fine_smem); \
-            if (e != cudaSuccess) { vm_set_error("vm_lean: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VM_ERR_CUDA; } \
-            attr_set[dev & 63] = fine_smem;                                                                         \
-        }                                                                                                           \
-        k_lean_fine<S, MB><<<sgrid, block, fine_smem, st>>>(S ? (const void *)packed : (const void *)(fg + ff0 * px * 4), \
-                                                            bg, n_bg, ff0, Ts, nx, ny, rows, cols, h, w, rpt, bs, o4, status); \
-    } while (0)
-            if (persist) {
-                const int n_tiles = ptx * pty * ms;
-                const int ctas = 2 * vl_sm_count();
-                const int per_cta = (n_tiles + ctas - 1) / ctas;
-                const int grid_p = (n_tiles + per_cta - 1) / per_cta;
-                const size_t psmem = vl_p_smem_bytes(pbox_cap);
-                const VlTileRec *rs = recs + (int64_t)fs * ptx * pty;
-                const dim3 pblock(VL_FW, VL_PS);
-#define VL_FINE_P(S)                                                                                                \
-    do {                                                                                                            \
-        static size_t attr_p[64];                                                                                   \
-        if (attr_p[dev & 63] < psmem) {                                                                             \
-            cudaError_t e = cudaFuncSetAttribute(k_lean_fine_p<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem); \
-            if (e != cudaSuccess) { vm_set_error("vm_lean: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VM_ERR_CUDA; } \
-            attr_p[dev & 63] = psmem;                                                                               \
-        }                                                                                                           \
-        k_lean_fine_p<S><<<grid_p, pblock, psmem, st>>>(S ? (const void *)packed : (const void *)(fg + ff0 * px * 4), bg, n_bg, ff0, \
-                                                        Ts, nx, ny, rows, cols, h, w, ptx, pty, n_tiles, per_cta, pbox_cap, rs, o4, status); \
-    } while (0)
-                if (mode != 0) VL_FINE_P(1); else VL_FINE_P(0);
-#undef VL_FINE_P
-            }
-            else if (mode != 0) { if (g_vl_minb == 8) VL_FINE(1, 8); else if (g_vl_minb == 6) VL_FINE(1, 6); else if (g_vl_minb == 5) VL_FINE(1, 5); else if (g_vl_minb == 4) VL_FINE(1, 4); else if (g_vl_minb == 3) VL_FINE(1, 3); else VL_FINE(1, 2); }
-            else           { if (g_vl_minb == 8) VL_FINE(0, 8); else if (g_vl_minb == 6) VL_FINE(0, 6); else if (g_vl_minb == 5) VL_FINE(0, 5); else if (g_vl_minb == 4) VL_FINE(0, 4); else if (g_vl_minb == 3) VL_FINE(0, 3); else VL_FINE(0, 2); }
-#undef VL_FINE
-            g_vl_launches += 1;
-            rc = vm_check_launch(what);
+            mark(3);
+            VlSlot part = sl;
+            part.T = sl.T + (int64_t)fs * nx * ny;
+            part.boxes = sl.boxes + (int64_t)fs * ((w + VL_FW - 1) / VL_FW) * ((h + VL_FS * c.rpt - 1) / (VL_FS * c.rpt));
+            rc = vl_enqueue_fine(c, part, f0 + fs, 0, ms, st);
             if (rc != VM_OK) return rc;
         }
-        rc = vm_check_launch(what);
-        if (rc != VM_OK) return rc;
-        if (tev) cudaEventRecord(g_vl_tev[dev][4], st);
-        if (overlap) cudaEventRecord(g_vl_ev_free[dev][par], st);
+        mark(4);
     }
     return VM_OK;
 }
@@ -1290,7 +924,8 @@ extern "C" int vm_lean_stage_ms(float *out4) {
         return VM_ERR_ARG;
     }
     for (int k = 0; k < 4; ++k)
-        if (cudaEventElapsedTime(out4 + k, g_vl_tev[dev][k], g_vl_tev[dev][k + 1]) != cudaSuccess) {
+        if (g_vl_tpair[dev][k][0] == g_vl_tpair[dev][k][1]) out4[k] = 0.f;
+        else if (cudaEventElapsedTime(out4 + k, g_vl_tev[dev][g_vl_tpair[dev][k][0]], g_vl_tev[dev][g_vl_tpair[dev][k][1]]) != cudaSuccess) {
             cudaGetLastError();
             vm_set_error("vm_lean_stage_ms: events not complete");
             return VM_ERR_ARG;

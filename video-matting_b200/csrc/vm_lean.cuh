@@ -47,7 +47,7 @@ __device__ __forceinline__ double vl_u_fast(double r2, uint32_t tab_adj) {
 }
 
 // any r2 >= 0 (tps.py:78-82: U = 0 for r < 1e-100)
-__device__ __noinline__ double vl_u_any(double r2, uint32_t tab_adj) {
+static __device__ __noinline__ double vl_u_any(double r2, uint32_t tab_adj) {
     const int hi = __double2hiint(r2);
     if (hi >= VL_HI_MIN && hi < VL_HI_MAX) return vl_u_fast(r2, tab_adj);
     if (r2 >= 1e-200) return r2 * log(r2);

@@ -7,6 +7,7 @@
 #include <mutex>
 
 int vm_lean_set_option(const char *key, int value);                                // vm_lean.cu
+int vm_fuse_set_option(const char *key, int value);                                // vm_fuse.cu
 extern int g_vm_flow_stage_layout;                                                 // vm_flow.cu
 
 // ---------------------------------------------------------------------------------------
@@ -906,6 +907,7 @@ extern "C" int vm_set_option(const char *key, int value) {
     if (!strcmp(key, "pipe_blocks") && value >= 0) { g_vp_blocks = value; return VM_OK; }
     if (!strcmp(key, "pipe_roles") && value >= 1 && value <= 7) { g_vp_roles = value; return VM_OK; }
     if (!strncmp(key, "lean_", 5) && vm_lean_set_option(key, value) == VM_OK) return VM_OK;
+    if (!strncmp(key, "fuse_", 5) && vm_fuse_set_option(key, value) == VM_OK) return VM_OK;
     if (!strcmp(key, "flow_stage_layout") && (value == 0 || value == 1)) { g_vm_flow_stage_layout = value; return VM_OK; }
     vm_set_error("vm_set_option: unknown option %s=%d", key, value);
     return VM_ERR_ARG;
@@ -935,6 +937,10 @@ int vm_lean_launch(int mode, const uint8_t *fg, const float *backward, const flo
                    int n_bg, const double *ctrl, const double *coef, int N, int nx, int ny, double step_x,
                    double step_y, const vm_axis_entry *rows, const vm_axis_entry *cols, int n, int h, int w,
                    float *out, void *scratch, int32_t *status, cudaStream_t st, const char *what);
+int vm_fuse_launch(int mode, const uint8_t *fg, const float *backward, const float *forward, const uint8_t *bg,
+                   int n_bg, const double *ctrl, const double *coef, int N, int nx, int ny, double step_x,
+                   double step_y, const vm_axis_entry *rows, const vm_axis_entry *cols, int n, int h, int w,
+                   float *out, int32_t *status, cudaStream_t st, const char *what);  // vm_fuse.cu
 int64_t vm_pipe_scratch_bytes(int n, int h, int w);                                // vm_pipe.cu
 int vm_pipe_launch(int mode, const uint8_t *fg, const float *backward, const float *forward, const uint8_t *bg,
                    int n_bg, const double *ctrl, const double *coef, int N, int nx, int ny, double step_x,
@@ -970,13 +976,18 @@ static int launch_fused(bool flow, const uint8_t *fg, const float *backward, con
     VM_REQUIRE(h <= 32767 && w <= 32767 && (int64_t)h * w < (1ll << 28), "frame too large");
     cudaStream_t st = (cudaStream_t)stream;
     const bool small_n = N <= TT_MAX_N && h >= 2 && w >= 2;
-    if (g_opt_variant == 4 && small_n && nx <= h / 2 + 1 && ny <= w / 2 + 1)
+    // variant 5: C4 in ONE kernel (vm_fuse.cu: every byte touches HBM once; measured slower than the lean split pipeline,
+    // DESIGN.md 5f); C3 and anything it does not take goes to the lean pipeline
+    if (g_opt_variant == 5 && flow && small_n && (int64_t)n * ((h + 59) / 60) * ((w + 59) / 60) < (1ll << 31))
+        return vm_fuse_launch(forward ? 2 : 1, fg, backward, forward, bg, n_bg, ctrl, coef, N, nx, ny, step_x, step_y,
+                              rows, cols, n, h, w, out, status, st, what);
+    if ((g_opt_variant == 4 || g_opt_variant == 5) && small_n && nx <= h / 2 + 1 && ny <= w / 2 + 1)
         return vm_lean_launch(flow ? (forward ? 2 : 1) : 0, fg, backward, forward, bg, n_bg, ctrl, coef, N, nx, ny,
                               step_x, step_y, rows, cols, n, h, w, out, scratch, status, st, what);
     if (g_opt_variant == 3 && small_n && nx == h / 2 && ny == w / 2)
         return vm_pipe_launch(flow ? (forward ? 2 : 1) : 0, fg, backward, forward, bg, n_bg, ctrl, coef, N, nx, ny,
                               step_x, step_y, rows, cols, n, h, w, out, scratch, status, st, what);
-    if ((g_opt_variant == 0 || g_opt_variant == 3 || g_opt_variant == 4) && small_n) {
+    if ((g_opt_variant == 0 || g_opt_variant == 3 || g_opt_variant == 4 || g_opt_variant == 5) && small_n) {
         // split pipeline: stage A (flow warp + mask -> packed intermediate, L2 resident) and stage B
         // (TPS + composite) per chunk of frames; C3 has no stage A.
         if (!flow)
