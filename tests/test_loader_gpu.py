@@ -311,3 +311,40 @@ def test_generate_trimaps_and_create_list(vm, tmp_path):
                                          os.path.join("VOC_bg", voc[ids[0]]))
     entries = vm.loader.get_file_list(str(root), str(tmp_path / "list.txt"))
     assert len(entries) == 200 and entries[0][0] == os.path.join(str(root), "fg", "S", fgs[0])
+
+
+def test_load_clip_odd_frame_size_and_chunk(vm, tmp_path):
+    """16-bit PNGs with an odd pixel count and an odd chunk: the converted frames land at 4-byte aligned offsets of the
+    clip (the vector path of vm_fg_from_u16 needs 8) - the element-wise path must take over."""
+    R = vm.reader
+    h, w, n = 45, 71, 4
+    rng = np.random.default_rng(11)
+    fgp = []
+    for k in range(n):
+        img = rng.integers(0, 65536, (h, w, 4)).astype(np.uint16)
+        fgp.append(str(tmp_path / f"fg{k}.png"))
+        assert cv2.imwrite(fgp[-1], img)
+    clip = R.load_clip(fgp, chunk=1, threads=2)
+    clip3 = R.load_clip(fgp, chunk=3, threads=2)
+    for k in range(n):
+        alpha, bgr = R.read_fg_img(fgp[k])
+        for c in (clip, clip3):
+            got = c["fg"][k].cpu().numpy()
+            assert np.array_equal(got[..., :3], bgr) and np.array_equal(got[..., 3] / 255., alpha)
+
+
+def test_flow_entry_rejects_misaligned_buffers(vm):
+    """the vectorised C entry points return VM_ERR_ARG for pointers their 16-byte accesses cannot take (no device fault)"""
+    import torch
+    P, Nt = vm.pipeline, vm._native
+    lib = Nt.load()
+    n, h, w = 1, 8, 16
+    fg = torch.zeros((n, h, w, 4), dtype=torch.uint8, device="cuda")
+    flow = torch.zeros(n * h * w * 2 + 2, dtype=torch.float32, device="cuda")
+    bgr = torch.empty((n, h, w, 3), dtype=torch.uint8, device="cuda")
+    alpha = torch.empty((n, h, w), dtype=torch.float32, device="cuda")
+    rc = lib.vm_flow_warp_mask_bgra(Nt.ptr(fg), flow.data_ptr() + 8, None, n, h, w, Nt.ptr(bgr), Nt.ptr(alpha), None, Nt.stream_ptr())
+    assert rc == 1 and b"unaligned" in lib.vm_last_error_string()
+    rc = lib.vm_flow_warp_mask_bgra(Nt.ptr(fg), flow.data_ptr(), None, n, h, w, Nt.ptr(bgr), Nt.ptr(alpha), None, Nt.stream_ptr())
+    assert rc == 0
+    torch.cuda.synchronize()

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libvm_sm100a.so")
-SOURCES = ["vm_capi.cu", "vm_flow.cu", "vm_tps.cu", "vm_pipe.cu", "vm_lean.cu", "vm_fuse.cu", "vm_affine.cu", "vm_loader.cu"]
+SOURCES = ["vm_capi.cu", "vm_flow.cu", "vm_tps.cu", "vm_lean.cu", "vm_fuse.cu", "vm_affine.cu", "vm_loader.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false", "-Xcompiler", "-fPIC", "-cudart", "shared",
               "-Xlinker", "-rpath=/usr/local/cuda/lib64"]

@@ -230,7 +230,7 @@ def _alpha_stats_clip(fg_d):
     return stats.cpu().numpy()
 
 
-def _augment_run(fg_d, bg_d, plan, alpha_dtype=torch.float32):
+def _augment_run(fg_d, bg_d, plan, alpha_dtype=torch.float32, status=None):
     """Device stages of augment() for a clip whose random parameters are known: host TPS solve (system built
     from the deformed grid, tps.py:51), spline, TPS resampling, fused affine passes + illumination.
     ``alpha_dtype`` float64 carries alpha through both stages in float64 with scipy's / OpenCV's operation
@@ -251,7 +251,6 @@ def _augment_run(fg_d, bg_d, plan, alpha_dtype=torch.float32):
     T = torch.empty((n, tplan.nx, tplan.ny, 2), dtype=torch.float64, device=dev)
     counter = torch.zeros(64, dtype=torch.int32, device=dev)
     inter = torch.empty((n, h + 1, w + 1, 2), dtype=torch.int32, device=dev)
-    status = N.new_status(dev)
     Np = ctrl.shape[1]
     N.check(lib.vm_tps_coarse_packed(N.ptr(ctrl), N.ptr(coef), n, Np, tplan.nx, tplan.ny, tplan.step_x, tplan.step_y,
                                      N.ptr(T), N.ptr(counter), N.stream_ptr()))
@@ -273,7 +272,7 @@ def alpha_stats(fg_bgra):
     return _alpha_stats_clip(fg_d.contiguous())
 
 
-def augment_clip(fg_bgra, bg, alpha_dtype=torch.float32, stats=None):
+def augment_clip(fg_bgra, bg, alpha_dtype=torch.float32, stats=None, status=None):
     """augment() for a whole clip in a handful of launches (BASELINE config 5).
 
     ``fg_bgra`` (n, H, W, 4) uint8 BGRA with alpha = A/255 (what reader.read_fg_img returns, reference
@@ -283,7 +282,9 @@ def augment_clip(fg_bgra, bg, alpha_dtype=torch.float32, stats=None):
     TPS systems are solved on the host with numpy's pinv (reference tps.py:119).  Returns
     (new_fg (n,H,W,3) uint8, new_bg (n,H,W,3) uint8, new_alpha (n,H,W) float32) of the input kind;
     ``alpha_dtype=torch.float64`` returns the alpha in float64 as the reference does (same operation order);
-    ``stats=alpha_stats(fg_bgra)`` skips the per-call alpha reduction and its host synchronisation."""
+    ``stats=alpha_stats(fg_bgra)`` skips the per-call alpha reduction and its host synchronisation;
+    ``status`` (a device int32[8] block, ``_native.new_status()``) receives the count of TPS samples that fell
+    outside the source (word 3) - nothing is counted when it is None."""
     fg_d, kind = N.to_device(fg_bgra)
     bg_d, _ = N.to_device(bg)
     assert fg_d.dtype == torch.uint8 and fg_d.dim() == 4 and fg_d.shape[3] == 4, "fg must be (n, H, W, 4) uint8 BGRA"
@@ -296,7 +297,7 @@ def augment_clip(fg_bgra, bg, alpha_dtype=torch.float32, stats=None):
                  torch.empty((0, h, w), dtype=alpha_dtype, device=dev))
         return tuple(N.from_device(t, kind) for t in empty)
     plan = _augment_plan(_alpha_stats_clip(fg_d) if stats is None else np.asarray(stats), h, w)
-    return tuple(N.from_device(t, kind) for t in _augment_run(fg_d, bg_d, plan, alpha_dtype))
+    return tuple(N.from_device(t, kind) for t in _augment_run(fg_d, bg_d, plan, alpha_dtype, status))
 
 
 #: variants written per foreground by augmentation() (reference augmentation.py:140) and how many of them go

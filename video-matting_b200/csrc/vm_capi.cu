@@ -12,8 +12,10 @@ void vm_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+// Launch errors are reported without being consumed (cudaPeekAtLastError): a failure that torch or the caller
+// caused earlier on this thread stays visible to them instead of being swallowed - or blamed on this library only.
 int vm_check_launch(const char *what) {
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) {
         vm_set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
         return VM_ERR_CUDA;

@@ -8,11 +8,12 @@
 #include "../../include/vm_b200.h"
 
 void vm_set_error(const char *fmt, ...);
-extern int g_vp_lead, g_vp_ring_rows, g_vp_cring_rows, g_vp_blocks, g_vp_roles;   // pipeline tuning (vm_pipe.cu)
 int  vm_check_launch(const char *what);
 
 #define VM_REQUIRE(cond, msg)                                   \
     do { if (!(cond)) { vm_set_error("%s: %s", __func__, msg); return VM_ERR_ARG; } } while (0)
+
+static inline bool vm_aligned(const void *p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }   // nullptr counts as aligned
 
 static inline unsigned vm_blocks(int64_t n, int per_block) {
     int64_t b = (n + per_block - 1) / per_block;

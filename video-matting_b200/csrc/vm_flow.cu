@@ -214,6 +214,8 @@ int g_vm_flow_stage_layout = 0;      // 1: column x 4 rows per thread (k_flow_st
 int vm_launch_flow_stage(const uint8_t *fg, const float *backward, const float *forward, int n, int h, int w,
                          void *packed, int32_t *status, cudaStream_t st, bool raw_ta) {
     const float2 *b2 = (const float2 *)backward, *f2 = (const float2 *)forward;
+    VM_REQUIRE(vm_aligned(fg, 4) && vm_aligned(backward, (w & 3) ? 8 : 16) && vm_aligned(forward, 8) &&
+               vm_aligned(packed, (w & 3) ? 8 : 16), "unaligned buffer");
     if (g_vm_flow_stage_layout == 1) {
         const dim3 grid((w + 31) / 32, (h + C2P_ROWS - 1) / C2P_ROWS, n);
         uint2 *o = (uint2 *)packed;
@@ -240,6 +242,9 @@ extern "C" int vm_flow_warp_mask_bgra(const uint8_t *fg, const float *backward, 
     VM_REQUIRE(fg && backward && out_bgr && out_alpha, "null pointer");
     VM_REQUIRE(n >= 0 && h > 0 && w > 0 && h <= 32767 && w <= 32767, "bad size");
     if (n == 0) return VM_OK;
+    // the 4-pixel path (w % 4 == 0) uses 16-byte flow loads / alpha stores and 4-byte BGRA / BGR accesses
+    VM_REQUIRE(vm_aligned(fg, 4) && vm_aligned(backward, (w & 3) ? 8 : 16) && vm_aligned(forward, 8) &&
+               vm_aligned(out_alpha, (w & 3) ? 4 : 16) && ((w & 3) || vm_aligned(out_bgr, 4)), "unaligned buffer");
     const int tiles_x = (w + C2_TW - 1) / C2_TW, tiles_y = (h + C2_ROWS - 1) / C2_ROWS;
     VM_REQUIRE(tiles_y <= 65535 && n <= 65535, "too many tiles for one launch");
     const dim3 tiles(tiles_x, tiles_y, n);

@@ -592,11 +592,9 @@ static int vf_launch_t(const uint8_t *fg, const float *backward, const float *fo
     return vm_check_launch(what);
 }
 
-int g_vf_nsw = 8;            // spline warps per CTA (4 or 8)
 int g_vf_ctas = 0;           // CTAs (0: one per SM)
 
 int vm_fuse_set_option(const char *key, int value) {
-    if (!strcmp(key, "fuse_nsw") && (value == 4 || value == 8)) { g_vf_nsw = value; return VM_OK; }
     if (!strcmp(key, "fuse_ctas") && value >= 0 && value <= 4096) { g_vf_ctas = value; return VM_OK; }
     return VM_ERR_ARG;
 }
@@ -614,8 +612,7 @@ int vm_fuse_launch(int mode, const uint8_t *fg, const float *backward, const flo
     const bool fw = mode == 2 && forward;
 #define VF_GO(NN, FW, NSW) return vf_launch_t<NN, FW, NSW>(fg, backward, forward, bg, n_bg, ctrl, coef, N, nx, ny, step_x, step_y, rows, cols, n, h, w, out, status, st, ctas, what)
 #define VF_N(FW, NSW) do { if (N == 25) VF_GO(25, FW, NSW); else if (N == 16) VF_GO(16, FW, NSW); else VF_GO(0, FW, NSW); } while (0)
-    if (g_vf_nsw == 4) { if (fw) VF_N(true, 4); else VF_N(false, 4); }
-    else { if (fw) VF_N(true, 8); else VF_N(false, 8); }
+    if (fw) VF_N(true, 8); else VF_N(false, 8);
 #undef VF_N
 #undef VF_GO
     return VM_OK;

@@ -258,10 +258,11 @@ __device__ __forceinline__ uint32_t vm_u16_quirk(uint32_t v) {
     return q == 0u ? 255u : (q < 256u ? 0u : (q >> 8) - 1u);
 }
 
-__global__ void __launch_bounds__(256) k_fg_from_u16(const uint16_t *__restrict__ src, int64_t n, uint8_t *__restrict__ dst) {
+// vec: src is 16-byte and dst 8-byte aligned (vector accesses); otherwise element by element
+__global__ void __launch_bounds__(256) k_fg_from_u16(const uint16_t *__restrict__ src, int64_t n, uint8_t *__restrict__ dst, int vec) {
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
     if (i >= n) return;
-    if (i + 8 <= n) {
+    if (vec && i + 8 <= n) {
         const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(src + i));
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
         uint32_t o[2] = {0u, 0u};
@@ -272,15 +273,18 @@ __global__ void __launch_bounds__(256) k_fg_from_u16(const uint16_t *__restrict_
         }
         __stcs(reinterpret_cast<uint2 *>(dst + i), make_uint2(o[0], o[1]));
     } else {
-        for (int64_t k = i; k < n; ++k) dst[k] = (uint8_t)vm_u16_quirk(src[k]);
+        for (int64_t k = i; k < n && k < i + 8; ++k) dst[k] = (uint8_t)vm_u16_quirk(src[k]);
     }
 }
 
 extern "C" int vm_fg_from_u16(const uint16_t *src, int64_t n, uint8_t *dst, void *stream) {
     VM_REQUIRE(src && dst && n >= 0, "bad argument");
-    VM_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0, "unaligned buffer");
+    VM_REQUIRE((reinterpret_cast<uintptr_t>(src) & 1) == 0, "source is not 2-byte aligned");
     if (n == 0) return VM_OK;
+    // any destination offset works (reader.load_clip converts into slices of a clip: odd frame sizes give 4-byte
+    // aligned slices); the vector path needs 16 / 8 byte alignment
+    const int vec = (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0;
     const int64_t threads = (n + 7) / 8;
-    k_fg_from_u16<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, n, dst);
+    k_fg_from_u16<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, n, dst, vec);
     return vm_check_launch("vm_fg_from_u16");
 }

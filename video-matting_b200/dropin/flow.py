@@ -10,5 +10,10 @@ if "video_matting_b200" not in _sys.modules:
                                        submodule_search_locations=[_pkg])
     _mod = _u.module_from_spec(_spec)
     _sys.modules["video_matting_b200"] = _mod
-    _spec.loader.exec_module(_mod)
+    try:
+        _spec.loader.exec_module(_mod)
+    except BaseException:                       # no half-initialised package behind: the next import shows the real error again
+        _sys.modules.pop("video_matting_b200", None)
+        _sys.modules.pop(__name__, None)
+        raise
 _sys.modules[__name__] = _sys.modules["video_matting_b200"].flow

@@ -367,10 +367,9 @@ DEFAULT_VARIANT = 4
 def set_fused_variant(v):
     """4 = lean split pipeline (default: flow stage, float64 spline stage, TMA-tiled resampling stage -
     csrc/vm_lean.cu), 5 = single-pass warp-specialised kernel for C4 (csrc/vm_fuse.cu: no intermediate in HBM,
-    1.10 x the algorithmic traffic, but slower - DESIGN.md 5f; C3 takes the lean pipeline),
-    0 = first split pipeline, 1 = per-pixel gather kernels, 2 = single shared-memory tiled kernel,
-    3 = persistent role-specialised kernel.  The non-default variants are kept as independent
-    implementations for differential tests."""
+    1.10 x the algorithmic traffic, but slower - DESIGN.md 5f; C3 takes the lean pipeline), 1 = per-pixel gather
+    kernels (the generic fallback, any control-point count).  All three give the same bits for 4 and 5 and the
+    same values within tolerance for 1 (differential tests)."""
     N.set_option("fused_variant", int(v))
     _variant[0] = int(v)
 
