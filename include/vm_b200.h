@@ -128,14 +128,27 @@ int vm_warp_affine(const void *src, int dtype, int channels, int sh, int sw,
                    const double *M_host, int dh, int dw, void *dst, void *stream);
 
 /* ---- augmentation.change_illumination ----------------------------------------------------
- * reference: augmentation.py:88-99.  BGR2HSV integer model (exact), S/V gamma in float64
- * with truncation, HSV2BGR float model (+-1 LSB of cv2).                    */
+ * reference: augmentation.py:88-99.  BGR2HSV integer model (exact), S/V gamma in float64 with truncation,
+ * HSV2BGR bit-exact for OpenCV 4.13 (row f2): float32 sector formula with the contracted 1 - s*f, result
+ * TRUNCATED in the SIMD body of every image row and rounded half-to-even in the row's scalar tail - cv2 converts
+ * `hsv_vec` pixels per SIMD step (32 with AVX2, 16 with SSE, 64 with AVX-512; the binding probes its cv2), so
+ * pixel x of a row of w pixels is "body" iff x < w - w % hsv_vec.                                          */
+int vm_illumination_lut_rows(const uint8_t *bgr, int64_t rows, int w, const uint8_t *lut_host, int hsv_vec,
+                             uint8_t *out, void *stream);
+/* The buffer as ONE row of npx pixels, hsv_vec = 32 (kept for callers without a row structure).         */
 int vm_change_illumination(const uint8_t *bgr, int64_t npx, double a, double b, double c,
                            uint8_t *out, void *stream);
 /* Same with the 256-entry S/V transfer table supplied by the caller (HOST pointer), so that a
  * NumPy host can build it with the reference's own expression (augmentation.py:91-98).     */
 int vm_illumination_lut(const uint8_t *bgr, int64_t npx, const uint8_t *lut_host,
                         uint8_t *out, void *stream);
+
+/* ---- cv2.resize(uint8, dsize, INTER_LINEAR) (row f2) ----------------------------------------
+ * reference: reader.py:41,53 (backgrounds to the frame size), augmentation.py:160.  n images (sh, sw, channels)
+ * -> (dh, dw, channels), channels 1 / 3 / 4; bit-exact for OpenCV 4.13: 11-bit coefficients from float32
+ * fractions, horizontal fraction forced to 0 at the row ends, rows clipped vertically, exact 2x reductions as
+ * the 2x2 block mean (OpenCV switches INTER_LINEAR to INTER_AREA there).                              */
+int vm_resize_u8(const uint8_t *src, int n, int sh, int sw, int channels, uint8_t *dst, int dh, int dw, void *stream);
 
 /* ---- augmentation.object_size / fg_center -------------------------------------------------
  * reference: augmentation.py:10-21.  out (device uint64[3]) += {count(alpha != 0),
@@ -217,7 +230,7 @@ int vm_tps_coarse_packed(const double *ctrl, const double *coef, int n, int N, i
 int vm_aug_tps(const uint8_t *fg_bgra, const void *T, int nx, int ny, const vm_axis_entry *rows,
                const vm_axis_entry *cols, int n, int h, int w, void *inter, double *alpha64, int32_t *status, void *stream);
 int vm_aug_affine(int mode, const void *src, const double *alpha64, const void *params, const uint8_t *luts, int n, int h, int w,
-                  uint8_t *out_bgr, float *out_alpha, double *out_alpha64, void *stream);
+                  uint8_t *out_bgr, float *out_alpha, double *out_alpha64, int hsv_vec, void *stream);
 
 /* ---- batch loader: loader.load_and_crop / simple_load_crop / video_load_crop ----
  * reference: loader.py:39-85, 119-157, 285-330 (one sample), loader.py:93-116, 160-171, 333-345 (batch).

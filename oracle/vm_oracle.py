@@ -516,22 +516,44 @@ def bgr2hsv_u8(bgr):
     return np.stack([hh, s, v], axis=-1).astype(np.uint8)
 
 
-def hsv2bgr_u8(hsv):
-    """cv2.cvtColor(COLOR_HSV2BGR) for uint8 (float formulation of color_hsv.simd.hpp:
-    h*6/180, sector table, scale by 255 and round).  The OpenCV 4.13 binary differs from
-    this (and from itself between the SIMD body and the row tail) by <= 1 LSB, so the
-    parity target for change_illumination is +-1 LSB (SURVEY a-9)."""
+def _fma32(a, b, c):
+    """float32 fused multiply-add (one rounding): exact product in float64, one add, one cast."""
+    return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(np.float32)
+
+
+HSV_VEC = 32      # pixels per SIMD step of cv2's HSV2BGR on the machine that made the fixtures (AVX2: v_uint8x32)
+
+
+def hsv2bgr_u8(hsv, vec=HSV_VEC):
+    """cv2.cvtColor(COLOR_HSV2BGR) for uint8 images (H, W, 3), bit-exact for opencv-python-headless 4.13
+    [probed over all 180 x 256 x 256 inputs, 0 mismatches on either path]:
+
+        s = S * (1/255.f); v = V * (1/255.f); hh = H * (6.f/180.f); sector = floor(hh); f = hh - sector
+        tab = {v, v*(1-s), v*fma(-s, f, 1), v*fma(-s, 1-f, 1)}         (float32; the compiler contracts 1 - s*f)
+        {b, g, r} = tab[sector_data[sector]];  s == 0 -> b = g = r = v
+        out = tab * 255.f, then  - TRUNCATED toward zero in the SIMD body of a row (pixels x < W - W % vec),
+                                 - rounded half-to-even (cvRound) in the scalar tail of the row (the last W % vec pixels).
+
+    ``vec`` is the SIMD width cv2 dispatches to on the host (32 with AVX2, 16 with SSE only, 64 with AVX-512);
+    rows are processed independently (cvtColor does not flatten continuous images)."""
     f32 = np.float32
-    h = hsv[..., 0].astype(f32) * f32(6. / 180.)
-    s = hsv[..., 1].astype(f32) * f32(1. / 255.)
-    v = hsv[..., 2].astype(f32) * f32(1. / 255.)
+    hsv = np.asarray(hsv)
+    assert hsv.ndim == 3 and hsv.shape[2] == 3
+    W = hsv.shape[1]
+    h = (hsv[..., 0].astype(f32) * f32(f32(6.) / f32(180.))).astype(f32)
+    s = (hsv[..., 1].astype(f32) * f32(1. / 255.)).astype(f32)
+    v = (hsv[..., 2].astype(f32) * f32(1. / 255.)).astype(f32)
     sector = np.floor(h)
-    hf = h - sector
-    sec = sector.astype(np.int64) % 6
+    hf = (h - sector).astype(f32)
+    sec = sector.astype(np.int64)
+    oob = (sec < 0) | (sec >= 6)
+    sec = np.where(oob, 0, sec)
+    hf = np.where(oob, f32(0), hf)
+    one = np.ones_like(s)
     t0 = v
-    t1 = v * (f32(1) - s)
-    t2 = v * (f32(1) - s * hf)
-    t3 = v * (f32(1) - s * (f32(1) - hf))
+    t1 = (v * (f32(1) - s)).astype(f32)
+    t2 = (v * _fma32(-s, hf, one)).astype(f32)
+    t3 = (v * _fma32(-s, (f32(1) - hf).astype(f32), one)).astype(f32)
     tab = np.stack([t0, t1, t2, t3], axis=-1)
     idx = np.array([[1, 3, 0], [1, 0, 2], [3, 0, 1], [0, 2, 1], [0, 1, 3], [2, 1, 0]])
     sel = idx[sec]
@@ -542,8 +564,68 @@ def hsv2bgr_u8(hsv):
     b = np.where(grey, v, b)
     g = np.where(grey, v, g)
     r = np.where(grey, v, r)
-    out = np.stack([b, g, r], axis=-1) * f32(255)
-    return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+    out = (np.stack([b, g, r], axis=-1) * f32(255)).astype(f32)
+    body = (np.arange(W) < W - W % int(vec))[None, :, None]
+    return np.clip(np.where(body, np.trunc(out), np.rint(out)), 0, 255).astype(np.uint8)
+
+
+def probe_hsv_vec():
+    """SIMD width of cv2's HSV2BGR on this host: the pixel (H, S, V) = (0, 1, 1) becomes (0, 0, 1) in the
+    truncating SIMD body and (1, 1, 1) in the rounding tail; a row of 255 pixels has 255 % vec tail pixels."""
+    import cv2
+    row = np.tile(np.array([0, 1, 1], np.uint8), (1, 255, 1))
+    tail = int((cv2.cvtColor(row, cv2.COLOR_HSV2BGR)[0, :, 0] == 1).sum())
+    return tail + 1
+
+
+# --------------------------------------------------------------------------------------
+# cv2.resize(uint8, INTER_LINEAR)            (reference reader.py:41,53, augmentation.py:160)
+# --------------------------------------------------------------------------------------
+
+def _resize_axis_u8(dn, sn, clamp_frac):
+    """OpenCV resize.cpp (8-bit INTER_LINEAR, INTER_RESIZE_COEF_BITS = 11): scale = 1. / (dn / sn) in double,
+    f = (float)((d + 0.5) * scale - 0.5), i = floor(f), f -= i; horizontally the fraction is forced to 0 where
+    the tap pair would leave the row (i < 0 or i >= sn - 1) - vertically it is NOT (rows are clipped instead,
+    both taps then read the same row with their two separately truncated weights); coefficients
+    cvRound((1 - f) * 2048), cvRound(f * 2048) from float32 products."""
+    scale = 1.0 / (float(dn) / float(sn))
+    d = np.arange(dn, dtype=np.float64)
+    f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    i = np.floor(f).astype(np.int64)
+    f = (f - i.astype(np.float32)).astype(np.float32)
+    if clamp_frac:
+        lo = i < 0
+        f[lo] = 0
+        i[lo] = 0
+        hi = i >= sn - 1
+        f[hi] = 0
+        i[hi] = sn - 1
+    w0 = np.rint((np.float32(1.0) - f) * np.float32(2048)).astype(np.int64)
+    w1 = np.rint(f * np.float32(2048)).astype(np.int64)
+    return i, w0, w1
+
+
+def resize_linear_u8(src, dsize):
+    """``cv2.resize(src uint8 (H, W[, C]), dsize=(width, height), interpolation=cv2.INTER_LINEAR)``, bit-exact for
+    opencv-python-headless 4.13 [probed: 0 mismatches on random images, up- and down-scaling, 1 and 3 channels,
+    optimisations on or off].  Horizontal pass: int32 rows S = s[i]*a0 + s[i+1]*a1 (11-bit coefficients);
+    vertical pass: (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.  Exact 2x reductions in both
+    directions are INTER_AREA in OpenCV (2x2 block mean, (a + b + c + d + 2) >> 2)."""
+    src = np.asarray(src)
+    assert src.dtype == np.uint8
+    dw, dh = int(dsize[0]), int(dsize[1])
+    sh, sw = src.shape[:2]
+    s = src.reshape(sh, sw, -1).astype(np.int64)
+    if sw == 2 * dw and sh == 2 * dh:
+        out = (s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2
+        return out.astype(np.uint8).reshape((dh, dw) + src.shape[2:])
+    xi, a0, a1 = _resize_axis_u8(dw, sw, True)
+    yi, b0, b1 = _resize_axis_u8(dh, sh, False)
+    x1 = np.minimum(xi + 1, sw - 1)
+    rows = s[:, xi] * a0[None, :, None] + s[:, x1] * a1[None, :, None]
+    S0, S1 = rows[np.clip(yi, 0, sh - 1)], rows[np.clip(yi + 1, 0, sh - 1)]
+    out = (((b0[:, None, None] * (S0 >> 4)) >> 16) + ((b1[:, None, None] * (S1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8).reshape((dh, dw) + src.shape[2:])
 
 
 def illumination_sv(x_u8, a, b, c):
@@ -553,12 +635,13 @@ def illumination_sv(x_u8, a, b, c):
     return (255. * new).astype(np.uint8)
 
 
-def change_illumination(bgr, a, b, c):
+def change_illumination(bgr, a, b, c, vec=HSV_VEC):
+    """augmentation.py:88-99, bit-exact for a host whose cv2 converts `vec` pixels per SIMD step."""
     hsv = bgr2hsv_u8(bgr)
     out = hsv.copy()
     out[..., 1] = illumination_sv(hsv[..., 1], a, b, c)
     out[..., 2] = illumination_sv(hsv[..., 2], a, b, c)
-    return hsv2bgr_u8(out)
+    return hsv2bgr_u8(out, vec)
 
 
 # --------------------------------------------------------------------------------------

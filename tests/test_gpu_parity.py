@@ -246,8 +246,12 @@ def test_warp_affine_random_vs_oracle(vm):
 def test_illumination_stats_golden(vm, golden):
     A = vm.augmentation
     got = A.change_illumination(golden["ci_bgr"], 1.03, 0.8, -0.02)
-    assert np.abs(got.astype(int) - golden["ci_out"].astype(int)).max() <= 1
-    assert np.array_equal(got, O.change_illumination(golden["ci_bgr"], 1.03, 0.8, -0.02))
+    vec = vm._native.hsv_vec()                       # the fixtures were made on an AVX2 host (32 pixels per SIMD step of cv2)
+    assert np.array_equal(got, O.change_illumination(golden["ci_bgr"], 1.03, 0.8, -0.02, vec))
+    if vec == 32:
+        assert np.array_equal(got, golden["ci_out"])
+    else:
+        assert np.abs(got.astype(int) - golden["ci_out"].astype(int)).max() <= 1
     alpha = golden["wi_fg"][..., 3] / 255.
     assert A.object_size(alpha) == float(golden["stats_size"])
     assert tuple(A.fg_center(alpha)) == tuple(golden["stats_center"])
@@ -265,10 +269,13 @@ def test_augment_golden(vm, golden):
     O.augment_params(bgr.shape[0], bgr.shape[1], alpha)
     assert after == np.random.uniform(), "augment must consume the reference's 40 RNG draws"
     assert nal.dtype == np.float64 and np.allclose(nal, golden["aug_alpha_out"], rtol=RTOL, atol=1e-6)
-    assert np.abs(nbg.astype(int) - golden["aug_bg_out"].astype(int)).max() <= 1
-    # fg: +-1 from HSV2BGR, plus knife-edge flips amplified by the colour transform
-    d = np.abs(nfg.astype(int) - golden["aug_fg_out"].astype(int))
-    assert np.count_nonzero(d > 1) <= 2
+    if vm._native.hsv_vec() == 32:                    # same SIMD width as the host that made the fixtures: exact
+        assert np.array_equal(nbg, golden["aug_bg_out"])
+        # fg: bit-exact up to TPS knife-edge flips (<= 2 pixels), which the colour transform may amplify
+        assert np.count_nonzero((nfg != golden["aug_fg_out"]).any(axis=2)) <= 2
+    else:
+        assert np.abs(nbg.astype(int) - golden["aug_bg_out"].astype(int)).max() <= 1
+        assert np.count_nonzero(np.abs(nfg.astype(int) - golden["aug_fg_out"].astype(int)) > 1) <= 2
 
 
 # ------------------------------------------------------------------------- fused C3 / C4
@@ -632,8 +639,12 @@ def test_augment_clip_golden(vm, golden):
     np.random.seed(77)
     nfg, nbg, nal = vm.augmentation.augment_clip(bgra[None], bg[None])
     assert np.allclose(nal[0], golden["aug_alpha_out"], rtol=RTOL, atol=1e-6)
-    assert np.abs(nbg[0].astype(int) - golden["aug_bg_out"].astype(int)).max() <= 1
-    assert np.count_nonzero(np.abs(nfg[0].astype(int) - golden["aug_fg_out"].astype(int)) > 1) <= 2
+    if vm._native.hsv_vec() == 32:
+        assert np.array_equal(nbg[0], golden["aug_bg_out"])
+        assert np.count_nonzero((nfg[0] != golden["aug_fg_out"]).any(axis=2)) <= 2
+    else:
+        assert np.abs(nbg[0].astype(int) - golden["aug_bg_out"].astype(int)).max() <= 1
+        assert np.count_nonzero(np.abs(nfg[0].astype(int) - golden["aug_fg_out"].astype(int)) > 1) <= 2
 
 
 def test_augmentation_writer_matches_sequential_augment(vm, tmp_path, capsys):

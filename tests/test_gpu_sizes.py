@@ -271,3 +271,57 @@ def test_tps_warp_images_order0_vs_oracle(vm):
     t0[0, :6] = [-1e-9, 0.0, 0.5, 1.5, h - 1.0, h - 1 + 1e-7]; t1[0, :6] = 2.5
     got = vm.pipeline.map_coordinates(dev(img), dev(t0), dev(t1), order=0).cpu().numpy()
     assert np.array_equal(got, O.map_coordinates_nearest(img, t0, t1))
+
+
+# ------------------------------------------------------------------------------------ row f2: exact resize / HSV2BGR
+
+def test_resize_u8_bit_exact_vs_cv2_and_oracle(vm):
+    """cv2.resize(uint8, INTER_LINEAR) on the device: equal to this host's cv2 and to the oracle, up- and down-scaling,
+    1 / 3 / 4 channels, the 2x INTER_AREA switch, batches; config 1's background (sea.jpg -> 500 x 1200) by digest."""
+    import cv2
+    P = vm.pipeline
+    rng = np.random.default_rng(0)
+    shapes = [(300, 400, 500, 1200), (333, 517, 500, 1200), (375, 500, 1080, 1920), (1080, 1920, 512, 512), (100, 100, 37, 53),
+              (64, 64, 128, 128), (128, 128, 64, 64), (128, 130, 64, 65), (5, 7, 50, 120), (1, 1, 4, 4), (2, 3, 1, 1), (17, 31, 16, 30)]
+    for sh, sw, dh, dw in shapes:
+        for cn in (1, 3, 4):
+            src = rng.integers(0, 256, (sh, sw, cn) if cn > 1 else (sh, sw), dtype=np.uint8)
+            got = P.resize_u8(dev(src), (dw, dh)).cpu().numpy()
+            assert np.array_equal(got, O.resize_linear_u8(src, (dw, dh))), (sh, sw, dh, dw, cn)
+            assert np.array_equal(got, cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR)), (sh, sw, dh, dw, cn)
+    batch = rng.integers(0, 256, (3, 90, 70, 3), dtype=np.uint8)
+    got = P.resize_u8(dev(batch), (111, 64)).cpu().numpy()
+    for k in range(3):
+        assert np.array_equal(got[k], cv2.resize(batch[k], (111, 64), interpolation=cv2.INTER_LINEAR))
+    with np.load(os.path.join(ROOT, "tests", "golden", "c1_full_golden.npz")) as z:
+        jpg, want = z["sea_jpg"], z["sha_bg"]
+    bg = vm.reader.resize_background(cv2.imdecode(jpg, cv2.IMREAD_COLOR), 500, 1200)
+    assert isinstance(bg, np.ndarray) and np.array_equal(sha(bg), want)
+
+
+def test_change_illumination_bit_exact(vm, golden):
+    """augmentation.change_illumination: BGR2HSV / HSV2BGR exactly as this host's cv2 computes them (truncating SIMD
+    body, rounding row tail), against cv2 itself, the oracle, the reference fixture (made on an AVX2 host: 32 pixels
+    per step) and - when baseline/_ref travels - the unmodified reference function."""
+    import cv2
+    vec = vm._native.hsv_vec()
+    assert vec == O.probe_hsv_vec()
+    rng = np.random.default_rng(12)
+    for (h, w), (a, b, c) in (((37, 53), (1.03, 0.8, -0.02)), ((40, 64), (0.95, 1.3, 0.07)), ((21, 100), (1.05, 0.7, -0.07)),
+                              ((8, 1), (1.0, 1.0, 0.0)), ((3, 257), (0.97, 0.9, 0.05))):
+        bgr = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        got = vm.augmentation.change_illumination(bgr, a, b, c)
+        assert np.array_equal(got, O.change_illumination(bgr, a, b, c, vec)), (h, w)
+        hsv = cv2.cvtColor(bgr, cv2.COLOR_BGR2HSV)
+        lut = vm.augmentation.illumination_lut(a, b, c)
+        hsv[..., 1] = lut[hsv[..., 1]]; hsv[..., 2] = lut[hsv[..., 2]]
+        assert np.array_equal(got, cv2.cvtColor(hsv, cv2.COLOR_HSV2BGR)), (h, w)
+    lut = vm.augmentation.illumination_lut(1.03, 0.8, -0.02)
+    got = vm.pipeline.illumination(dev(golden["ci_bgr"]), lut, hsv_vec=32).cpu().numpy()
+    assert np.array_equal(got, golden["ci_out"])
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import refshim
+    if refshim.reference_dir() is not None:
+        aug = refshim.load(("augmentation",))["augmentation"]
+        bgr = rng.integers(0, 256, (45, 71, 3), dtype=np.uint8)
+        assert np.array_equal(vm.augmentation.change_illumination(bgr, 1.02, 1.1, 0.03), aug.change_illumination(bgr, 1.02, 1.1, 0.03))

@@ -36,6 +36,8 @@ SIGNATURES = {
     "vm_warp_affine": [_P, _I, _I, _I, _I, _P, _I, _I, _P, _P],
     "vm_change_illumination": [_P, _L, _D, _D, _D, _P, _P],
     "vm_illumination_lut": [_P, _L, _P, _P, _P],
+    "vm_illumination_lut_rows": [_P, _L, _I, _P, _I, _P, _P],
+    "vm_resize_u8": [_P, _I, _I, _I, _I, _P, _I, _I, _P],
     "vm_alpha_stats": [_P, _I, _I, _I, _P, _P],
     "vm_flow_warp_mask_bgra": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "vm_fused_scratch_bytes": [_I, _I, _I],
@@ -45,7 +47,7 @@ SIGNATURES = {
     "vm_tps_coarse_packed": [_P, _P, _I, _I, _I, _I, _D, _D, _P, _P, _P],
     "vm_aug_tps": [_P, _P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "vm_alpha_stats_bgra": [_P, _I, _I, _I, _P, _P],
-    "vm_aug_affine": [_I, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "vm_aug_affine": [_I, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _P],
     "vm_loader_batch": [_P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P],
     "vm_sq_err_sum": [_P, _P, _I, _L, _P, _P],
     "vm_trimap_from_matte": [_P, _I, _I, _I, _I, _P, _P],
@@ -150,6 +152,25 @@ def from_device(t, kind):
 
 def new_status(device=None):
     return torch.zeros(STATUS_WORDS, dtype=torch.int32, device=device or "cuda")
+
+
+_hsv_vec = [None]
+
+
+def hsv_vec():
+    """Pixels cv2's HSV2BGR converts per SIMD step on this host (its results are truncated in the SIMD body of a
+    row and rounded in the scalar tail, include/vm_b200.h).  Probed once with cv2 itself: the pixel (H, S, V) =
+    (0, 1, 1) becomes (0, 0, 1) in the body and (1, 1, 1) in the tail; a row of 255 pixels has 255 % vec tail
+    pixels.  32 (AVX2) when cv2 cannot be asked."""
+    if _hsv_vec[0] is None:
+        try:
+            import cv2
+            row = np.tile(np.array([0, 1, 1], np.uint8), (1, 255, 1))
+            tail = int((cv2.cvtColor(row, cv2.COLOR_HSV2BGR)[0, :, 0] == 1).sum())
+            _hsv_vec[0] = tail + 1 if tail + 1 in (16, 32, 64, 128, 256) else 32
+        except Exception:
+            _hsv_vec[0] = 32
+    return _hsv_vec[0]
 
 
 def set_option(key, value):

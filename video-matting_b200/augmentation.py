@@ -257,9 +257,9 @@ def _augment_run(fg_d, bg_d, plan, alpha_dtype=torch.float32, status=None):
     N.check(lib.vm_aug_tps(N.ptr(fg_d), N.ptr(T), tplan.nx, tplan.ny, N.ptr(tplan.rows), N.ptr(tplan.cols), n, h, w,
                            N.ptr(inter), N.ptr(a64), N.ptr(status), N.stream_ptr()))
     N.check(lib.vm_aug_affine(1, N.ptr(inter), N.ptr(a64), N.ptr(par_fg_d), N.ptr(luts_d), n, h, w, N.ptr(new_fg),
-                              None if wide else N.ptr(new_alpha), N.ptr(new_alpha) if wide else None, N.stream_ptr()))
+                              None if wide else N.ptr(new_alpha), N.ptr(new_alpha) if wide else None, N.hsv_vec(), N.stream_ptr()))
     N.check(lib.vm_aug_affine(0, N.ptr(bg_d), None, N.ptr(par_bg_d), N.ptr(luts_d), n, h, w, N.ptr(new_bg), None, None,
-                              N.stream_ptr()))
+                              N.hsv_vec(), N.stream_ptr()))
     return new_fg, new_bg, new_alpha
 
 

@@ -67,42 +67,49 @@ extern "C" int vm_warp_affine(const void *src, int dtype, int channels, int sh, 
 // ---------------------------------------------------------------------------------------
 struct VmLut256 { uint8_t v[256]; };
 
-// one pixel of change_illumination: BGR2HSV (integer tables) -> S/V through `slut` -> HSV2BGR (float
-// formulation of OpenCV's HSV2RGB_f with hscale = 6/180).  Returns B | G<<8 | R<<16.
+// one pixel of change_illumination: BGR2HSV (integer tables) -> S/V through `slut` -> HSV2BGR, bit-exact for
+// OpenCV 4.13's 8-bit HSV2BGR (probed over all 180 x 256 x 256 inputs against cv2, see the CPU test suite):
+//   s = S*(1/255.f), v = V*(1/255.f), hh = H*(6.f/180.f), f = hh - floor(hh),
+//   tab = {v, v*(1-s), v*fma(-s,f,1), v*fma(-s,1-f,1)}, out = tab*255.f,
+//   TRUNCATED in the SIMD body of a row (`trunc`), rounded half-to-even in the row's scalar tail.
+// Returns B | G<<8 | R<<16.
 __device__ __forceinline__ uint32_t vm_illum_px(int b, int g, int r, const int *__restrict__ sdiv, const int *__restrict__ hdiv,
-                                                const uint8_t *__restrict__ slut) {
+                                                const uint8_t *__restrict__ slut, bool trunc) {
     const int v = max(max(b, g), r), vmin = min(min(b, g), r), d = v - vmin;
     int hh = (v == r) ? (g - b) : ((v == g) ? (b - r + 2 * d) : (r - g + 4 * d));
     const int s = (d * sdiv[v] + (1 << 11)) >> 12;
     hh = (hh * hdiv[d] + (1 << 11)) >> 12;
     if (hh < 0) hh += 180;
     const int s2 = slut[s], v2 = slut[v];
-    const float fv = (float)v2 * (1.f / 255.f), fs = (float)s2 * (1.f / 255.f);
+    const float fv = __fmul_rn((float)v2, 1.f / 255.f), fs = __fmul_rn((float)s2, 1.f / 255.f);
     float ob = fv, og = fv, orr = fv;
     if (s2 != 0) {
-        float hf = (float)hh * (6.f / 180.f);
+        float hf = __fmul_rn((float)hh, 6.f / 180.f);
         const float fl = floorf(hf);
         int sec = (int)fl;
-        hf -= fl;
-        sec %= 6; if (sec < 0) sec += 6;
+        hf = __fsub_rn(hf, fl);
+        if ((unsigned)sec >= 6u) { sec = 0; hf = 0.f; }
         float tab[4];
         tab[0] = fv;
-        tab[1] = __fmul_rn(fv, 1.f - fs);
-        tab[2] = __fmul_rn(fv, 1.f - __fmul_rn(fs, hf));
-        tab[3] = __fmul_rn(fv, 1.f - __fmul_rn(fs, 1.f - hf));
+        tab[1] = __fmul_rn(fv, __fsub_rn(1.f, fs));
+        tab[2] = __fmul_rn(fv, __fmaf_rn(-fs, hf, 1.f));
+        tab[3] = __fmul_rn(fv, __fmaf_rn(-fs, __fsub_rn(1.f, hf), 1.f));
         const int ib[6] = {1, 1, 3, 0, 0, 2}, ig[6] = {3, 0, 0, 2, 1, 1}, ir[6] = {0, 2, 1, 1, 3, 0};
         ob = tab[ib[sec]]; og = tab[ig[sec]]; orr = tab[ir[sec]];
     }
-    const uint32_t B = (uint32_t)max(0, min(255, __float2int_rn(ob * 255.f)));
-    const uint32_t G = (uint32_t)max(0, min(255, __float2int_rn(og * 255.f)));
-    const uint32_t R = (uint32_t)max(0, min(255, __float2int_rn(orr * 255.f)));
+    const float xb = __fmul_rn(ob, 255.f), xg = __fmul_rn(og, 255.f), xr = __fmul_rn(orr, 255.f);
+    const uint32_t B = (uint32_t)max(0, min(255, trunc ? __float2int_rz(xb) : __float2int_rn(xb)));
+    const uint32_t G = (uint32_t)max(0, min(255, trunc ? __float2int_rz(xg) : __float2int_rn(xg)));
+    const uint32_t R = (uint32_t)max(0, min(255, trunc ? __float2int_rz(xr) : __float2int_rn(xr)));
     return B | (G << 8) | (R << 16);
 }
 
-
+// cv2 converts `vec` pixels per SIMD step and rows independently: pixel x of a row of w pixels is in the truncating
+// SIMD body iff x < w - w % vec
+__device__ __forceinline__ bool vm_hsv_body(int x, int w, int vec) { return x < w - w % vec; }
 
 __global__ void __launch_bounds__(256)
-k_illumination(const uint8_t *__restrict__ bgr, int64_t npx, VmLut256 lut, uint8_t *__restrict__ out) {
+k_illumination(const uint8_t *__restrict__ bgr, int64_t rows, int w, int vec, VmLut256 lut, uint8_t *__restrict__ out) {
     __shared__ int sdiv[256], hdiv[256];
     __shared__ uint8_t slut[256];
     {
@@ -112,21 +119,31 @@ k_illumination(const uint8_t *__restrict__ bgr, int64_t npx, VmLut256 lut, uint8
         slut[k] = lut.v[k];
     }
     __syncthreads();
+    const int64_t npx = rows * w;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npx;
          p += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t o = vm_illum_px(bgr[p * 3], bgr[p * 3 + 1], bgr[p * 3 + 2], sdiv, hdiv, slut);
+        const int x = (int)(p % w);
+        const uint32_t o = vm_illum_px(bgr[p * 3], bgr[p * 3 + 1], bgr[p * 3 + 2], sdiv, hdiv, slut, vm_hsv_body(x, w, vec));
         out[p * 3] = (uint8_t)o; out[p * 3 + 1] = (uint8_t)(o >> 8); out[p * 3 + 2] = (uint8_t)(o >> 16);
     }
 }
 
-extern "C" int vm_illumination_lut(const uint8_t *bgr, int64_t npx, const uint8_t *lut_host,
-                                   uint8_t *out, void *stream) {
+extern "C" int vm_illumination_lut_rows(const uint8_t *bgr, int64_t rows, int w, const uint8_t *lut_host, int vec,
+                                        uint8_t *out, void *stream) {
     VM_REQUIRE(bgr && lut_host && out, "null pointer");
-    if (npx <= 0) return VM_OK;
+    VM_REQUIRE(rows >= 0 && w >= 0 && vec >= 1 && vec <= 1024, "bad size");
+    if (rows * w <= 0) return VM_OK;
     VmLut256 lut;
     for (int k = 0; k < 256; ++k) lut.v[k] = lut_host[k];
-    k_illumination<<<min(vm_blocks(npx, 256), 148u * 16u), 256, 0, (cudaStream_t)stream>>>(bgr, npx, lut, out);
+    k_illumination<<<min(vm_blocks(rows * w, 256), 148u * 16u), 256, 0, (cudaStream_t)stream>>>(bgr, rows, w, vec, lut, out);
     return vm_check_launch("vm_change_illumination");
+}
+
+// the buffer as ONE row of npx pixels on an AVX2 host (32 pixels per SIMD step); images go through vm_illumination_lut_rows
+extern "C" int vm_illumination_lut(const uint8_t *bgr, int64_t npx, const uint8_t *lut_host,
+                                   uint8_t *out, void *stream) {
+    VM_REQUIRE(npx < (1ll << 31), "too many pixels for one row");
+    return vm_illumination_lut_rows(bgr, 1, (int)npx, lut_host, 32, out, stream);
 }
 
 extern "C" int vm_change_illumination(const uint8_t *bgr, int64_t npx, double a, double b, double c,
@@ -139,6 +156,68 @@ extern "C" int vm_change_illumination(const uint8_t *bgr, int64_t npx, double a,
         lut[k] = (uint8_t)(255. * nv);
     }
     return vm_illumination_lut(bgr, npx, lut, out, stream);
+}
+
+// ---------------------------------------------------------------------------------------
+// cv2.resize(uint8, INTER_LINEAR) (reader.py:41,53, augmentation.py:160), bit-exact for OpenCV 4.13:
+// 11-bit coefficients from float32 fractions, int32 horizontal pass, vertical pass
+// (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2; the horizontal fraction is forced to 0 at the row
+// ends, vertically rows are clipped instead; exact 2x reductions are the 2x2 block mean (OpenCV switches to INTER_AREA).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void vm_resize_coef(int d, double scale, int sn, bool clamp_frac, int &i, int &w0, int &w1) {
+    float f = (float)(((double)d + 0.5) * scale - 0.5);
+    const float fl = floorf(f);
+    i = (int)fl;
+    f = __fsub_rn(f, fl);
+    if (clamp_frac) {
+        if (i < 0) { i = 0; f = 0.f; }
+        if (i >= sn - 1) { i = sn - 1; f = 0.f; }
+    }
+    w0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+    w1 = __float2int_rn(__fmul_rn(f, 2048.f));
+}
+
+template <int C>
+__global__ void __launch_bounds__(256)
+k_resize_u8(const uint8_t *__restrict__ src, int sh, int sw, uint8_t *__restrict__ dst, int dh, int dw, double scale_x,
+            double scale_y, int area2) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, img = blockIdx.z;
+    if (x >= dw) return;
+    const uint8_t *s = src + (int64_t)img * sh * sw * C;
+    uint8_t *o = dst + (((int64_t)img * dh + y) * dw + x) * C;
+    if (area2) {
+        const uint8_t *p0 = s + ((int64_t)(2 * y) * sw + 2 * x) * C, *p1 = p0 + (int64_t)sw * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) o[c] = (uint8_t)((p0[c] + p0[C + c] + p1[c] + p1[C + c] + 2) >> 2);
+        return;
+    }
+    int xi, a0, a1, yi, b0, b1;
+    vm_resize_coef(x, scale_x, sw, true, xi, a0, a1);
+    vm_resize_coef(y, scale_y, sh, false, yi, b0, b1);
+    const int x1 = min(xi + 1, sw - 1), r0 = max(0, min(yi, sh - 1)), r1 = max(0, min(yi + 1, sh - 1));
+    const uint8_t *q0 = s + (int64_t)r0 * sw * C, *q1 = s + (int64_t)r1 * sw * C;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int S0 = __ldg(q0 + xi * C + c) * a0 + __ldg(q0 + x1 * C + c) * a1;
+        const int S1 = __ldg(q1 + xi * C + c) * a0 + __ldg(q1 + x1 * C + c) * a1;
+        const int v = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+        o[c] = (uint8_t)max(0, min(255, v));
+    }
+}
+
+extern "C" int vm_resize_u8(const uint8_t *src, int n, int sh, int sw, int channels, uint8_t *dst, int dh, int dw, void *stream) {
+    VM_REQUIRE(src && dst, "null pointer");
+    VM_REQUIRE(n >= 0 && n < 65536 && sh >= 1 && sw >= 1 && dh >= 1 && dw >= 1 && dh < 65536, "bad size");
+    if (n == 0) return VM_OK;
+    const double scale_x = 1.0 / ((double)dw / (double)sw), scale_y = 1.0 / ((double)dh / (double)sh);   // OpenCV: 1. / inv_scale
+    const int area2 = (sw == 2 * dw && sh == 2 * dh) ? 1 : 0;
+    const dim3 grid((dw + 255) / 256, dh, n);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (channels == 1) k_resize_u8<1><<<grid, 256, 0, st>>>(src, sh, sw, dst, dh, dw, scale_x, scale_y, area2);
+    else if (channels == 3) k_resize_u8<3><<<grid, 256, 0, st>>>(src, sh, sw, dst, dh, dw, scale_x, scale_y, area2);
+    else if (channels == 4) k_resize_u8<4><<<grid, 256, 0, st>>>(src, sh, sw, dst, dh, dw, scale_x, scale_y, area2);
+    else { vm_set_error("vm_resize_u8: channels must be 1, 3 or 4"); return VM_ERR_ARG; }
+    return vm_check_launch("vm_resize_u8");
 }
 
 // ---------------------------------------------------------------------------------------
@@ -231,7 +310,7 @@ template <bool FG>
 __global__ void __launch_bounds__(256)
 k_aug_affine(const void *__restrict__ src_all, const double *__restrict__ alpha64, const VmAugParams *__restrict__ params,
              const uint8_t *__restrict__ luts, int h, int w, uint8_t *__restrict__ out_bgr, float *__restrict__ out_alpha,
-             double *__restrict__ out_alpha64) {
+             double *__restrict__ out_alpha64, int vec) {
     __shared__ int sdiv[256], hdiv[256];
     __shared__ uint8_t slut[256];
     __shared__ VmAffineInv Ash;
@@ -288,7 +367,7 @@ k_aug_affine(const void *__restrict__ src_all, const double *__restrict__ alpha6
 #pragma unroll
         for (int k = 0; k < 3; ++k)
             ch[k] = VmTap<uint8_t>::blend((c[0] >> (8 * k)) & 255, (c[1] >> (8 * k)) & 255, (c[2] >> (8 * k)) & 255, (c[3] >> (8 * k)) & 255, fx, fy);
-        const uint32_t o = vm_illum_px(ch[0], ch[1], ch[2], sdiv, hdiv, slut);
+        const uint32_t o = vm_illum_px(ch[0], ch[1], ch[2], sdiv, hdiv, slut, vm_hsv_body(x, w, vec));
         const int64_t p = ((int64_t)frame * h + y) * w + x;
         out_bgr[p * 3] = (uint8_t)o; out_bgr[p * 3 + 1] = (uint8_t)(o >> 8); out_bgr[p * 3 + 2] = (uint8_t)(o >> 16);
         if (FG) {
@@ -301,14 +380,15 @@ k_aug_affine(const void *__restrict__ src_all, const double *__restrict__ alpha6
 // mode 0: background (src = (n,h,w,3) uint8, out_alpha unused); mode 1: foreground (src = vm_aug_tps intermediate).
 // params: device array of n {double M[6]; int tu, tv}; luts: device (n, 256) uint8 S/V tables.
 extern "C" int vm_aug_affine(int mode, const void *src, const double *alpha64, const void *params, const uint8_t *luts, int n, int h,
-                             int w, uint8_t *out_bgr, float *out_alpha, double *out_alpha64, void *stream) {
+                             int w, uint8_t *out_bgr, float *out_alpha, double *out_alpha64, int hsv_vec, void *stream) {
     VM_REQUIRE(src && params && luts && out_bgr && (mode == 0 || out_alpha || out_alpha64), "null pointer");
+    VM_REQUIRE(hsv_vec >= 1 && hsv_vec <= 1024, "hsv_vec out of range");
     VM_REQUIRE(mode == 0 || (alpha64 != nullptr) == (out_alpha64 != nullptr), "float64 alpha needs both the float64 source plane and the float64 output");
     VM_REQUIRE(n >= 0 && n < 65536 && h >= 1 && h < 65536 && w >= 1, "bad size");
     if (n == 0) return VM_OK;
     const dim3 grid((w + 255) / 256, (h + VA_AFF_ROWS - 1) / VA_AFF_ROWS, n);
     cudaStream_t st = (cudaStream_t)stream;
-    if (mode == 1) k_aug_affine<true><<<grid, 256, 0, st>>>(src, alpha64, (const VmAugParams *)params, luts, h, w, out_bgr, out_alpha, out_alpha64);
-    else k_aug_affine<false><<<grid, 256, 0, st>>>(src, nullptr, (const VmAugParams *)params, luts, h, w, out_bgr, nullptr, nullptr);
+    if (mode == 1) k_aug_affine<true><<<grid, 256, 0, st>>>(src, alpha64, (const VmAugParams *)params, luts, h, w, out_bgr, out_alpha, out_alpha64, hsv_vec);
+    else k_aug_affine<false><<<grid, 256, 0, st>>>(src, nullptr, (const VmAugParams *)params, luts, h, w, out_bgr, nullptr, nullptr, hsv_vec);
     return vm_check_launch("vm_aug_affine");
 }

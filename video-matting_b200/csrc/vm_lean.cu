@@ -88,12 +88,14 @@ const void *vl_table_device() {
 #define VL_B1_THREADS (VL_B1_WARPS * 32)
 #define VL_B1_WARPS_HI 24
 #define VL_B1_THREADS_HI (VL_B1_WARPS_HI * 32)
-#define VL_RG 4                                    // coarse rows evaluated together
+#ifndef VL_RG
+#define VL_RG 4                                    // coarse rows evaluated together (4 or 8)
+#endif
 
 struct __align__(16) VlWarpSmem {
     double2 p[VL_MAX_N];                           // control point {x (row axis), y (column axis)}
     double2 wv[VL_MAX_N];                          // {w0 / 2, w1 / 2}
-    double4 dx2[VL_MAX_N];                         // (x_r - Px)^2 for the VL_RG rows of the group
+    double4 dx2[VL_RG / 4][VL_MAX_N];              // (x_r - Px)^2 for the VL_RG rows of the group
     double aff[8];
 };
 
@@ -227,7 +229,8 @@ k_lean_coarse(const double *__restrict__ ctrl, const double *__restrict__ coef, 
                         const double dx = (double)min(kg + r, kend) * step_x - px;
                         d[r] = dx * dx;
                     }
-                    Ws.dx2[a] = make_double4(d[0], d[1], d[2], d[3]);
+#pragma unroll
+                    for (int g = 0; g < VL_RG / 4; ++g) Ws.dx2[g][a] = make_double4(d[4 * g], d[4 * g + 1], d[4 * g + 2], d[4 * g + 3]);
                 }
                 __syncwarp();
                 double s0[VL_RG], s1[VL_RG];
@@ -236,8 +239,12 @@ k_lean_coarse(const double *__restrict__ ctrl, const double *__restrict__ coef, 
 #pragma unroll
                 for (int a = 0; a < NF; ++a) {
                     const double2 wv = Ws.wv[a];
-                    const double4 dx2 = Ws.dx2[a];
-                    const double dd[VL_RG] = {dx2.x, dx2.y, dx2.z, dx2.w};
+                    double dd[VL_RG];
+#pragma unroll
+                    for (int g = 0; g < VL_RG / 4; ++g) {
+                        const double4 dx2 = Ws.dx2[g][a];
+                        dd[4 * g] = dx2.x; dd[4 * g + 1] = dx2.y; dd[4 * g + 2] = dx2.z; dd[4 * g + 3] = dx2.w;
+                    }
                     double dy2a;
                     if (DYR) dy2a = dy2[a];
                     else { const double dy = y - Ws.p[a].y; dy2a = dy * dy; }

@@ -94,16 +94,38 @@ def warp_affine(src, M, dsize):
     return dst
 
 
-def illumination(bgr, lut):
-    """BGR2HSV -> S,V through a 256-entry table -> HSV2BGR (reference augmentation.py:88-99)."""
+def illumination(bgr, lut, hsv_vec=None):
+    """BGR2HSV -> S,V through a 256-entry table -> HSV2BGR (reference augmentation.py:88-99) of (..., H, W, 3)
+    uint8 images, bit-exact for this host's cv2 (``hsv_vec``: pixels per SIMD step of its HSV2BGR, probed by
+    default - the results of a row's SIMD body are truncated, those of its tail rounded)."""
     lib = N.load()
     bgr = bgr.contiguous()
-    assert bgr.dtype == torch.uint8 and bgr.shape[-1] == 3
+    assert bgr.dtype == torch.uint8 and bgr.dim() >= 2 and bgr.shape[-1] == 3
     lut = np.ascontiguousarray(lut, dtype=np.uint8)
     assert lut.shape == (256,)
     out = torch.empty_like(bgr)
-    N.check(lib.vm_illumination_lut(N.ptr(bgr), bgr.numel() // 3, lut.ctypes.data_as(ctypes.c_void_p),
-                                    N.ptr(out), N.stream_ptr()))
+    w = bgr.shape[-2]
+    rows = bgr.numel() // 3 // max(w, 1)
+    N.check(lib.vm_illumination_lut_rows(N.ptr(bgr), rows, w, lut.ctypes.data_as(ctypes.c_void_p),
+                                         int(hsv_vec or N.hsv_vec()), N.ptr(out), N.stream_ptr()))
+    return out
+
+
+def resize_u8(img, dsize):
+    """cv2.resize(img, dsize=(width, height), interpolation=cv2.INTER_LINEAR) for uint8 images (H, W), (H, W, C) or
+    a batch (n, H, W, C), C in {1, 3, 4} - bit-exact for OpenCV 4.13 (reference reader.py:41,53, augmentation.py:160)."""
+    lib = N.load()
+    img = img.contiguous()
+    assert img.dtype == torch.uint8 and img.dim() in (2, 3, 4)
+    dw, dh = int(dsize[0]), int(dsize[1])
+    if img.dim() == 2:
+        n, sh, sw, ch, shape = 1, img.shape[0], img.shape[1], 1, (dh, dw)
+    elif img.dim() == 3:
+        n, sh, sw, ch, shape = 1, img.shape[0], img.shape[1], img.shape[2], (dh, dw, img.shape[2])
+    else:
+        n, sh, sw, ch, shape = img.shape[0], img.shape[1], img.shape[2], img.shape[3], (img.shape[0], dh, dw, img.shape[3])
+    out = torch.empty(shape, dtype=torch.uint8, device=img.device)
+    N.check(lib.vm_resize_u8(N.ptr(img), n, sh, sw, ch, N.ptr(out), dh, dw, N.stream_ptr()))
     return out
 
 

@@ -58,6 +58,16 @@ def create_composite_image(fg, bg, alpha):
     return N.from_device(P.composite(f, b, a), kind)
 
 
+def resize_background(bg, h, w):
+    """cv2.resize(bg, dsize=(w, h), interpolation=cv2.INTER_LINEAR) (reference reader.py:40-41, 52-53,
+    augmentation.py:159-160) on the device - bit-exact for uint8 images (vm_resize_u8); NumPy in, NumPy out, CUDA
+    tensors stay on the device."""
+    src, kind = N.to_device(bg)
+    if src.dtype != torch.uint8:
+        raise TypeError("resize_background expects a uint8 image (as cv2.imread returns)")
+    return N.from_device(P.resize_u8(src, (w, h)), kind)
+
+
 def load_test_image(filename='in0062.png', bg_name='sea.jpg'):
     """loads a test image - reference reader.py:33-43 (paths relative to the cwd)."""
     import cv2
@@ -65,7 +75,7 @@ def load_test_image(filename='in0062.png', bg_name='sea.jpg'):
     bg = cv2.imread(os.path.join('test_data', bg_name))
     h, w = fg.shape[:2]
     if bg.shape[0] != h or bg.shape[1] != w:
-        bg = cv2.resize(bg, dsize=(w, h), interpolation=cv2.INTER_LINEAR)
+        bg = resize_background(bg, h, w)
     return fg, bg, create_composite_image(fg, bg, alpha), alpha
 
 
@@ -77,7 +87,7 @@ def load_test_video(folder_name='hairball2', bg_name='grass.jpg'):
     h, w = cv2.imread(os.path.join('test_data', folder_name, names[0])).shape[:2]
     bg = cv2.imread(os.path.join('test_data', bg_name))
     if bg.shape[0] != h or bg.shape[1] != w:
-        bg = cv2.resize(bg, dsize=(w, h), interpolation=cv2.INTER_LINEAR)
+        bg = resize_background(bg, h, w)
     fg_list, alpha_list, cmp_list = [], [], []
     for name in names:
         alpha, fg = read_fg_img(os.path.join('test_data', folder_name, name))
