@@ -232,7 +232,8 @@ def run_ours(args):
         return float(t.item())
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    solve_workers = max(1, min(8, (placement.get("cores") or os.cpu_count() or 2) - 1))
+    ncores = placement.get("cores") or os.cpu_count() or 2
+    solve_workers = max(1, min(8, ncores if ncores <= 4 else ncores - 1))       # the launching thread mostly waits: few cores -> use them all
     pool = P.SolverPool(solve_workers)
 
     fg, fb, ff, bg = make_clip(torch, 1234 + rank, CLIP, H, W, dev)
