@@ -59,6 +59,7 @@ def test_fuse_equals_lean_bit_for_bit(vm, h, w, n, n_ctrl):
         b, stb = run(vm, 4, args, forward)
         assert torch.equal(a, b), f"{h}x{w} forward={forward}: " + report_diff(a, b)
         assert sta[3] == stb[3], "same number of samples outside the source"
+        assert sta[6] == stb[6], "same number of near-knife-edge samples (status word 6)"
         assert sta[5] == 0
 
 

@@ -725,7 +725,8 @@ k_lean_fine(const void *__restrict__ src_all, const uint8_t *__restrict__ bg, in
     vl_fine_tile<SRC, false>(S, phase, src_all, bg, n_bg, frame0, T, nx, ny, rows, cols, h, w, rpt, rec, blockIdx.z, blockIdx.y, blockIdx.x,
                       out, outside, slow);
     if (status) {
-        if (outside) atomicAdd(status + VM_STATUS_TPS_OUTSIDE, outside);
+        if (outside & (VL_NEAR_KNIFE_UNIT - 1)) atomicAdd(status + VM_STATUS_TPS_OUTSIDE, outside & (VL_NEAR_KNIFE_UNIT - 1));
+        if (outside >= VL_NEAR_KNIFE_UNIT) atomicAdd(status + VM_STATUS_NEAR_KNIFE, outside / VL_NEAR_KNIFE_UNIT);
         if (slow) atomicAdd(status + VM_STATUS_SLOW_TILES, slow);
     }
 }

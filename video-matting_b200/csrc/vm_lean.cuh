@@ -74,6 +74,8 @@ template <> struct VlSrc<1> {                      // packed {bgr, TA}: alpha = 
     static __device__ __forceinline__ uint2 lds(const elem *p) { return *p; }
 };
 
+#define VL_NEAR_KNIFE_UNIT 65536                    // per-thread counter: low 16 bits = samples outside the source, high = near-knife samples
+
 // exact per-pixel evaluation (frame borders, samples outside the source, undecidable roundings):
 // scipy's float64 arithmetic on the fast path's coordinates.  `mask` bit c set =
 // recompute colour c; bit 3 = the fast geometry did not apply: recompute everything.
@@ -102,10 +104,13 @@ __device__ __noinline__ float4 vl_exact_px(const typename VlSrc<SRC>::elem *__re
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         if (mask & (1u << c)) {
-            const float col = (float)vm_round_half_up_u8(vm_mapcoord_blend(
-                s, (double)((e0.x >> (8 * c)) & 255u), (double)((e1.x >> (8 * c)) & 255u),
-                (double)((e2.x >> (8 * c)) & 255u), (double)((e3.x >> (8 * c)) & 255u)));
-            res[c] = __fmaf_rn(a2, col, na * bgv[c]);
+            const double v = vm_mapcoord_blend(s, (double)((e0.x >> (8 * c)) & 255u), (double)((e1.x >> (8 * c)) & 255u),
+                                               (double)((e2.x >> (8 * c)) & 255u), (double)((e3.x >> (8 * c)) & 255u));
+            // samples whose half-up rounding a 1e-9 level perturbation of the value could flip (knife-edge
+            // samples are counted, never masked): high half of the per-thread counter -> VM_STATUS_NEAR_KNIFE
+            const double fr = (v + 0.5) - floor(v + 0.5);
+            if (fr < 1e-9 || fr > 1.0 - 1e-9) *outside += VL_NEAR_KNIFE_UNIT;
+            res[c] = __fmaf_rn(a2, (float)vm_round_half_up_u8(v), na * bgv[c]);
         }
     }
     return make_float4(res[0], res[1], res[2], a2);
