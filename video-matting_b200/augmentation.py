@@ -230,7 +230,7 @@ def _alpha_stats_clip(fg_d):
     return stats.cpu().numpy()
 
 
-def _augment_run(fg_d, bg_d, plan, alpha_dtype=torch.float32, status=None):
+def _augment_run(fg_d, bg_d, plan, alpha_dtype=torch.float32, status=None, pool=None):
     """Device stages of augment() for a clip whose random parameters are known: host TPS solve (system built
     from the deformed grid, tps.py:51), spline, TPS resampling, fused affine passes + illumination.
     ``alpha_dtype`` float64 carries alpha through both stages in float64 with scipy's / OpenCV's operation
@@ -245,7 +245,7 @@ def _augment_run(fg_d, bg_d, plan, alpha_dtype=torch.float32, status=None):
     new_alpha = torch.empty((n, h, w), dtype=torch.float64 if wide else torch.float32, device=dev)
     a64 = torch.empty((n, h + 1, w + 1), dtype=torch.float64, device=dev) if wide else None
     tplan = P.get_plan((0, 0, h, w), 2, dev)
-    ctrl, coef = P.solve_grids(grids, dev)
+    ctrl, coef = P.solve_grids(grids, dev, pool=pool)
     up = lambda arr: torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).to(dev)
     par_bg_d, par_fg_d, luts_d = up(par_bg), up(par_fg), up(luts)
     T = torch.empty((n, tplan.nx, tplan.ny, 2), dtype=torch.float64, device=dev)
@@ -272,7 +272,7 @@ def alpha_stats(fg_bgra):
     return _alpha_stats_clip(fg_d.contiguous())
 
 
-def augment_clip(fg_bgra, bg, alpha_dtype=torch.float32, stats=None, status=None):
+def augment_clip(fg_bgra, bg, alpha_dtype=torch.float32, stats=None, status=None, pool=None):
     """augment() for a whole clip in a handful of launches (BASELINE config 5).
 
     ``fg_bgra`` (n, H, W, 4) uint8 BGRA with alpha = A/255 (what reader.read_fg_img returns, reference
@@ -284,7 +284,8 @@ def augment_clip(fg_bgra, bg, alpha_dtype=torch.float32, stats=None, status=None
     ``alpha_dtype=torch.float64`` returns the alpha in float64 as the reference does (same operation order);
     ``stats=alpha_stats(fg_bgra)`` skips the per-call alpha reduction and its host synchronisation;
     ``status`` (a device int32[8] block, ``_native.new_status()``) receives the count of TPS samples that fell
-    outside the source (word 3) - nothing is counted when it is None."""
+    outside the source (word 3) - nothing is counted when it is None; ``pool`` (a ``pipeline.SolverPool``) spreads the
+    per-frame ``np.linalg.pinv`` solves over host cores (same numpy call, bit-identical coefficients)."""
     fg_d, kind = N.to_device(fg_bgra)
     bg_d, _ = N.to_device(bg)
     assert fg_d.dtype == torch.uint8 and fg_d.dim() == 4 and fg_d.shape[3] == 4, "fg must be (n, H, W, 4) uint8 BGRA"
@@ -297,7 +298,7 @@ def augment_clip(fg_bgra, bg, alpha_dtype=torch.float32, stats=None, status=None
                  torch.empty((0, h, w), dtype=alpha_dtype, device=dev))
         return tuple(N.from_device(t, kind) for t in empty)
     plan = _augment_plan(_alpha_stats_clip(fg_d) if stats is None else np.asarray(stats), h, w)
-    return tuple(N.from_device(t, kind) for t in _augment_run(fg_d, bg_d, plan, alpha_dtype, status))
+    return tuple(N.from_device(t, kind) for t in _augment_run(fg_d, bg_d, plan, alpha_dtype, status, pool))
 
 
 #: variants written per foreground by augmentation() (reference augmentation.py:140) and how many of them go
@@ -328,7 +329,8 @@ def augmentation(dim_dataset, voc_dataset, sig_dataset):
 
     def load_bg(p, h, w):
         bg = cv2.imread(p)
-        return cv2.resize(bg, dsize=(w, h), interpolation=cv2.INTER_LINEAR)  # augmentation.py:159-160
+        return cv2.resize(bg, dsize=(w, h), interpolation=cv2.INTER_LINEAR)  # augmentation.py:159-160 (host thread; the
+        #                                                                       device twin is reader.resize_background)
 
     with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as pool:
         pending = []
@@ -344,10 +346,19 @@ def augmentation(dim_dataset, voc_dataset, sig_dataset):
             stats = np.repeat(_alpha_stats_clip(fg_d), n, axis=0)
             picks = []
             plan = _augment_plan(stats, h, w, before_frame=lambda i: picks.append(voc_list[np.random.randint(len(voc_list))]))
-            bg_jobs = [pool.submit(load_bg, p, h, w) for p in picks]
+            # backgrounds are decoded / resized at most two batches ahead of the device stages (bounded host memory:
+            # 50 resized backgrounds of a 3000 x 2000 foreground would be 0.9 GB)
+            bg_jobs = {}
+
+            def prefetch(upto):
+                for i in range(len(bg_jobs), min(upto, n)):
+                    bg_jobs[i] = pool.submit(load_bg, picks[i], h, w)
+
+            prefetch(2 * VARIANT_BATCH)
             for lo in range(0, n, VARIANT_BATCH):
                 hi = min(lo + VARIANT_BATCH, n)
-                bgs = [j.result() for j in bg_jobs[lo:hi]]
+                prefetch(hi + 2 * VARIANT_BATCH)
+                bgs = [bg_jobs.pop(i).result() for i in range(lo, hi)]
                 bg_d = torch.from_numpy(np.stack(bgs)).cuda()
                 sub = (plan[0][lo:hi], plan[1][lo:hi], plan[2][lo:hi], plan[3][lo:hi])
                 nfg, nbg, nal = _augment_run(fg_d.expand(hi - lo, h, w, 4).contiguous(), bg_d, sub, torch.float64)
