@@ -682,13 +682,13 @@ def augment_params(h, w, alpha, rng=None, n=5):
     return params_bg, params_fg, (grid, def_grid), (a, b, c)
 
 
-def augment(fg, bg, alpha, rng=None):
+def augment(fg, bg, alpha, rng=None, vec=HSV_VEC):
     h, w = fg.shape[:2]
     params_bg, params_fg, grids, (a, b, c) = augment_params(h, w, alpha, rng)
     new_bg = warp_image(bg, params_bg)
     new_fg = warp_image(fg, params_fg, thin=grids)
     new_alpha = warp_image(alpha, params_fg, thin=grids)
-    return change_illumination(new_fg, a, b, c), change_illumination(new_bg, a, b, c), new_alpha
+    return change_illumination(new_fg, a, b, c, vec), change_illumination(new_bg, a, b, c, vec), new_alpha
 
 
 # --------------------------------------------------------------------------------------

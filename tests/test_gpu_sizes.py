@@ -325,3 +325,33 @@ def test_change_illumination_bit_exact(vm, golden):
         aug = refshim.load(("augmentation",))["augmentation"]
         bgr = rng.integers(0, 256, (45, 71, 3), dtype=np.uint8)
         assert np.array_equal(vm.augmentation.change_illumination(bgr, 1.02, 1.1, 0.03), aug.change_illumination(bgr, 1.02, 1.1, 0.03))
+
+
+# ------------------------------------------------------------------------------------ config 5 at 1080p
+
+def test_config5_augment_1080p_vs_oracle(vm):
+    """augmentation.augment on one 1080p frame (config 5's size) against the oracle with the same np.random seed: the
+    background (affine + illumination) is bit-exact, the alpha within tolerance, the foreground bit-exact up to TPS
+    knife-edge pixels; and augment_clip with a solver pool gives the same frame."""
+    h, w = 1080, 1920
+    frame = O.synth_frame(5001, h, w)
+    bgr, alpha = np.ascontiguousarray(frame[..., :3]), frame[..., 3] / 255.
+    bg = O.synth_background(5, h, w)
+    vec = vm._native.hsv_vec()
+    np.random.seed(501)
+    nfg, nbg, nal = vm.augmentation.augment(bgr, bg, alpha)
+    state = np.random.get_state()[1][:4].copy()
+    np.random.seed(501)
+    rfg, rbg, ral = O.augment(bgr, bg, alpha, vec=vec)   # the oracle's default is the fixture host's SIMD width (32)
+    assert np.array_equal(state, np.random.get_state()[1][:4]), "same np.random consumption"
+    assert np.array_equal(nbg, rbg)
+    assert np.allclose(nal, ral, rtol=RTOL, atol=1e-6)
+    assert np.count_nonzero((nfg != rfg).any(axis=2)) <= 6, "foreground differs beyond TPS knife-edge pixels"
+    pool = vm.pipeline.SolverPool(2)
+    try:
+        np.random.seed(501)
+        cfg, cbg, cal = vm.augmentation.augment_clip(frame[None], bg[None], pool=pool)
+    finally:
+        pool.close()
+    assert np.array_equal(cbg[0], nbg) and np.allclose(cal[0], nal, rtol=RTOL, atol=1e-6)
+    assert np.count_nonzero((cfg[0] != nfg).any(axis=2)) <= 6
