@@ -1,4 +1,5 @@
-"""Device-resident throughput of the BASELINE.json configs 2-4 (one GPU): frames/s, algorithmic GB/s and
+"""(Round 1; since round 2 `bench.py` carries these configs in its own line - `configs`.)
+Device-resident throughput of the BASELINE.json configs 2-4 (one GPU): frames/s, algorithmic GB/s and
 fraction of the measured HBM peak.  python scripts/bench_configs.py [iters] > profiles/rNN_configs.json"""
 import json
 import os

@@ -41,7 +41,7 @@ for k in range(2):
     bgp.append(os.path.join(tmp, f"bg{k}.png")); cv2.imwrite(bgp[-1], O.synth_background(50 + k, H, W))
 file_bytes = sum(os.path.getsize(p) for p in fgp + fbp + ffp + bgp)
 
-grids = bench.make_grids(O, 1, n, H, W)
+grids = bench.make_grids(vm, 1, n, H, W)
 dev = torch.device("cuda", 0)
 ctrl, coef = P.solve_grids(grids, dev)
 out = torch.empty((n, H, W, 4), dtype=torch.float32, device=dev)

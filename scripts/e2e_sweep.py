@@ -10,7 +10,7 @@ vm = ge.load_package(); P = vm.pipeline
 dev = torch.device("cuda", 0)
 n, H, W = 64, bench.H, bench.W
 fg, fb, ff, bg = bench.make_clip(torch, 1, n, H, W, dev)
-grids = bench.make_grids(O, 1, n, H, W)
+grids = bench.make_grids(vm, 1, n, H, W)
 host = [t.cpu().pin_memory() for t in (fg, fb, ff)]
 bg_h = bg[torch.arange(n) % bg.shape[0]].cpu().pin_memory()
 out_h = torch.empty((n, H, W, 4), dtype=torch.float32).pin_memory()

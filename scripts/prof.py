@@ -21,14 +21,9 @@ vm = ge.load_package()
 P = vm.pipeline
 if os.environ.get("VM_VARIANT"):
     P.set_fused_variant(int(os.environ["VM_VARIANT"]))
-for key in ("pipe_lead", "pipe_ring_rows", "pipe_cring_rows", "pipe_blocks", "pipe_roles", "chunk_frames"):
-    if os.environ.get("VM_" + key.upper()):
-        vm._native.set_option(key, int(os.environ["VM_" + key.upper()]))
 for kv in filter(None, os.environ.get("VM_OPTS", "").split(",")):
     k, v = kv.split("=")
     vm._native.set_option(k, int(v))
-if os.environ.get("VM_TILE_H"):
-    vm._native.set_option("tile_h", int(os.environ["VM_TILE_H"]))
 dev = torch.device("cuda", 0)
 fg, fb, ff, bg = bench.make_clip(torch, 1234, n, H, W, dev)
 grids = bench.make_grids(vm, 1, n, H, W)
@@ -53,15 +48,3 @@ ms = e0.elapsed_time(e1) / iters
 bpp = {"c4": 39, "c3": 23, "c2": 27}[which]
 print(f"{which}: {n} frames {ms:.3f} ms/launch = {ms / n * 1e3:.1f} us/frame, "
       f"{bpp * H * W * n / ms / 1e6:.0f} GB/s algorithmic, status {st.tolist()}")
-
-if os.environ.get("VM_TIMING"):
-    import numpy as np
-    sc = next(iter(P._scratch_cache.values()))
-    off = (-sc.data_ptr()) % 256
-    hdr = sc[off:off + 64].cpu().numpy().view(np.uint32)
-    names = {2: "A n", 3: "A ns", 4: "A wait", 5: "R n", 6: "R ns", 8: "B n", 9: "B loop", 10: "B waitR", 11: "B waitA+tc"}
-    its = iters + 1
-    for k, nm in names.items():
-        print(f"   {nm:12s} {hdr[k]}")
-    print(f"   per item: A {hdr[3]/max(hdr[2],1):.0f} ns (+wait {hdr[4]/max(hdr[2],1):.0f}), R {hdr[6]/max(hdr[5],1):.0f} ns, "
-          f"B loop {hdr[9]/max(hdr[8],1):.0f} ns, waitR {hdr[10]/max(hdr[8],1):.0f}, waitA+tc {hdr[11]/max(hdr[8],1):.0f}")
