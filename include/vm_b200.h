@@ -187,9 +187,10 @@ int vm_tps_composite_bgra(const uint8_t *fg, const uint8_t *bg, int n_bg,
 /* flow warp + consistency mask + TPS + composite (SURVEY 8d "C4 pipeline"):
  * warp_bgr/warp_img (flow.py:9-33), correct_alpha (flow.py:36-65), warp_image(identity affine,
  * thin) (augmentation.py:44-63 -> tps.py:14-123), create_composite_image (reader.py:72-79).
- * 39 algorithmic B/px.  forward may be NULL (no consistency test).  The default variant runs
- * two kernels per chunk of frames - stage A writes the flow-warped pixel {bgr, alpha code}
- * (8 B/px) into `scratch`, stage B resamples it - with the chunk sized to stay in L2.        */
+ * 39 algorithmic B/px.  forward may be NULL (no consistency test).  The default variant (lean split
+ * pipeline) runs four kernels per round of frames - flow stage (packed {bgr, TA} pixels, 8 B/px, into
+ * `scratch`), float64 spline on the coarse grid, tile boxes, resampling + composite; fused_variant 5
+ * runs the whole pipeline in one kernel and does not touch `scratch`.                         */
 int vm_flow_tps_composite_bgra(const uint8_t *fg, const float *backward, const float *forward,
                                const uint8_t *bg, int n_bg,
                                const double *ctrl, const double *coef, int N,
@@ -198,12 +199,14 @@ int vm_flow_tps_composite_bgra(const uint8_t *fg, const float *backward, const f
                                int n, int h, int w, float *out, void *scratch,
                                int32_t *status, void *stream);
 
-/* Tuning / test switches: "fused_variant" 4 = lean split pipeline (default: flow stage, float64
- * spline stage, TMA-tiled resampling stage), 0 = first split pipeline, 1 = per-pixel gather
- * kernel, 2 = single shared-memory tiled kernel, 3 = persistent role-specialised kernel;
- * "tile_h" 32 or 64 (rows per tile of variant 2); "chunk_frames" frames per stage pair of
- * variant 0; "lean_chunk" frames per stage round of variant 4; "lean_timing" 1 = record CUDA
- * events around the stages of variant 4 (read back with vm_lean_stage_ms).                   */
+/* Tuning / test switches (process-wide configuration: set before use, not concurrently with calls; every
+ * setting gives bit-identical output for variants 4 and 5):
+ * "fused_variant" 4 = lean split pipeline (default: flow stage, float64 spline stage, TMA-tiled resampling
+ * stage), 5 = single-pass warp-specialised kernel for the C4 entry point (no intermediate in HBM), 1 =
+ * per-pixel gather kernels (generic fallback); "lean_chunk" frames per stage round, "lean_sub", "lean_rb",
+ * "lean_b1_warps", "lean_b1_dyr", "lean_b1_ctas", "lean_minb", "lean_fine_rows", "lean_box_cap",
+ * "lean_floors", "flow_stage_layout": schedule parameters of variant 4; "fuse_ctas": persistent CTAs of
+ * variant 5; "lean_timing" 1 = record CUDA events around the stages of variant 4 (vm_lean_stage_ms).       */
 int vm_set_option(const char *key, int value);
 
 /* Batched augmentation (reference augmentation.py:102-135, `augment` for a whole clip; BASELINE config 5).

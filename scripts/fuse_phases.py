@@ -13,6 +13,7 @@ import bench
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 vm = ge.load_package()
 P = vm.pipeline
+P.set_fused_variant(5)                # the single-pass kernel (the default is the lean split pipeline)
 lib = vm._native.load()
 for kv in filter(None, os.environ.get("VM_OPTS", "").split(",")):
     k, v = kv.split("=")

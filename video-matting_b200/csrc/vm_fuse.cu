@@ -240,7 +240,13 @@ k_fuse_c4(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd, const 
     vl_mbar_wait_parity(bar, 0);
     const uint32_t tab_adj = vl_smem_u32(S.tab) - (uint32_t)(((1023 + VL_EMIN) << VL_BITS) << 4);
 
-    if (warp < NSW) {
+#ifdef VF_SPLINE_HIGH
+    constexpr int SPL_BASE = NPT, PIX_BASE = 0;     // spline warps = the LAST warps of the CTA (the issue arbiter favours high warp ids)
+#else
+    constexpr int SPL_BASE = 0, PIX_BASE = NST;
+#endif
+    if (tid >= SPL_BASE && tid < SPL_BASE + NST) {
+        const int stid = tid - SPL_BASE, swarp = stid >> 5;
         // =====================================================================================================
         // spline warps: T and the source box of tile it (buffer it & 1), one tile ahead of the pixel warps
         // =====================================================================================================
@@ -263,14 +269,14 @@ k_fuse_c4(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd, const 
                 vf_bar_sync(VF_BAR_SPLINE, NST);                       // nobody still reads the previous frame's controls
                 const double *P = ctrl + (int64_t)frame * NC * 2;
                 const double *C = coef + (int64_t)frame * (NC + 3) * 2;
-                for (int a = tid; a < NC; a += NST) {
+                for (int a = stid; a < NC; a += NST) {
                     S.p[a] = make_double2(P[2 * a], P[2 * a + 1]);
                     S.wv[a] = make_double2(0.5 * C[2 * a], 0.5 * C[2 * a + 1]);
                 }
-                if (tid < 6) S.aff[tid] = C[(NC + tid % 3) * 2 + tid / 3];
+                if (stid < 6) S.aff[stid] = C[(NC + stid % 3) * 2 + stid / 3];
                 cur_frame = frame;
             }
-            if (tid == 0) {
+            if (stid == 0) {
                 VfTileInfo &I = S.info[b];
                 I.frame = frame; I.I0 = I0; I.J0 = J0; I.th = th; I.tw = tw;
                 I.kr0 = kr0; I.nkr = nkr; I.kc0 = kc0; I.nkc = nkc; I.valid = valid ? 1 : 0;
@@ -298,7 +304,7 @@ k_fuse_c4(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd, const 
                 }
                 const bool slow = __any_sync(0xffffffffu, badc) || (N == 0);
                 int rlo = INT_MAX, rhi = INT_MIN, clo = INT_MAX, chi = INT_MIN, bad = 0;
-                for (int kg = kr0 + VF_RG * warp; kg <= kend; kg += VF_RG * NSW) {
+                for (int kg = kr0 + VF_RG * swarp; kg <= kend; kg += VF_RG * NSW) {
                     double v0[VF_RG], v1[VF_RG];
                     if (!slow) {
                         constexpr int NF = N > 0 ? N : 1;
@@ -311,7 +317,7 @@ k_fuse_c4(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd, const 
                                 const double dx = (double)min(kg + r, kend) * step_x - px;
                                 d[r] = dx * dx;
                             }
-                            S.dx2[warp][a] = make_double4(d[0], d[1], d[VF_RG > 2 ? 2 : 0], d[VF_RG > 2 ? 3 : 1]);
+                            S.dx2[swarp][a] = make_double4(d[0], d[1], d[VF_RG > 2 ? 2 : 0], d[VF_RG > 2 ? 3 : 1]);
                         }
                         __syncwarp();
                         double s0[VF_RG], s1[VF_RG];
@@ -320,7 +326,7 @@ k_fuse_c4(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd, const 
 #pragma unroll
                         for (int a = 0; a < NF; ++a) {
                             const double2 wv = S.wv[a];
-                            const double4 dx2 = S.dx2[warp][a];
+                            const double4 dx2 = S.dx2[swarp][a];
                             const double dd[4] = {dx2.x, dx2.y, dx2.z, dx2.w};
                             const double dy = y - S.p[a].y;
                             const double dy2a = dy * dy;
@@ -377,7 +383,7 @@ k_fuse_c4(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd, const 
                 }
             }
             vf_bar_sync(VF_BAR_SPLINE, NST);
-            if (tid == 0) {
+            if (stid == 0) {
                 VfTileInfo &I = S.info[b];
                 I.rmin = 0; I.bh = 0; I.cmin = 0; I.bw = 0;
                 if (valid && !I.bad && I.rlo <= I.rhi) {
@@ -392,14 +398,14 @@ k_fuse_c4(const uint8_t *__restrict__ fg, const float2 *__restrict__ bwd, const 
             __threadfence_block();
             vf_bar_arrive(VF_BAR_FULL0 + b, VF_THREADS);
 #ifdef VF_TIMING
-            if (tid == 0) { VF_T(ts2); VF_ACC(0, ts0, ts1); VF_ACC(1, ts1, ts2); VF_ACC(2, 0, 1); }
+            if (stid == 0) { VF_T(ts2); VF_ACC(0, ts0, ts1); VF_ACC(1, ts1, ts2); VF_ACC(2, 0, 1); }
 #endif
         }
     } else {
         // =====================================================================================================
         // pixel warps
         // =====================================================================================================
-        const int tp = tid - NST;                        // 0 .. NPT-1
+        const int tp = tid - PIX_BASE;                   // 0 .. NPT-1
         const int x = tp & 63, strip = tp >> 6;
         int outside = 0, slow_tiles = 0, flags = 0, near_knife = 0, bad_tiles = 0, it = 0;
         for (int64_t t = blockIdx.x; t < total; t += gridDim.x, ++it) {
