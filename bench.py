@@ -498,14 +498,14 @@ def bench_configs(vm, torch, dev, rank, world, barrier, max_over_ranks, peak, po
         np.random.seed(1 + rank)
         barrier()
         for _ in range(2):
-            vm.augmentation.augment_clip(fg, bgn, stats=stats, pool=pool)
+            vm.augmentation.augment_clip(fg, bgn, stats=stats)
         barrier()
         t = time.perf_counter()
         for _ in range(iters):
-            vm.augmentation.augment_clip(fg, bgn, stats=stats, pool=pool)
+            vm.augmentation.augment_clip(fg, bgn, stats=stats)
         barrier()
         ms5 = 1e3 * max_over_ranks(time.perf_counter() - t) / iters
-        rec("C5 augmentation.augment_clip (RNG plan + host pinv on the solver pool + TPS + 2 affine passes + illumination), 1080p x 64, wall clock",
+        rec("C5 augmentation.augment_clip (RNG plan + host pinv + TPS + 2 affine passes + illumination), 1080p x 64, wall clock",
             "c5", h, w, n, ms5, {"host_bound": True})
         del fg, fb, ff, bg, bgn
         torch.cuda.empty_cache()

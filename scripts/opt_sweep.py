@@ -19,7 +19,7 @@ fg, fb, ff, bg = bench.make_clip(torch, 1234, n, H, W, dev)
 ctrl, coef = P.solve_grids(bench.make_grids(vm, 1, n, H, W), dev)
 out = torch.empty((n, H, W, 4), dtype=torch.float32, device=dev)
 ref = None
-DEFAULTS = {"fused_variant": P.DEFAULT_VARIANT, "lean_chunk": 64, "lean_sub": 0, "lean_b1_warps": 16,
+DEFAULTS = {"fused_variant": P.DEFAULT_VARIANT, "lean_chunk": 0, "lean_sub": 0, "lean_b1_warps": 16,
             "lean_b1_dyr": 1, "lean_b1_ctas": 0, "lean_minb": 4, "lean_fine_rows": 8, "lean_rb": 0, "lean_box_cap": 0}
 for arg in sys.argv[1:] or ["fused_variant=4"]:
     opts = dict(DEFAULTS)

@@ -410,7 +410,7 @@ def test_lean_partition_independent(vm, lean):
     base, st0 = P.flow_tps_composite(*args)
     base3, _ = P.tps_composite(args[0], args[3], ctrl, coef)
     assert int(st0[4]) < 4, "most tiles of a mild grid must take the shared-memory box path"
-    defaults = {"lean_chunk": 64, "lean_rb": 0, "lean_minb": 4, "lean_box_cap": 0, "lean_fine_rows": 8, "lean_sub": 0,
+    defaults = {"lean_chunk": 0, "lean_rb": 0, "lean_minb": 4, "lean_box_cap": 0, "lean_fine_rows": 8, "lean_sub": 0,
                 "lean_b1_warps": 16, "lean_b1_dyr": 1, "flow_stage_layout": 0, "lean_floors": 1,
                 "lean_b1_ctas": 0}
     configs = [{"lean_chunk": 1}, {"lean_chunk": 2}, {"lean_chunk": 3}, {"lean_rb": 4}, {"lean_rb": 16}, {"lean_rb": 32},

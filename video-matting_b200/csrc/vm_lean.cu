@@ -25,7 +25,13 @@
 int vm_launch_flow_stage(const uint8_t *fg, const float *backward, const float *forward, int n, int h, int w,
                          void *packed, int32_t *status, cudaStream_t st, bool raw_ta);     // vm_flow.cu
 
-int g_vl_chunk = 64;         // frames per A/B1/B2 round
+int g_vl_chunk = 0;          // frames per A/B1/B2 round; 0: as many as make ~64 frames of 1080p (long launches: no ramp/tail losses)
+static int vl_chunk_for(int h, int w) {
+    if (g_vl_chunk > 0) return g_vl_chunk;
+    const int64_t px = (int64_t)h * w;
+    int64_t c = (64ll * 1080 * 1920 + px / 2) / (px > 0 ? px : 1);
+    return (int)(c < 8 ? 8 : (c > 1024 ? 1024 : c));
+}
 int g_vl_rb = 0;             // coarse rows per B1 unit (0 = pick on the host)
 int g_vl_fine_rows = 8;      // fine rows per B2 thread
 int g_vl_timing = 0;         // 1: bracket the stages of the first chunk of every call with CUDA events (vm_lean_stage_ms)
@@ -757,12 +763,12 @@ static VlSlot vl_slot_at(unsigned char *base, int m, int h, int w) {
 }
 
 int64_t vm_lean_scratch_bytes(int n, int h, int w) {
-    const int m = n < g_vl_chunk ? n : g_vl_chunk;
+    const int chunk = vl_chunk_for(h, w), m = n < chunk ? n : chunk;
     return 512 + vl_slot_bytes(m, h, w);
 }
 
 int vm_lean_set_option(const char *key, int value) {
-    if (!strcmp(key, "lean_chunk") && value >= 1 && value <= 4096) { g_vl_chunk = value; return VM_OK; }
+    if (!strcmp(key, "lean_chunk") && value >= 0 && value <= 4096) { g_vl_chunk = value; return VM_OK; }
     if (!strcmp(key, "lean_rb") && value >= 0 && value <= 64) { g_vl_rb = value; return VM_OK; }
     if (!strcmp(key, "lean_b1_warps") && value >= 1 && value <= VL_B1_WARPS_HI) { g_vl_b1_warps = value; return VM_OK; }
     if (!strcmp(key, "lean_b1_dyr") && value >= 0 && value <= 1) { g_vl_b1_dyr = value; return VM_OK; }
@@ -878,7 +884,7 @@ int vm_lean_launch(int mode, const uint8_t *fg, const float *backward, const flo
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
     // ---- one round per chunk of `lean_chunk` frames on the caller's stream: spline, tile boxes, flow stage, resampling
-    const int chunk = g_vl_chunk;
+    const int chunk = vl_chunk_for(h, w);
     const int mc = n < chunk ? n : chunk;
     const VlSlot sl = vl_slot_at(base, mc, h, w);
     const bool timing = g_vl_timing && cap == cudaStreamCaptureStatusNone;
