@@ -270,7 +270,7 @@ def solve_grids(grids, device=None, pool=None):
     augmentation.warp_image(..., thin=grids): the system is built from the DEFORMED grid and maps
     back onto the regular one (reference tps.py:51).  ``pool``: a SolverPool to spread the solves over
     host cores.  Returns CUDA (ctrl, coef)."""
-    ctrl, coef = pool.solve(grids) if pool is not None else _host.solve_many(grids)
+    ctrl, coef = pool.solve(grids, per_task=8) if pool is not None else _host.solve_many(grids)
     dev = torch.device(device if device is not None else "cuda")
     return torch.from_numpy(ctrl).to(dev), torch.from_numpy(coef).to(dev)
 
