@@ -240,6 +240,27 @@ __device__ __forceinline__ float vm_byte2f(uint32_t word, int byte) {
 
 struct VmFlowPx { uint32_t bgr; uint32_t ta; int masked; };
 
+// The four channel blends of vm_blend_bgra as two 64-bit multiply-add chains: the tap words are split
+// into {B, R} and {G, A} with one channel in byte 0 and the other in byte 3, the weights are scaled by 64
+// (sum 2^16), so a channel's sum (+ 2^15 for the rounding) stays below 2^24 and never reaches its
+// neighbour: lane 0 = (sum S w + 512) << 6, i.e. the blended byte sits in bits 16..23; the alpha lane
+// (no rounding term) holds TA << 6 from bit 24 on.  Same integers as vm_blend_bgra, 19 instead of 40
+// instructions.
+__device__ __forceinline__ void vm_blend_lanes(uint32_t s00, uint32_t s01, uint32_t s10, uint32_t s11, uint32_t fx,
+                                               uint32_t fy, uint32_t &bgr, uint32_t &ta) {
+    const uint32_t gx = 32u - fx, fy6 = fy << 6, gy6 = 2048u - fy6;
+    const uint32_t w00 = gx * gy6, w01 = fx * gy6, w10 = gx * fy6, w11 = fx * fy6;
+    unsigned long long br = 0x0000008000008000ull, ga = 0x0000000000008000ull;
+    br += (unsigned long long)__byte_perm(s00, 0, 0x2440) * w00; ga += (unsigned long long)__byte_perm(s00, 0, 0x3441) * w00;
+    br += (unsigned long long)__byte_perm(s01, 0, 0x2440) * w01; ga += (unsigned long long)__byte_perm(s01, 0, 0x3441) * w01;
+    br += (unsigned long long)__byte_perm(s10, 0, 0x2440) * w10; ga += (unsigned long long)__byte_perm(s10, 0, 0x3441) * w10;
+    br += (unsigned long long)__byte_perm(s11, 0, 0x2440) * w11; ga += (unsigned long long)__byte_perm(s11, 0, 0x3441) * w11;
+    const uint32_t brl = (uint32_t)br, brh = (uint32_t)(br >> 32), gal = (uint32_t)ga, gah = (uint32_t)(ga >> 32);
+    // B = bits 16..23 of br, R = bits 40..47 (byte 1 of the high word, whose byte 3 is zero), G = bits 16..23 of ga
+    bgr = __byte_perm(__byte_perm(brl, brh, 0x7572), gal, 0x3260);
+    ta = __funnelshift_r(gal, gah, 30);
+}
+
 // warp_bgr / warp_img / correct_alpha for the pixel (i, j) of a BGRA frame: fast path for
 // in-range coordinates, otherwise the generic routines.  fi/fj = (float)i / (float)j.
 template <bool MASK>
@@ -255,8 +276,8 @@ __device__ __forceinline__ VmFlowPx vm_flow_px(const uint32_t *__restrict__ fg32
         uint32_t s00, s01, s10, s11;
         const int base = (int)((unsigned)iy * (unsigned)W + (unsigned)ix);
         if ((unsigned)ix < (unsigned)(W - 1) && (unsigned)iy < (unsigned)(H - 1)) {
-            const uint32_t *p = fg32 + base;
-            s00 = __ldg(p); s01 = __ldg(p + 1); s10 = __ldg(p + W); s11 = __ldg(p + W + 1);
+            const uint32_t *p = fg32 + (unsigned)base, *q = p + (unsigned)W;
+            s00 = __ldg(p); s01 = __ldg(p + 1); s10 = __ldg(q); s11 = __ldg(q + 1);
         } else {
             const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
             const bool y0 = (unsigned)iy < (unsigned)H, y1 = (unsigned)(iy + 1) < (unsigned)H;
@@ -265,22 +286,14 @@ __device__ __forceinline__ VmFlowPx vm_flow_px(const uint32_t *__restrict__ fg32
             s10 = (y1 && x0) ? __ldg(fg32 + base + W) : 0u;
             s11 = (y1 && x1) ? __ldg(fg32 + base + W + 1) : 0u;
         }
-        const uint32_t gx = 32 - fx, gy = 32 - fy;
-        const uint32_t w00 = gx * gy, w01 = fx * gy, w10 = gx * fy, w11 = fx * fy;
-        const uint32_t b = ((s00 & 255u) * w00 + (s01 & 255u) * w01 + (s10 & 255u) * w10 + (s11 & 255u) * w11 + 512u) >> 10;
-        const uint32_t g = (__byte_perm(s00, 0, 0x4441) * w00 + __byte_perm(s01, 0, 0x4441) * w01 +
-                            __byte_perm(s10, 0, 0x4441) * w10 + __byte_perm(s11, 0, 0x4441) * w11 + 512u) >> 10;
-        const uint32_t r = (__byte_perm(s00, 0, 0x4442) * w00 + __byte_perm(s01, 0, 0x4442) * w01 +
-                            __byte_perm(s10, 0, 0x4442) * w10 + __byte_perm(s11, 0, 0x4442) * w11 + 512u) >> 10;
-        o.ta = (s00 >> 24) * w00 + (s01 >> 24) * w01 + (s10 >> 24) * w10 + (s11 >> 24) * w11;
-        o.bgr = b | (g << 8) | (r << 16);
+        vm_blend_lanes(s00, s01, s10, s11, (uint32_t)fx, (uint32_t)fy, o.bgr, o.ta);
         o.masked = 0;
         if (MASK) {
             // flow.py:44: a = bx + j (same float as mx), trunc toward zero; fast when it lands
             // inside the frame (no clamp, no wrap)
             const int j0 = __float2int_rz(mx), i0 = __float2int_rz(my);
             if ((unsigned)j0 < (unsigned)W && (unsigned)i0 < (unsigned)H) {
-                const float2 ff = __ldg(fwd + (i0 * W + j0));
+                const float2 ff = __ldg(fwd + (unsigned)(i0 * W + j0));
                 const float c = __fadd_rn(ff.x, (float)j0), d = __fadd_rn(ff.y, (float)i0);
                 if ((fabsf(c) < 3.0e38f) & (fabsf(d) < 3.0e38f)) {              // finite, and false for NaN
                     // min(trunc(c), W-1) - j, in float: exact for |.| < 2^24, monotone beyond
@@ -307,6 +320,72 @@ __device__ __forceinline__ VmFlowPx vm_flow_px(const uint32_t *__restrict__ fg32
 // 20 gathers of a thread are in flight together instead of as eight dependent round trips.  Pixels that
 // leave the fast path (frame border, out-of-range or NaN coordinates) are redone by the same code as
 // vm_flow_px afterwards; results are identical to four vm_flow_px calls.
+// gather addresses of one pixel (always valid): the four taps p, p + dx, q, q + dx and the forward-flow vector pf.
+// Pixels off the fast path (frame border, out-of-range or NaN coordinates) get pixel 0; vm_flow_px_finish redoes them.
+// (dx as an immediate 1 saves four instructions and costs a spill at the 48-register cap: 0.877 ms against 0.813 ms.)
+template <bool MASK>
+__device__ __forceinline__ void vm_flow_px_addr(const uint32_t *__restrict__ fg32, const float2 *__restrict__ fwd, int H, int W,
+                                                float fi, float fj, float2 fb, const uint32_t *&p, const uint32_t *&q,
+                                                int &dx, const float2 *&pf) {
+    const float mx = __fadd_rn(fj, fb.x), my = __fadd_rn(fi, fb.y);
+    const bool inr = (fabsf(mx) < 60000.f) & (fabsf(my) < 60000.f);
+    const int ix = vm_fix5_fast(mx) >> 5, iy = vm_fix5_fast(my) >> 5;
+    const bool inner = inr && (unsigned)ix < (unsigned)(W - 1) && (unsigned)iy < (unsigned)(H - 1);
+    p = fg32 + (inner ? (unsigned)iy * (unsigned)W + (unsigned)ix : 0u);
+    q = p + (inner ? (unsigned)W : 0u);
+    dx = inner ? 1 : 0;
+    if (MASK) {
+        const int j0 = __float2int_rz(mx), i0 = __float2int_rz(my);
+        const bool fwd_ok = inr && (unsigned)j0 < (unsigned)W && (unsigned)i0 < (unsigned)H;
+        pf = fwd + (fwd_ok ? (unsigned)(i0 * W + j0) : 0u);
+    }
+}
+
+// the arithmetic of vm_flow_px on values gathered from the addresses of vm_flow_px_addr
+template <bool MASK>
+__device__ __forceinline__ VmFlowPx vm_flow_px_finish(const uint32_t *__restrict__ fg32, const float2 *__restrict__ fwd,
+                                                      int H, int W, int i, int j, float fi, float fj, float2 fb,
+                                                      uint32_t s00, uint32_t s01, uint32_t s10, uint32_t s11, float2 fv,
+                                                      int &flags) {
+    VmFlowPx o;
+    const float mx = __fadd_rn(fj, fb.x), my = __fadd_rn(fi, fb.y);
+    if ((fabsf(mx) < 60000.f) & (fabsf(my) < 60000.f)) {
+        const int SX = vm_fix5_fast(mx), SY = vm_fix5_fast(my);
+        const int ix = SX >> 5, iy = SY >> 5, fx = SX & 31, fy = SY & 31;
+        if (!((unsigned)ix < (unsigned)(W - 1) && (unsigned)iy < (unsigned)(H - 1))) {     // frame border: taps outside read 0
+            const int base = (int)((unsigned)iy * (unsigned)W + (unsigned)ix);
+            const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
+            const bool y0 = (unsigned)iy < (unsigned)H, y1 = (unsigned)(iy + 1) < (unsigned)H;
+            s00 = (y0 && x0) ? __ldg(fg32 + base) : 0u;
+            s01 = (y0 && x1) ? __ldg(fg32 + base + 1) : 0u;
+            s10 = (y1 && x0) ? __ldg(fg32 + base + W) : 0u;
+            s11 = (y1 && x1) ? __ldg(fg32 + base + W + 1) : 0u;
+        }
+        vm_blend_lanes(s00, s01, s10, s11, (uint32_t)fx, (uint32_t)fy, o.bgr, o.ta);
+        o.masked = 0;
+        if (MASK) {
+            const int j0 = __float2int_rz(mx), i0 = __float2int_rz(my);
+            if ((unsigned)j0 < (unsigned)W && (unsigned)i0 < (unsigned)H) {
+                const float c = __fadd_rn(fv.x, (float)j0), d = __fadd_rn(fv.y, (float)i0);
+                if ((fabsf(c) < 3.0e38f) & (fabsf(d) < 3.0e38f)) {
+                    const float dj = __fadd_rn(fminf(truncf(c), (float)(W - 1)), -fj);
+                    const float di = __fadd_rn(fminf(truncf(d), (float)(H - 1)), -fi);
+                    o.masked = __fmaf_rn(dj, dj, __fmul_rn(di, di)) > 225.f;
+                } else {
+                    flags |= 2; o.masked = 1;
+                }
+            } else {
+                o.masked = vm_consistency(fwd, H, W, i, j, fb, flags);
+            }
+        }
+    } else {
+        const VmWarped wv = vm_flow_warp_bgra(reinterpret_cast<const uint8_t *>(fg32), H, W, i, j, fb);
+        o.bgr = wv.bgr; o.ta = wv.ta;
+        o.masked = MASK ? vm_consistency(fwd, H, W, i, j, fb, flags) : 0;
+    }
+    return o;
+}
+
 template <bool MASK, int G>
 __device__ __forceinline__ void vm_flow_pxn(const uint32_t *__restrict__ fg32, const float2 *__restrict__ fwd,
                                             int H, int W, int i, int j, float fi, float fj, const float2 *__restrict__ fb,
@@ -314,71 +393,20 @@ __device__ __forceinline__ void vm_flow_pxn(const uint32_t *__restrict__ fg32, c
     uint32_t s[G][4];
     float2 fv[G];
     // phase 1: addresses and loads only (the geometry is recomputed in phase 2: a few ALU instructions
-    // are cheaper than carrying it in registers across twenty outstanding loads)
+    // are cheaper than carrying it in registers across the outstanding loads)
 #pragma unroll
     for (int k = 0; k < G; ++k) {
-        const float mx = __fadd_rn(fj + (float)k, fb[k].x), my = __fadd_rn(fi, fb[k].y);
-        const bool inr = (fabsf(mx) < 60000.f) & (fabsf(my) < 60000.f);
-        const int ix = vm_fix5_fast(mx) >> 5, iy = vm_fix5_fast(my) >> 5;
-        const bool inner = inr && (unsigned)ix < (unsigned)(W - 1) && (unsigned)iy < (unsigned)(H - 1);
-        const uint32_t *p = fg32 + (inner ? (int)((unsigned)iy * (unsigned)W + (unsigned)ix) : 0);
-        const int dx = inner ? 1 : 0, dy = inner ? W : 0;
-        s[k][0] = __ldg(p); s[k][1] = __ldg(p + dx); s[k][2] = __ldg(p + dy); s[k][3] = __ldg(p + dy + dx);
-        if (MASK) {
-            const int j0 = __float2int_rz(mx), i0 = __float2int_rz(my);
-            const bool fwd_ok = inr && (unsigned)j0 < (unsigned)W && (unsigned)i0 < (unsigned)H;
-            fv[k] = __ldg(fwd + (fwd_ok ? i0 * W + j0 : 0));
-        }
+        const uint32_t *p, *q;
+        const float2 *pf = nullptr;
+        int dx;
+        vm_flow_px_addr<MASK>(fg32, fwd, H, W, fi, fj + (float)k, fb[k], p, q, dx, pf);
+        s[k][0] = __ldg(p); s[k][1] = __ldg(p + dx); s[k][2] = __ldg(q); s[k][3] = __ldg(q + dx);
+        fv[k] = MASK ? __ldg(pf) : make_float2(0.f, 0.f);
     }
     // phase 2: the arithmetic of vm_flow_px on the loaded values
 #pragma unroll
-    for (int k = 0; k < G; ++k) {
-        const float fjk = fj + (float)k;
-        const float mx = __fadd_rn(fjk, fb[k].x), my = __fadd_rn(fi, fb[k].y);
-        if ((fabsf(mx) < 60000.f) & (fabsf(my) < 60000.f)) {
-            const int SX = vm_fix5_fast(mx), SY = vm_fix5_fast(my);
-            const int ix = SX >> 5, iy = SY >> 5, fx = SX & 31, fy = SY & 31;
-            uint32_t s00 = s[k][0], s01 = s[k][1], s10 = s[k][2], s11 = s[k][3];
-            if (!((unsigned)ix < (unsigned)(W - 1) && (unsigned)iy < (unsigned)(H - 1))) {     // frame border: taps outside read 0
-                const int base = (int)((unsigned)iy * (unsigned)W + (unsigned)ix);
-                const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
-                const bool y0 = (unsigned)iy < (unsigned)H, y1 = (unsigned)(iy + 1) < (unsigned)H;
-                s00 = (y0 && x0) ? __ldg(fg32 + base) : 0u;
-                s01 = (y0 && x1) ? __ldg(fg32 + base + 1) : 0u;
-                s10 = (y1 && x0) ? __ldg(fg32 + base + W) : 0u;
-                s11 = (y1 && x1) ? __ldg(fg32 + base + W + 1) : 0u;
-            }
-            const uint32_t gx = 32 - fx, gy = 32 - fy;
-            const uint32_t w00 = gx * gy, w01 = fx * gy, w10 = gx * fy, w11 = fx * fy;
-            const uint32_t b = ((s00 & 255u) * w00 + (s01 & 255u) * w01 + (s10 & 255u) * w10 + (s11 & 255u) * w11 + 512u) >> 10;
-            const uint32_t g = (__byte_perm(s00, 0, 0x4441) * w00 + __byte_perm(s01, 0, 0x4441) * w01 +
-                                __byte_perm(s10, 0, 0x4441) * w10 + __byte_perm(s11, 0, 0x4441) * w11 + 512u) >> 10;
-            const uint32_t r = (__byte_perm(s00, 0, 0x4442) * w00 + __byte_perm(s01, 0, 0x4442) * w01 +
-                                __byte_perm(s10, 0, 0x4442) * w10 + __byte_perm(s11, 0, 0x4442) * w11 + 512u) >> 10;
-            o[k].ta = (s00 >> 24) * w00 + (s01 >> 24) * w01 + (s10 >> 24) * w10 + (s11 >> 24) * w11;
-            o[k].bgr = b | (g << 8) | (r << 16);
-            o[k].masked = 0;
-            if (MASK) {
-                const int j0 = __float2int_rz(mx), i0 = __float2int_rz(my);
-                if ((unsigned)j0 < (unsigned)W && (unsigned)i0 < (unsigned)H) {
-                    const float c = __fadd_rn(fv[k].x, (float)j0), d = __fadd_rn(fv[k].y, (float)i0);
-                    if ((fabsf(c) < 3.0e38f) & (fabsf(d) < 3.0e38f)) {
-                        const float dj = __fadd_rn(fminf(truncf(c), (float)(W - 1)), -fjk);
-                        const float di = __fadd_rn(fminf(truncf(d), (float)(H - 1)), -fi);
-                        o[k].masked = __fmaf_rn(dj, dj, __fmul_rn(di, di)) > 225.f;
-                    } else {
-                        flags |= 2; o[k].masked = 1;
-                    }
-                } else {
-                    o[k].masked = vm_consistency(fwd, H, W, i, j + k, fb[k], flags);
-                }
-            }
-        } else {
-            const VmWarped wv = vm_flow_warp_bgra(reinterpret_cast<const uint8_t *>(fg32), H, W, i, j + k, fb[k]);
-            o[k].bgr = wv.bgr; o[k].ta = wv.ta;
-            o[k].masked = MASK ? vm_consistency(fwd, H, W, i, j + k, fb[k], flags) : 0;
-        }
-    }
+    for (int k = 0; k < G; ++k)
+        o[k] = vm_flow_px_finish<MASK>(fg32, fwd, H, W, i, j + k, fi, fj + (float)k, fb[k], s[k][0], s[k][1], s[k][2], s[k][3], fv[k], flags);
 }
 
 // alpha numerator ta (0..261120) -> signed-complement float: +alpha when alpha <= 1/2,
@@ -432,12 +460,11 @@ __device__ __forceinline__ vm_axis_entry vm_ld_axis(const vm_axis_entry *p) {
 // ---------------------------------------------------------------------------------------
 // fused flow stage (C2 / stage A of C4) - shared by vm_flow.cu and the dependency-driven kernel of vm_lean.cu
 // ---------------------------------------------------------------------------------------
-#ifndef C2_GROUP
-#define C2_GROUP 1                 /* pixels whose gathers are issued together (vm_flow_pxn): 1 (pixel by pixel, default), 2 or 4.
-                                      Measured (1080p x 64, C2): 1 @ 5 CTAs/SM 13.8 us per frame, 2 @ 4 CTAs/SM 14.0 us, 4 @ 3 CTAs/SM
-                                      16.9 us, 4 @ 4 CTAs/SM (spills) 19.9 us - the registers that keep more gathers in flight per
-                                      thread cost more occupancy than they buy */
-#endif
+// Gathers of a pixel: vm_flow_pxn<., 1> issues the four taps AND the forward-flow vector (whose address depends on the
+// coordinate only) before the first use, so a pixel costs one memory round trip instead of two.  Measured on the
+// stage-A launch (1080p x 64, round 2): 0.813 ms against 0.878 ms pixel by pixel (vm_flow_px), 0.87 ms with the gathers
+// of two pixels grouped (spills at 48 registers), 0.90-1.06 ms at 4 CTAs per SM; the lane-packed blend and the opaque frame
+// pointers are worth 1 % each on their own, 4 % together with the hoisted forward-flow load.
 #define C2_TW 128
 #define C2_TH 8                    /* rows in flight per CTA (one per warp) */
 #define C2_ROWS 40                 /* rows per CTA: each warp walks C2_ROWS / C2_TH of them */
@@ -473,6 +500,10 @@ __device__ __forceinline__ void vm_flow_unit_t(const uint8_t *__restrict__ fg, c
     const uint32_t *fg32 = reinterpret_cast<const uint32_t *>(fg) + fbase;
     const float2 *bf = bwd + fbase;
     const float2 *ff = HAS_FWD ? fwd + fbase : nullptr;
+    // the frame pointers as opaque per-thread values: a gather address is then one 32 x 32 + 64 multiply-add
+    // instead of (index + frame offset) -> 64-bit scale -> add, five instructions per address
+    asm volatile("" : "+l"(fg32));
+    if (HAS_FWD) asm volatile("" : "+l"(ff));
     const float fj = (float)j;
     int flags = 0;
     if (j + 3 < w && (w & 3) == 0) {
@@ -488,15 +519,9 @@ __device__ __forceinline__ void vm_flow_unit_t(const uint8_t *__restrict__ fg, c
             const float fi = (float)i;
             const float2 fl[4] = {{f01.x, f01.y}, {f01.z, f01.w}, {f23.x, f23.y}, {f23.z, f23.w}};
             VmFlowPx px[4];
-#if C2_GROUP == 1
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                px[k] = vm_flow_px<HAS_FWD>(fg32, ff, h, w, i, j + k, fi, fj + (float)k, fl[k], flags);
-#else
-#pragma unroll
-            for (int g = 0; g < 4; g += C2_GROUP)
-                vm_flow_pxn<HAS_FWD, C2_GROUP>(fg32, ff, h, w, i, j + g, fi, fj + (float)g, fl + g, px + g, flags);
-#endif
+                vm_flow_pxn<HAS_FWD, 1>(fg32, ff, h, w, i, j + k, fi, fj + (float)k, fl + k, px + k, flags);
             if (PACKED) {
                 uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<uint2 *>(out_bgr) + fbase + p);
                 op[0] = make_uint4(px[0].bgr, vm_pack_alpha<PACKED>(px[0]), px[1].bgr, vm_pack_alpha<PACKED>(px[1]));

@@ -150,7 +150,7 @@ extern "C" int vm_composite(const void *fg, int fg_dtype, const void *bg, int bg
 // (C2_* tile constants, vm_alpha_f32, vm_pack_alpha and the unit body vm_flow_unit live in vm_common.cuh)
 
 #ifndef C2_MINB
-#define C2_MINB 5                  /* CTAs of 256 threads per SM (48 registers); see C2_GROUP in vm_common.cuh */
+#define C2_MINB 5                  /* CTAs of 256 threads per SM (48 registers) */
 #endif
 template <bool HAS_FWD, int PACKED>
 __global__ void __launch_bounds__(256, C2_MINB)
@@ -176,31 +176,33 @@ k_flow_stage_packed(const uint8_t *__restrict__ fg, const float2 *__restrict__ b
     if (j >= w || rbeg >= rend) return;
     const int64_t fbase = (int64_t)frame * h * w;
     const uint32_t *fg32 = reinterpret_cast<const uint32_t *>(fg) + fbase;
-    const float2 *bf = bwd + fbase;
+    const float2 *bf = bwd + fbase + j;
     const float2 *ff = HAS_FWD ? fwd + fbase : nullptr;
-    uint2 *op = out + fbase;
+    uint2 *op = out + fbase + j;
+    asm volatile("" : "+l"(fg32));
+    if (HAS_FWD) asm volatile("" : "+l"(ff));
     const float fj = (float)j;
     int flags = 0;
     float2 nx[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) nx[k] = __ldcs(bf + min(rbeg + k, h - 1) * w + j);          // streamed once: evict first
+    for (int k = 0; k < 4; ++k) nx[k] = __ldcs(bf + (unsigned)(min(rbeg + k, h - 1) * w));      // streamed once: evict first
     for (int i = rbeg; i < rend; i += 32) {
         float2 fl[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) fl[k] = nx[k];
         if (i + 32 < rend) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) nx[k] = __ldcs(bf + min(i + 32 + k, h - 1) * w + j);
+            for (int k = 0; k < 4; ++k) nx[k] = __ldcs(bf + (unsigned)(min(i + 32 + k, h - 1) * w));
         }
         VmFlowPx px[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int ii = min(i + k, h - 1);
-            px[k] = vm_flow_px<HAS_FWD>(fg32, ff, h, w, ii, j, (float)ii, fj, fl[k], flags);
+            vm_flow_pxn<HAS_FWD, 1>(fg32, ff, h, w, ii, j, (float)ii, fj, &fl[k], &px[k], flags);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (i + k < rend) op[(i + k) * w + j] = make_uint2(px[k].bgr, vm_pack_alpha<PACKED>(px[k]));
+            if (i + k < rend) op[(unsigned)((i + k) * w)] = make_uint2(px[k].bgr, vm_pack_alpha<PACKED>(px[k]));
     }
     if (HAS_FWD && flags && status) {
         if (flags & 1) atomicAdd(status + VM_STATUS_INDEX_ERR, 1);
