@@ -142,6 +142,16 @@ def to_device(x, dtype=None):
     return t.contiguous(), kind
 
 
+def upload(arr, device):
+    """Small host array -> CUDA tensor without blocking the host: a copy from PAGEABLE memory first waits for
+    everything already queued on the stream (CUDA's rule for pageable transfers), which serialises the host
+    work of a call with the kernels of the previous one.  Staged through torch's caching pinned allocator the
+    copy is only enqueued (the allocator keeps the block until the copy has run)."""
+    require_cuda()
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    return t.pin_memory().to(device, non_blocking=True)
+
+
 def from_device(t, kind):
     if kind == "cuda":
         return t

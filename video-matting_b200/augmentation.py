@@ -246,7 +246,7 @@ def _augment_run(fg_d, bg_d, plan, alpha_dtype=torch.float32, status=None, pool=
     a64 = torch.empty((n, h + 1, w + 1), dtype=torch.float64, device=dev) if wide else None
     tplan = P.get_plan((0, 0, h, w), 2, dev)
     ctrl, coef = P.solve_grids(grids, dev, pool=pool)
-    up = lambda arr: torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).to(dev)
+    up = lambda arr: N.upload(np.ascontiguousarray(arr).view(np.uint8).reshape(-1), dev)
     par_bg_d, par_fg_d, luts_d = up(par_bg), up(par_fg), up(luts)
     T = torch.empty((n, tplan.nx, tplan.ny, 2), dtype=torch.float64, device=dev)
     counter = torch.zeros(64, dtype=torch.int32, device=dev)

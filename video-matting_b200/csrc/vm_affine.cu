@@ -2,6 +2,7 @@
 // Reference behaviour: augmentation.py:10-21, 44-63, 88-99 (see include/vm_b200.h).
 #include "vm_common.cuh"
 #include <math.h>
+#include <mutex>
 
 struct VmAffineInv { double i00, i01, b0, i10, i11, b1; };
 
@@ -89,13 +90,14 @@ __device__ __forceinline__ uint32_t vm_illum_px(int b, int g, int r, const int *
         int sec = (int)fl;
         hf = __fsub_rn(hf, fl);
         if ((unsigned)sec >= 6u) { sec = 0; hf = 0.f; }
-        float tab[4];
-        tab[0] = fv;
-        tab[1] = __fmul_rn(fv, __fsub_rn(1.f, fs));
-        tab[2] = __fmul_rn(fv, __fmaf_rn(-fs, hf, 1.f));
-        tab[3] = __fmul_rn(fv, __fmaf_rn(-fs, __fsub_rn(1.f, hf), 1.f));
-        const int ib[6] = {1, 1, 3, 0, 0, 2}, ig[6] = {3, 0, 0, 2, 1, 1}, ir[6] = {0, 2, 1, 1, 3, 0};
-        ob = tab[ib[sec]]; og = tab[ig[sec]]; orr = tab[ir[sec]];
+        const float p_ = __fmul_rn(fv, __fsub_rn(1.f, fs));
+        const float q_ = __fmul_rn(fv, __fmaf_rn(-fs, hf, 1.f));
+        const float t_ = __fmul_rn(fv, __fmaf_rn(-fs, __fsub_rn(1.f, hf), 1.f));
+        // OpenCV's sector table {v, p, q, t}[{1,1,3,0,0,2} / {3,0,0,2,1,1} / {0,2,1,1,3,0}][sec] as selects (an indexed
+        // local array would live in local memory)
+        ob = sec < 2 ? p_ : (sec == 2 ? t_ : (sec == 5 ? q_ : fv));
+        og = sec == 0 ? t_ : (sec < 3 ? fv : (sec == 3 ? q_ : p_));
+        orr = (sec == 0 || sec == 5) ? fv : (sec == 1 ? q_ : (sec == 4 ? t_ : p_));
     }
     const float xb = __fmul_rn(ob, 255.f), xg = __fmul_rn(og, 255.f), xr = __fmul_rn(orr, 255.f);
     const uint32_t B = (uint32_t)max(0, min(255, trunc ? __float2int_rz(xb) : __float2int_rn(xb)));
@@ -304,24 +306,46 @@ extern "C" int vm_alpha_stats_bgra(const uint8_t *bgra, int n, int h, int w, uns
     return vm_check_launch("vm_alpha_stats_bgra");
 }
 
+// BGR2HSV division tables of OpenCV (hsv_shift = 12): the same for every launch, computed once per device
+__device__ int g_va_sdiv[256], g_va_hdiv[256];
+__global__ void k_va_tables() {
+    const int k = threadIdx.x;
+    g_va_sdiv[k] = k ? __double2int_rn(1044480.0 / (double)k) : 0;            // 255 << 12
+    g_va_hdiv[k] = k ? __double2int_rn(737280.0 / (6.0 * (double)k)) : 0;     // 180 << 12
+}
+
+// three bytes at byte offset `o` of a uint8 buffer through aligned 32-bit loads (two words and a funnel shift instead
+// of three byte loads); `last` = index of the last whole word of the buffer, so nothing is read behind it
+__device__ __forceinline__ uint32_t vm_ld3(const uint32_t *__restrict__ words, int64_t o, int64_t last) {
+    const int64_t wi = o >> 2;
+    const uint32_t lo = __ldg(words + wi), hi = __ldg(words + min(wi + 1, last));
+    return __funnelshift_r(lo, hi, ((unsigned)o & 3u) * 8u) & 0x00FFFFFFu;
+}
+
 // FG: source = packed (sh, sw) = (h+1, w+1) intermediate {bgr, alpha float bits} of vm_aug_tps -> new_fg uint8 x3
 // (after the illumination change) + new_alpha float32.  !FG: source = (h, w, 3) uint8 background -> new_bg.
-template <bool FG>
+// CTA = 256 columns x VA_AFF_ROWS rows, one column per thread.  Per-row terms of the coordinate transform come from
+// shared memory (they are the same for the whole row), the division tables from global memory; W4 (w % 4 == 0 and
+// 4-byte aligned planes): the background is read with aligned 32-bit loads and the three colour bytes of four
+// neighbouring lanes leave as three 32-bit stores (one shuffle per lane) instead of twelve byte stores.
+template <bool FG, bool W4>
 __global__ void __launch_bounds__(256)
 k_aug_affine(const void *__restrict__ src_all, const double *__restrict__ alpha64, const VmAugParams *__restrict__ params,
              const uint8_t *__restrict__ luts, int h, int w, uint8_t *__restrict__ out_bgr, float *__restrict__ out_alpha,
-             double *__restrict__ out_alpha64, int vec) {
+             double *__restrict__ out_alpha64, int vec, int64_t src_last_word) {
     __shared__ int sdiv[256], hdiv[256];
     __shared__ uint8_t slut[256];
     __shared__ VmAffineInv Ash;
     __shared__ int tsh[2];
+    __shared__ int rowX0[VA_AFF_ROWS], rowY0[VA_AFF_ROWS];
     const int frame = blockIdx.z;
+    const int y0 = blockIdx.y * VA_AFF_ROWS;
     {
         const int k = threadIdx.x;
-        sdiv[k] = k ? __double2int_rn(1044480.0 / (double)k) : 0;            // 255 << 12
-        hdiv[k] = k ? __double2int_rn(737280.0 / (6.0 * (double)k)) : 0;     // 180 << 12
+        sdiv[k] = g_va_sdiv[k];
+        hdiv[k] = g_va_hdiv[k];
         slut[k] = luts[frame * 256 + k];
-        if (k == 0) {
+        if (k < 32) {
             const VmAugParams P = params[frame];
             double D = P.M[0] * P.M[4] - P.M[1] * P.M[3];                      // OpenCV's closed-form inverse
             D = D != 0 ? 1. / D : 0;
@@ -330,19 +354,28 @@ k_aug_affine(const void *__restrict__ src_all, const double *__restrict__ alpha6
             r.i10 = P.M[3] * (-D); r.i11 = P.M[0] * D;
             r.b0 = -r.i00 * P.M[2] - r.i01 * P.M[5];
             r.b1 = -r.i10 * P.M[2] - r.i11 * P.M[5];
-            Ash = r; tsh[0] = P.tu; tsh[1] = P.tv;
+            if (k == 0) { Ash = r; tsh[0] = P.tu; tsh[1] = P.tv; }
+            if (k < VA_AFF_ROWS) {                                             // the row terms of vm_affine_coords
+                const double y = (double)(y0 + k);
+                rowX0[k] = (int)((unsigned)vm_cvround_f64(__dmul_rn(__dadd_rn(__dmul_rn(r.i01, y), r.b0), 1024.0)) + 16u);
+                rowY0[k] = (int)((unsigned)vm_cvround_f64(__dmul_rn(__dadd_rn(__dmul_rn(r.i11, y), r.b1), 1024.0)) + 16u);
+            }
         }
     }
     __syncthreads();
     const int sh = FG ? h + 1 : h, sw = FG ? w + 1 : w;
     const int tu = tsh[0], tv = tsh[1];
-    const VmAffineInv A = Ash;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= w) return;
-    const int yend = min((int)(blockIdx.y + 1) * VA_AFF_ROWS, h);
-    for (int y = blockIdx.y * VA_AFF_ROWS; y < yend; ++y) {
-        int SX, SY;
-        vm_affine_coords(A, x, y, SX, SY);
+    const bool live = x < w;
+    if (!W4 && !live) return;                                              // W4: whole groups of four lanes stay for the shuffle
+    const int adelta = vm_cvround_f64(__dmul_rn(__dmul_rn(Ash.i00, (double)x), 1024.0));
+    const int bdelta = vm_cvround_f64(__dmul_rn(__dmul_rn(Ash.i10, (double)x), 1024.0));
+    const bool body = vm_hsv_body(x, w, vec);
+    const int yend = min(y0 + VA_AFF_ROWS, h);
+    const int64_t fsrc = (int64_t)frame * sh * sw;
+    for (int y = y0; y < yend; ++y) {
+        const int SX = (int)((unsigned)rowX0[y - y0] + (unsigned)adelta) >> 5;
+        const int SY = (int)((unsigned)rowY0[y - y0] + (unsigned)bdelta) >> 5;
         const int ix = vm_sat_s16(SX >> 5), iy = vm_sat_s16(SY >> 5), fx = SX & 31, fy = SY & 31;
         uint32_t c[4];
         double al[4];
@@ -350,15 +383,17 @@ k_aug_affine(const void *__restrict__ src_all, const double *__restrict__ alpha6
         for (int t = 0; t < 4; ++t) {
             const int Y = iy + (t >> 1), X = ix + (t & 1);
             const int sy = Y - tv, sx = X - tu;
-            const bool ok = (unsigned)Y < (unsigned)h && (unsigned)X < (unsigned)w && (unsigned)sy < (unsigned)sh && (unsigned)sx < (unsigned)sw;
+            const bool ok = live && (unsigned)Y < (unsigned)h && (unsigned)X < (unsigned)w && (unsigned)sy < (unsigned)sh && (unsigned)sx < (unsigned)sw;
             c[t] = 0u; al[t] = 0.0;
             if (ok) {
+                const int64_t q = fsrc + (int64_t)sy * sw + sx;
                 if (FG) {
-                    const int64_t q = ((int64_t)frame * sh + sy) * sw + sx;
                     const uint2 e = __ldg(reinterpret_cast<const uint2 *>(src_all) + q);
                     c[t] = e.x; al[t] = alpha64 ? __ldg(alpha64 + q) : (double)__uint_as_float(e.y);
+                } else if (W4) {
+                    c[t] = vm_ld3(reinterpret_cast<const uint32_t *>(src_all), q * 3, src_last_word);
                 } else {
-                    const uint8_t *p = reinterpret_cast<const uint8_t *>(src_all) + (((int64_t)frame * sh + sy) * sw + sx) * 3;
+                    const uint8_t *p = reinterpret_cast<const uint8_t *>(src_all) + q * 3;
                     c[t] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
                 }
             }
@@ -367,10 +402,20 @@ k_aug_affine(const void *__restrict__ src_all, const double *__restrict__ alpha6
 #pragma unroll
         for (int k = 0; k < 3; ++k)
             ch[k] = VmTap<uint8_t>::blend((c[0] >> (8 * k)) & 255, (c[1] >> (8 * k)) & 255, (c[2] >> (8 * k)) & 255, (c[3] >> (8 * k)) & 255, fx, fy);
-        const uint32_t o = vm_illum_px(ch[0], ch[1], ch[2], sdiv, hdiv, slut, vm_hsv_body(x, w, vec));
+        const uint32_t o = vm_illum_px(ch[0], ch[1], ch[2], sdiv, hdiv, slut, body);
         const int64_t p = ((int64_t)frame * h + y) * w + x;
-        out_bgr[p * 3] = (uint8_t)o; out_bgr[p * 3 + 1] = (uint8_t)(o >> 8); out_bgr[p * 3 + 2] = (uint8_t)(o >> 16);
-        if (FG) {
+        if (W4) {
+            // lanes 4g .. 4g+3 hold pixels o0 .. o3 = 12 bytes = words {o0 | o1 << 24, o1 >> 8 | o2 << 16, o2 >> 16 | o3 << 8}
+            const uint32_t nxt = __shfl_down_sync(0xffffffffu, o, 1);
+            const int k = threadIdx.x & 3;
+            if (live && k < 3) {
+                const uint32_t word = (o >> (8 * k)) | (nxt << (24 - 8 * k));
+                reinterpret_cast<uint32_t *>(out_bgr)[((p - k) * 3 >> 2) + k] = word;
+            }
+        } else {
+            out_bgr[p * 3] = (uint8_t)o; out_bgr[p * 3 + 1] = (uint8_t)(o >> 8); out_bgr[p * 3 + 2] = (uint8_t)(o >> 16);
+        }
+        if (FG && live) {
             const double a = VmTap<double>::blend(al[0], al[1], al[2], al[3], fx, fy);
             if (out_alpha64) out_alpha64[p] = a; else out_alpha[p] = (float)a;
         }
@@ -388,7 +433,27 @@ extern "C" int vm_aug_affine(int mode, const void *src, const double *alpha64, c
     if (n == 0) return VM_OK;
     const dim3 grid((w + 255) / 256, (h + VA_AFF_ROWS - 1) / VA_AFF_ROWS, n);
     cudaStream_t st = (cudaStream_t)stream;
-    if (mode == 1) k_aug_affine<true><<<grid, 256, 0, st>>>(src, alpha64, (const VmAugParams *)params, luts, h, w, out_bgr, out_alpha, out_alpha64, hsv_vec);
-    else k_aug_affine<false><<<grid, 256, 0, st>>>(src, nullptr, (const VmAugParams *)params, luts, h, w, out_bgr, nullptr, nullptr, hsv_vec);
+    {
+        static std::mutex mu;
+        static bool done[64];
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { vm_set_error("vm_aug_affine: cudaGetDevice failed"); return VM_ERR_CUDA; }
+        std::lock_guard<std::mutex> lk(mu);
+        if (!done[dev]) {                                                  // division tables: once per device (stream-ordered before the first use)
+            k_va_tables<<<1, 256, 0, st>>>();
+            if (cudaStreamSynchronize(st) != cudaSuccess) { vm_set_error("vm_aug_affine: table init failed"); return VM_ERR_CUDA; }
+            done[dev] = true;
+        }
+    }
+    // 32-bit colour accesses need 4-byte aligned planes and rows: w % 4 == 0 makes every row start a multiple of 12 bytes
+    const bool w4 = (w & 3) == 0 && vm_aligned(out_bgr, 4) && (mode == 1 || vm_aligned(src, 4));
+    const int64_t last_word = mode == 0 ? ((int64_t)n * h * w * 3) / 4 - 1 : 0;
+    if (mode == 1) {
+        if (w4) k_aug_affine<true, true><<<grid, 256, 0, st>>>(src, alpha64, (const VmAugParams *)params, luts, h, w, out_bgr, out_alpha, out_alpha64, hsv_vec, last_word);
+        else k_aug_affine<true, false><<<grid, 256, 0, st>>>(src, alpha64, (const VmAugParams *)params, luts, h, w, out_bgr, out_alpha, out_alpha64, hsv_vec, last_word);
+    } else {
+        if (w4) k_aug_affine<false, true><<<grid, 256, 0, st>>>(src, nullptr, (const VmAugParams *)params, luts, h, w, out_bgr, nullptr, nullptr, hsv_vec, last_word);
+        else k_aug_affine<false, false><<<grid, 256, 0, st>>>(src, nullptr, (const VmAugParams *)params, luts, h, w, out_bgr, nullptr, nullptr, hsv_vec, last_word);
+    }
     return vm_check_launch("vm_aug_affine");
 }

@@ -272,7 +272,7 @@ def solve_grids(grids, device=None, pool=None):
     host cores.  Returns CUDA (ctrl, coef)."""
     ctrl, coef = pool.solve(grids, per_task=8) if pool is not None else _host.solve_many(grids)
     dev = torch.device(device if device is not None else "cuda")
-    return torch.from_numpy(ctrl).to(dev), torch.from_numpy(coef).to(dev)
+    return N.upload(ctrl, dev), N.upload(coef, dev)
 
 
 # ----------------------------------------------------------------------------------------
