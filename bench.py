@@ -497,14 +497,15 @@ def bench_configs(vm, torch, dev, rank, world, barrier, max_over_ranks, peak, po
         stats = vm.augmentation.alpha_stats(fg)
         np.random.seed(1 + rank)
         barrier()
-        for _ in range(2):
+        c5_iters = 3 * iters                            # a long-running writer: the first calls after a pause wait for the solver pool to wake up
+        for _ in range(4):
             vm.augmentation.augment_clip(fg, bgn, stats=stats, pool=pool)
         barrier()
         t = time.perf_counter()
-        for _ in range(iters):
+        for _ in range(c5_iters):
             vm.augmentation.augment_clip(fg, bgn, stats=stats, pool=pool)
         barrier()
-        ms5 = 1e3 * max_over_ranks(time.perf_counter() - t) / iters
+        ms5 = 1e3 * max_over_ranks(time.perf_counter() - t) / c5_iters
         rec("C5 augmentation.augment_clip (RNG plan + host pinv on the solver pool + TPS + 2 affine passes + illumination), 1080p x 64, wall clock",
             "c5", h, w, n, ms5, {"host_bound": True})
         del fg, fb, ff, bg, bgn

@@ -152,6 +152,46 @@ def upload(arr, device):
     return t.pin_memory().to(device, non_blocking=True)
 
 
+_rings = {}
+
+
+def upload_many(arrays, device, slots=8):
+    """Several small host arrays -> CUDA tensors with ONE asynchronous copy from a persistent ring of pinned
+    staging buffers (no allocator call, no implicit synchronisation; slot k is reused `slots` calls later, after the
+    event recorded behind its copy).  Returns tensors of the arrays' dtypes and shapes (views of one device buffer)."""
+    require_cuda()
+    device = torch.device(device)
+    arrs = [np.ascontiguousarray(a) for a in arrays]
+    offs, total = [], 0
+    for a in arrs:
+        offs.append(total)
+        total += (a.nbytes + 15) & ~15
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    ring = _rings.get(key)
+    if ring is None or ring["bytes"] < total:
+        size = max(1 << 16, 1 << (max(total, 1) - 1).bit_length())
+        ring = {"bytes": size, "next": 0,
+                "slots": [(torch.empty(size, dtype=torch.uint8).pin_memory(), torch.cuda.Event()) for _ in range(slots)], "used": [False] * slots}
+        _rings[key] = ring
+    k = ring["next"]
+    ring["next"] = (k + 1) % len(ring["slots"])
+    pinned, event = ring["slots"][k]
+    if ring["used"][k]:
+        event.synchronize()
+    host = pinned.numpy()
+    for a, o in zip(arrs, offs):
+        host[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
+    dev = torch.empty(max(total, 16), dtype=torch.uint8, device=device)
+    dev[:total].copy_(pinned[:total], non_blocking=True)
+    event.record(torch.cuda.current_stream(device))
+    ring["used"][k] = True
+    out = []
+    for a, o in zip(arrs, offs):
+        t = dev[o:o + a.nbytes]
+        out.append(t.view(torch.from_numpy(a[:0].reshape(-1)).dtype).view(a.shape) if a.dtype != np.uint8 else t.view(a.shape))
+    return out
+
+
 def from_device(t, kind):
     if kind == "cuda":
         return t

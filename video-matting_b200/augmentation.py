@@ -245,9 +245,10 @@ def _augment_run(fg_d, bg_d, plan, alpha_dtype=torch.float32, status=None, pool=
     new_alpha = torch.empty((n, h, w), dtype=torch.float64 if wide else torch.float32, device=dev)
     a64 = torch.empty((n, h + 1, w + 1), dtype=torch.float64, device=dev) if wide else None
     tplan = P.get_plan((0, 0, h, w), 2, dev)
-    ctrl, coef = P.solve_grids(grids, dev, pool=pool)
-    up = lambda arr: N.upload(np.ascontiguousarray(arr).view(np.uint8).reshape(-1), dev)
-    par_bg_d, par_fg_d, luts_d = up(par_bg), up(par_fg), up(luts)
+    ctrl_h, coef_h = P.solve_grids_host(grids, pool=pool)
+    flat = lambda arr: np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+    # one asynchronous upload per call (pinned ring): nothing here waits for the kernels of the previous call
+    ctrl, coef, par_bg_d, par_fg_d, luts_d = N.upload_many([ctrl_h, coef_h, flat(par_bg), flat(par_fg), flat(luts)], dev)
     T = torch.empty((n, tplan.nx, tplan.ny, 2), dtype=torch.float64, device=dev)
     counter = torch.zeros(64, dtype=torch.int32, device=dev)
     inter = torch.empty((n, h + 1, w + 1, 2), dtype=torch.int32, device=dev)

@@ -325,9 +325,14 @@ __device__ __forceinline__ uint32_t vm_ld3(const uint32_t *__restrict__ words, i
 // FG: source = packed (sh, sw) = (h+1, w+1) intermediate {bgr, alpha float bits} of vm_aug_tps -> new_fg uint8 x3
 // (after the illumination change) + new_alpha float32.  !FG: source = (h, w, 3) uint8 background -> new_bg.
 // CTA = 256 columns x VA_AFF_ROWS rows, one column per thread.  Per-row terms of the coordinate transform come from
-// shared memory (they are the same for the whole row), the division tables from global memory; W4 (w % 4 == 0 and
-// 4-byte aligned planes): the background is read with aligned 32-bit loads and the three colour bytes of four
-// neighbouring lanes leave as three 32-bit stores (one shuffle per lane) instead of twelve byte stores.
+// shared memory (they are the same for the whole row), the division tables from global memory.  W4 (w % 4 == 0 and
+// 4-byte aligned planes): *interior* pixels - all four taps inside the shifted image and inside the source, the bulk of
+// a frame - take a branch-free path: one 32-bit offset from the frame's base pointer, the background's two taps of a
+// row as three aligned words + funnel shifts, the lane-packed blend of vm_blend_lanes (same integers as VmTap<uint8_t>),
+// float32 alpha taps blended in float32 (the float64 plane, when carried, in cv2's float64 order); the three colour
+// bytes of four neighbouring lanes leave as three 32-bit stores (one shuffle per lane).  Everything else goes through the
+// tap-by-tap code with OpenCV's border rule.  ncu before this path: 366 executed instructions per pixel, issue slots
+// 82 % busy - the kernel was bound by its predicates, branches and 64-bit index arithmetic, not by memory.
 template <bool FG, bool W4>
 __global__ void __launch_bounds__(256)
 k_aug_affine(const void *__restrict__ src_all, const double *__restrict__ alpha64, const VmAugParams *__restrict__ params,
@@ -373,36 +378,84 @@ k_aug_affine(const void *__restrict__ src_all, const double *__restrict__ alpha6
     const bool body = vm_hsv_body(x, w, vec);
     const int yend = min(y0 + VA_AFF_ROWS, h);
     const int64_t fsrc = (int64_t)frame * sh * sw;
+    // interior: iy in [ylo, yhi] and ix in [xlo, xhi] <=> 0 <= Y, Y + 1 < h, 0 <= Y - tv, Y + 1 - tv < sh (same for X)
+    const int ylo = max(0, tv), yhi = min(h - 2, sh - 2 + tv), xlo = max(0, tu), xhi = min(w - 2, sw - 2 + tu);
+    const bool any_fast = W4 && yhi >= ylo && xhi >= xlo && (int64_t)sh * sw < (1ll << 28);
+    const unsigned yspan = (unsigned)(yhi - ylo), xspan = (unsigned)(xhi - xlo);
+    const int qoff = tv * sw + tu;
+    const uint2 *fsrc2 = reinterpret_cast<const uint2 *>(src_all) + (FG ? fsrc : 0);               // FG: packed {bgr, alpha} frame
+    const uint32_t *fsrcw = reinterpret_cast<const uint32_t *>(src_all) + (FG ? 0 : (fsrc * 3 >> 2));   // !FG, W4: rows are 4-byte aligned
+    asm volatile("" : "+l"(fsrc2));
+    asm volatile("" : "+l"(fsrcw));
     for (int y = y0; y < yend; ++y) {
         const int SX = (int)((unsigned)rowX0[y - y0] + (unsigned)adelta) >> 5;
         const int SY = (int)((unsigned)rowY0[y - y0] + (unsigned)bdelta) >> 5;
-        const int ix = vm_sat_s16(SX >> 5), iy = vm_sat_s16(SY >> 5), fx = SX & 31, fy = SY & 31;
-        uint32_t c[4];
-        double al[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int Y = iy + (t >> 1), X = ix + (t & 1);
-            const int sy = Y - tv, sx = X - tu;
-            const bool ok = live && (unsigned)Y < (unsigned)h && (unsigned)X < (unsigned)w && (unsigned)sy < (unsigned)sh && (unsigned)sx < (unsigned)sw;
-            c[t] = 0u; al[t] = 0.0;
-            if (ok) {
-                const int64_t q = fsrc + (int64_t)sy * sw + sx;
-                if (FG) {
-                    const uint2 e = __ldg(reinterpret_cast<const uint2 *>(src_all) + q);
-                    c[t] = e.x; al[t] = alpha64 ? __ldg(alpha64 + q) : (double)__uint_as_float(e.y);
-                } else if (W4) {
-                    c[t] = vm_ld3(reinterpret_cast<const uint32_t *>(src_all), q * 3, src_last_word);
+        const int fx = SX & 31, fy = SY & 31;
+        uint32_t bgr;
+        float af = 0.f;
+        double ad = 0.0;
+        if (any_fast && live && (unsigned)((SY >> 5) - ylo) <= yspan && (unsigned)((SX >> 5) - xlo) <= xspan) {
+            const unsigned q = (unsigned)((SY >> 5) * sw + (SX >> 5) - qoff);
+            uint32_t c0, c1, c2, c3;
+            if (FG) {
+                const uint2 *g0 = fsrc2 + q, *g1 = g0 + (unsigned)sw;
+                const uint2 e0 = __ldg(g0), e1 = __ldg(g0 + 1), e2 = __ldg(g1), e3 = __ldg(g1 + 1);
+                c0 = e0.x & 0x00FFFFFFu; c1 = e1.x & 0x00FFFFFFu; c2 = e2.x & 0x00FFFFFFu; c3 = e3.x & 0x00FFFFFFu;
+                if (alpha64) {
+                    const double *ap = alpha64 + fsrc + q;
+                    ad = VmTap<double>::blend(__ldg(ap), __ldg(ap + 1), __ldg(ap + sw), __ldg(ap + sw + 1), fx, fy);
                 } else {
-                    const uint8_t *p = reinterpret_cast<const uint8_t *>(src_all) + q * 3;
-                    c[t] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+                    af = VmTap<float>::blend(__uint_as_float(e0.y), __uint_as_float(e1.y), __uint_as_float(e2.y), __uint_as_float(e3.y), fx, fy);
+                }
+            } else {
+                // the two taps of a row are 6 consecutive bytes at byte offset 3 q: three aligned words and funnel shifts;
+                // the row pitch 3 sw is a multiple of 4, so both rows share the byte phase
+                const unsigned o = 3u * q, sh8 = (o & 3u) * 8u;
+                const uint32_t *r0 = fsrcw + (o >> 2), *r1 = r0 + (unsigned)(3 * sw >> 2);
+                const uint32_t u0 = __ldg(r0), u1 = __ldg(r0 + 1), u2 = __ldg(r0 + 2);
+                const uint32_t v0 = __ldg(r1), v1 = __ldg(r1 + 1), v2 = __ldg(r1 + 2);
+                const uint32_t ul = __funnelshift_r(u0, u1, sh8), uh = __funnelshift_r(u1, u2, sh8);
+                const uint32_t vl = __funnelshift_r(v0, v1, sh8), vh = __funnelshift_r(v1, v2, sh8);
+                c0 = ul & 0x00FFFFFFu; c1 = __funnelshift_r(ul, uh, 24) & 0x00FFFFFFu;
+                c2 = vl & 0x00FFFFFFu; c3 = __funnelshift_r(vl, vh, 24) & 0x00FFFFFFu;
+            }
+            uint32_t ta_unused;
+            vm_blend_lanes(c0, c1, c2, c3, (uint32_t)fx, (uint32_t)fy, bgr, ta_unused);
+        } else {
+            const int ix = vm_sat_s16(SX >> 5), iy = vm_sat_s16(SY >> 5);
+            uint32_t c[4];
+            double al[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int Y = iy + (t >> 1), X = ix + (t & 1);
+                const int sy = Y - tv, sx = X - tu;
+                const bool ok = live && (unsigned)Y < (unsigned)h && (unsigned)X < (unsigned)w && (unsigned)sy < (unsigned)sh && (unsigned)sx < (unsigned)sw;
+                c[t] = 0u; al[t] = 0.0;
+                if (ok) {
+                    const int64_t q = fsrc + (int64_t)sy * sw + sx;
+                    if (FG) {
+                        const uint2 e = __ldg(reinterpret_cast<const uint2 *>(src_all) + q);
+                        c[t] = e.x; al[t] = alpha64 ? __ldg(alpha64 + q) : (double)__uint_as_float(e.y);
+                    } else if (W4) {
+                        c[t] = vm_ld3(reinterpret_cast<const uint32_t *>(src_all), q * 3, src_last_word);
+                    } else {
+                        const uint8_t *p = reinterpret_cast<const uint8_t *>(src_all) + q * 3;
+                        c[t] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+                    }
                 }
             }
-        }
-        int ch[3];
+            bgr = 0u;
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-            ch[k] = VmTap<uint8_t>::blend((c[0] >> (8 * k)) & 255, (c[1] >> (8 * k)) & 255, (c[2] >> (8 * k)) & 255, (c[3] >> (8 * k)) & 255, fx, fy);
-        const uint32_t o = vm_illum_px(ch[0], ch[1], ch[2], sdiv, hdiv, slut, body);
+            for (int k = 0; k < 3; ++k)
+                bgr |= (uint32_t)VmTap<uint8_t>::blend((c[0] >> (8 * k)) & 255, (c[1] >> (8 * k)) & 255, (c[2] >> (8 * k)) & 255, (c[3] >> (8 * k)) & 255, fx, fy) << (8 * k);
+            if (FG) {
+                // float32 alpha taps: float32 products of exact weights, summed in tap order - the same expression as the
+                // interior path, so a pixel's value does not depend on which path took it
+                if (alpha64) ad = VmTap<double>::blend(al[0], al[1], al[2], al[3], fx, fy);
+                else af = VmTap<float>::blend((float)al[0], (float)al[1], (float)al[2], (float)al[3], fx, fy);
+            }
+        }
+        const uint32_t o = vm_illum_px((int)(bgr & 255u), (int)((bgr >> 8) & 255u), (int)(bgr >> 16), sdiv, hdiv, slut, body);
         const int64_t p = ((int64_t)frame * h + y) * w + x;
         if (W4) {
             // lanes 4g .. 4g+3 hold pixels o0 .. o3 = 12 bytes = words {o0 | o1 << 24, o1 >> 8 | o2 << 16, o2 >> 16 | o3 << 8}
@@ -416,8 +469,7 @@ k_aug_affine(const void *__restrict__ src_all, const double *__restrict__ alpha6
             out_bgr[p * 3] = (uint8_t)o; out_bgr[p * 3 + 1] = (uint8_t)(o >> 8); out_bgr[p * 3 + 2] = (uint8_t)(o >> 16);
         }
         if (FG && live) {
-            const double a = VmTap<double>::blend(al[0], al[1], al[2], al[3], fx, fy);
-            if (out_alpha64) out_alpha64[p] = a; else out_alpha[p] = (float)a;
+            if (out_alpha64) out_alpha64[p] = ad; else out_alpha[p] = af;
         }
     }
 }

@@ -265,6 +265,11 @@ _stacked_kernel_ok = _host._stacked_kernel_ok      # same list object: tests fli
 _solve_chunk = _host.solve_chunk
 
 
+def solve_grids_host(grids, pool=None):
+    """solve_grids without the upload: NumPy (ctrl (n, N, 2), coef (n, N + 3, 2)) float64."""
+    return pool.solve(grids, per_task=8) if pool is not None else _host.solve_many(grids)
+
+
 def solve_grids(grids, device=None, pool=None):
     """Host solve for a batch of (regular grid, deformed grid) pairs as used by
     augmentation.warp_image(..., thin=grids): the system is built from the DEFORMED grid and maps
