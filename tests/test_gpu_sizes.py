@@ -355,3 +355,25 @@ def test_config5_augment_1080p_vs_oracle(vm):
         pool.close()
     assert np.array_equal(cbg[0], nbg) and np.allclose(cal[0], nal, rtol=RTOL, atol=1e-6)
     assert np.count_nonzero((cfg[0] != nfg).any(axis=2)) <= 6
+
+
+def test_upload_many_ring_reuse(vm):
+    """_native.upload_many: every array arrives intact, with its dtype and shape, also when the pinned ring wraps
+    around (more calls than slots) and when a later call needs a larger staging buffer."""
+    N = vm._native
+    dev = torch.device("cuda", 0)
+    rng = np.random.RandomState(5)
+    kept = []
+    for k in range(20):
+        arrs = [rng.rand(3 + k % 4, 25, 2), rng.rand(3 + k % 4, 28, 2), rng.randint(0, 256, size=(7 + k, 56)).astype(np.uint8),
+                rng.randint(0, 256, size=(257,)).astype(np.uint8), rng.rand(5).astype(np.float32)]
+        if k == 12:
+            arrs.append(rng.rand(40000))                                   # 320 KB: the ring is rebuilt with larger slots
+        outs = N.upload_many(arrs, dev)
+        kept.append((arrs, outs))
+    torch.cuda.synchronize()
+    for arrs, outs in kept:
+        assert len(arrs) == len(outs)
+        for a, t in zip(arrs, outs):
+            assert t.is_cuda and tuple(t.shape) == a.shape and t.cpu().numpy().dtype == a.dtype
+            assert np.array_equal(t.cpu().numpy(), a)
