@@ -43,6 +43,8 @@ int g_vl_sub = 0;            // frames per flow-stage / resampling sub-round ins
 int g_vl_box_cap = 0;        // source-box entries per B2 tile (0: as many as the occupancy target allows)
 int g_vl_floors = 1;         // 1: the spline stage also writes packed int16 floors of T for the tile-box stage
 int g_vl_minb = 4;           // B2 occupancy target (CTAs of 256 threads per SM: 2, 3 or 4)
+int g_va_minb = 12;          // k_aug_tps: CTAs of 128 threads per SM: 12 (40 registers, 60 bytes of spills, 48 warps per SM) measured 4.22 ms per
+                             // augment_clip call of 64 x 1080p against 4.32-4.47 at 8 (64 registers), 4.33 at 10, 4.76 at 16: the gathers want warps
 
 __device__ double2 g_vl_tab[VL_TAB_N];
 
@@ -779,6 +781,7 @@ int vm_lean_set_option(const char *key, int value) {
     if (!strcmp(key, "lean_fine_rows") && value >= 1 && value <= 256) { g_vl_fine_rows = value; return VM_OK; }
     if (!strcmp(key, "lean_floors") && (value == 0 || value == 1)) { g_vl_floors = value; return VM_OK; }
     if (!strcmp(key, "lean_b1_ctas") && value >= 0 && value <= 4096) { g_vl_b1_ctas = value; return VM_OK; }
+    if (!strcmp(key, "lean_aug_minb") && (value == 8 || value == 12)) { g_va_minb = value; return VM_OK; }
     return VM_ERR_ARG;
 }
 
@@ -980,7 +983,8 @@ __device__ __noinline__ uint2 vl_exact_cols(const uint32_t *__restrict__ src, do
 }
 
 #define VA_ROWS 16
-__global__ void __launch_bounds__(128)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_aug_tps(const uint32_t *__restrict__ fg, const double2 *__restrict__ T, int nx, int ny,
           const vm_axis_entry *__restrict__ rows, const vm_axis_entry *__restrict__ cols, int h, int w,
           uint2 *__restrict__ inter, double *__restrict__ alpha64, int32_t *__restrict__ status) {
@@ -1066,7 +1070,9 @@ extern "C" int vm_aug_tps(const uint8_t *fg_bgra, const void *T, int nx, int ny,
     if (n == 0) return VM_OK;
     const dim3 grid((w + 1 + 127) / 128, (h + 1 + VA_ROWS - 1) / VA_ROWS, n);
     VM_REQUIRE(grid.y <= 65535, "frame too tall");
-    k_aug_tps<<<grid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t *>(fg_bgra), reinterpret_cast<const double2 *>(T), nx, ny,
-                                                       rows, cols, h, w, reinterpret_cast<uint2 *>(inter), alpha64, status);
+#define VA_TPS(U) k_aug_tps<U><<<grid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t *>(fg_bgra), reinterpret_cast<const double2 *>(T), nx, ny, \
+                                                       rows, cols, h, w, reinterpret_cast<uint2 *>(inter), alpha64, status)
+    if (g_va_minb == 8) VA_TPS(8); else VA_TPS(12);
+#undef VA_TPS
     return vm_check_launch("vm_aug_tps");
 }
