@@ -47,6 +47,22 @@ int g_va_minb = 12;          // k_aug_tps: CTAs of 128 threads per SM: 12 (40 re
                              // augment_clip call of 64 x 1080p against 4.32-4.47 at 8 (64 registers), 4.33 at 10, 4.76 at 16: the gathers want warps
 
 __device__ double2 g_vl_tab[VL_TAB_N];
+// -DVL_TIMING: cycles per phase of the resampling CTAs, accumulated by thread 0 and by the last thread of every CTA
+// (scripts/fine_phases.py); not part of the product build
+#ifdef VL_TIMING
+__constant__ int c_vl_abl;        // timing-only ablation (wrong output): 1 no source-box copies, 2 no background copies, 4 no transform loads, 8 no store
+__device__ unsigned long long g_vl_prof[16];
+#define VL_T(i) do { if (vl_tim) { const long long t_ = clock64(); vl_acc[i] += (unsigned long long)(t_ - vl_t0); vl_t0 = t_; } } while (0)
+extern "C" int vm_lean_prof_read(unsigned long long *out16, int reset) {
+    if (cudaMemcpyFromSymbol(out16, g_vl_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return VM_ERR_CUDA;
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_vl_prof, z, sizeof(z)); }
+    return VM_OK;
+}
+#define VL_ABL(b) (c_vl_abl & (b))
+#else
+#define VL_T(i) do { } while (0)
+#define VL_ABL(b) false
+#endif
 
 static std::mutex g_vl_mu;
 static bool g_vl_done[64];
@@ -392,7 +408,10 @@ static int vl_launch_coarse(const double *ctrl, const double *coef, int N, int n
 // Tiles whose box does not fit (strongly stretched grids) gather the taps from global memory;
 // plans whose axis tables are not monotone windows take everything from global memory.
 // ---------------------------------------------------------------------------------------
+#ifndef VL_FW
 #define VL_FW 64                                   // columns per CTA
+#endif
+#define VL_BG ((VL_FW / 2 + 4 + 31) / 32)          // 32-lane groups covering the coarse columns of a tile
 #ifndef VL_FS
 #define VL_FS 4                                    // row strips per CTA (256 threads; -DVL_FS=2: 128-thread CTAs, 64 x 16 tiles)
 #endif
@@ -453,7 +472,7 @@ __device__ __forceinline__ void vl_strip_tile(const typename VlSrc<SRC>::elem *_
             if (n0 <= -2 || n0 >= h || n1 <= -2 || n1 >= w) { o = make_float4(b0, b1, b2, 0.f); ++*outside; }
             else o = vl_exact_px<SRC>(src, t0, t1, h, w, bgp, o, na, unc, outside);
         }
-        __stcs(op, o);                                                 // streamed once: evict first
+        if (!VL_ABL(8) || o.x == 1.2345e33f) __stcs(op, o);             // streamed once: evict first
         bgl += pitch; bgp += w3; op += w;
     }
 }
@@ -544,20 +563,20 @@ k_lean_boxes(const double2 *__restrict__ T, const int *__restrict__ F, int nx, i
         const int64_t woff = (int64_t)frame * nx * ny + (int64_t)kr0 * ny + kc0;
         const double2 *Tf = T + woff;
         int rlo = INT_MAX, rhi = INT_MIN, clo = INT_MAX, chi = INT_MIN, bad = 0;
-        if (F && nkr <= VL_TR && nkc <= 64) {                            // packed floors written by the spline stage:
+        if (F && nkr <= VL_TR && nkc <= 32 * VL_BG) {                            // packed floors written by the spline stage:
             const int *Ff = F + woff;                                    // every load of the window is issued before the
-            int v[VL_TR][2];                                             // first one is used (the stage is latency bound)
+            int v[VL_TR][VL_BG];                                             // first one is used (the stage is latency bound)
 #pragma unroll
             for (int r = 0; r < VL_TR; ++r)
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
+                for (int g = 0; g < VL_BG; ++g) {
                     const int c = lane + 32 * g;
                     v[r][g] = (r < nkr && c < nkc) ? __ldg(Ff + (int64_t)r * ny + c) : 0x7FFF7FFF;     // 0x7FFF7FFF: no point
                 }
 #pragma unroll
             for (int r = 0; r < VL_TR; ++r)
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
+                for (int g = 0; g < VL_BG; ++g) {
                     const int x = v[r][g];
                     if (x == VL_FLOOR_BAD) bad = 1;
                     else if (x != 0x7FFF7FFF) {
@@ -605,6 +624,11 @@ __device__ __forceinline__ void vl_fine_tile(VlFineSmem &S, uint32_t &phase, con
                                              float4 *__restrict__ out, int &outside, int &slow) {
     typedef typename VlSrc<SRC>::elem elem;
     const int tid = threadIdx.y * VL_FW + threadIdx.x;
+#ifdef VL_TIMING
+    const bool vl_tim = tid == 0 || tid == VL_FW * VL_FS - 1;          // warp 0 (issues / polls the bulk copies) and the last warp
+    long long vl_t0 = clock64();
+    unsigned long long vl_acc[6] = {0, 0, 0, 0, 0, 0};
+#endif
     const int J0 = bx * VL_FW, I0 = by * (VL_FS * rpt);
     const int tw = min(VL_FW, w - J0), th = min(VL_FS * rpt, h - I0);
     const int jc = min((int)threadIdx.x, tw - 1), j = J0 + jc;
@@ -616,21 +640,36 @@ __device__ __forceinline__ void vl_fine_tile(VlFineSmem &S, uint32_t &phase, con
     const uint8_t *bgf = bg + (int64_t)bgi * h * w * 3;
     const double2 *Tf = T + (int64_t)frame * nx * ny;
 
-    // ---- P0: axis entries ------------------------------------------------------------------
+    // ---- P0: axis entries.  Every load of the prologue that does not depend on another one is issued here, before the
+    // first use: the column entry of the thread, the first / last column and row entries of the tile (they give the coarse
+    // window without a round trip through shared memory) and the thread's row entry ------------------------------------
     const vm_axis_entry ce = vm_ld_axis(cols + j);
-    vm_axis_entry myrow = {0.0, 0, 0};
-    if (tid < th) { myrow = vm_ld_axis(rows + I0 + tid); S.rows[tid] = myrow; }
-    __syncthreads();
-    const int kr0 = S.rows[0].i0, kr1 = max(S.rows[th - 1].i1, S.rows[th - 1].i0);
-    const int nkr = kr1 - kr0 + 1;
-    // every (i0, i1) of the tile's rows must lie inside the window that Cs covers
-    const bool row_ok = tid >= th || (myrow.i0 >= kr0 && myrow.i0 <= kr1 && myrow.i1 >= kr0 && myrow.i1 <= kr1);
-    // ... and every (i0, i1) of its columns inside the window k_lean_boxes scanned
     const vm_axis_entry cf = vm_ld_axis(cols + J0), cl = vm_ld_axis(cols + J0 + tw - 1);
+    const vm_axis_entry rf = vm_ld_axis(rows + I0), rl = vm_ld_axis(rows + I0 + th - 1);
+    vm_axis_entry myrow = {0.0, 0, 0};
+    if (tid < th) myrow = vm_ld_axis(rows + I0 + tid);
+    const int kr0 = rf.i0, kr1 = max(rl.i1, rl.i0);
+    const int nkr = kr1 - kr0 + 1;
     const int kc0 = cf.i0, kc1 = max(cl.i1, cl.i0);
+    // every (i0, i1) of the tile's rows must lie inside the window that Cs covers, and every (i0, i1) of its columns
+    // inside the window k_lean_boxes scanned
+    const bool row_ok = tid >= th || (myrow.i0 >= kr0 && myrow.i0 <= kr1 && myrow.i1 >= kr0 && myrow.i1 <= kr1);
     const bool win_ok = nkr >= 1 && nkr <= VL_TR && kr0 >= 0 && kr1 < nx && kc0 >= 0 && kc1 < ny &&
                         ce.i0 >= kc0 && ce.i0 <= kc1 && ce.i1 >= kc0 && ce.i1 <= kc1;
-    const bool all_staged = __syncthreads_and(row_ok && win_ok);
+    // the thread's share of the coarse window (P2) is requested now: its latency runs under the vote and the bulk-copy issue
+    constexpr int KMAX = (VL_TR + VL_FS - 1) / VL_FS;
+    double2 ta[KMAX], tb[KMAX];
+    if (win_ok) {
+        const double2 *Ta = Tf + (int64_t)kr0 * ny + ce.i0, *Tb = Tf + (int64_t)kr0 * ny + ce.i1;
+#pragma unroll
+        for (int u = 0; u < KMAX; ++u) {
+            const int k = min((int)threadIdx.y + u * VL_FS, nkr - 1);
+            ta[u] = __ldg(Ta + k * ny); tb[u] = __ldg(Tb + k * ny);
+        }
+    }
+    if (tid < th) S.rows[tid] = myrow;
+    const bool all_staged = __syncthreads_and(row_ok && win_ok);         // (also publishes S.rows)
+    VL_T(0);                                                            // P0: set-up, axis entries, one CTA barrier
 
     const int strip0 = threadIdx.y * rpt;                               // first row of the strip inside the CTA
     const int nrows = min(rpt, th - strip0);
@@ -648,42 +687,37 @@ __device__ __forceinline__ void vl_fine_tile(VlFineSmem &S, uint32_t &phase, con
     // ---- P1: bulk async copies (TMA): background rows + source box, all on one mbarrier -------
     const bool bg_sm = tw == VL_FW && (w & 15) == 0 && (reinterpret_cast<uintptr_t>(bg) & 15) == 0;
     const bool boxed = rec.bw > 0 && (reinterpret_cast<uintptr_t>(src_all) & 15) == 0;
-    const bool used = bg_sm || boxed;
+    const bool copy_box = boxed && !VL_ABL(1), copy_bg = bg_sm && !VL_ABL(2);
+    const bool used = copy_bg || copy_box;
     elem *boxp = reinterpret_cast<elem *>(S.box);
-    if (tid < 32 && used) {                                             // warp 0: one lane per row, 32 copies per instruction
+    if (used) {
+        // the copies are dealt out over all warps - copy c goes to lane c / W of warp c % W (W warps per CTA): a warp's
+        // bulk-copy instruction is executed lane by lane (~65 cycles per copy, -DVL_TIMING), so 72 copies by the lanes of ONE
+        // warp kept that warp busy for a third of the tile's time while the other seven waited at the barrier
+        constexpr int NW = VL_FW * VL_FS / 32;
         if (tid == 0) {
-            const uint32_t bytes = (bg_sm ? (uint32_t)(th * VL_FW * 3) : 0u) + (boxed ? (uint32_t)(rec.bh * rec.bw * (int)sizeof(elem)) : 0u);
+            const uint32_t bytes = (copy_bg ? (uint32_t)(th * VL_FW * 3) : 0u) + (copy_box ? (uint32_t)(rec.bh * rec.bw * (int)sizeof(elem)) : 0u);
             // earlier generic accesses (this CTA's reads of the buffers; with XCTA also the acquired global
             // writes of other CTAs) are ordered before the async-proxy copies
             if (XCTA) asm volatile("fence.proxy.async;" ::: "memory");
             else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0), "r"(bytes) : "memory");
         }
-        __syncwarp();
-        if (boxed) {
-            const uint32_t row_bytes = (uint32_t)(rec.bw * (int)sizeof(elem));
-            const elem *g = src + (int64_t)rec.rmin * w + rec.cmin;
-            for (int r = tid; r < rec.bh; r += 32)
-                vl_bulk_g2s(vl_smem_u32(boxp + r * rec.bw), g + (int64_t)r * w, row_bytes, bar0);
-        }
-        if (bg_sm) {
-            const uint8_t *g = bgf + ((int64_t)I0 * w + J0) * 3;
-            for (int r = tid; r < th; r += 32)
-                vl_bulk_g2s(vl_smem_u32(S.bgt + r * (VL_FW * 3)), g + (int64_t)r * w * 3, VL_FW * 3, bar0);
+        const int c0 = (tid & 31) * NW + (tid >> 5);                   // this thread's first copy; further ones 32 * NW apart
+        const int nbox = copy_box ? rec.bh : 0, nbg = copy_bg ? th : 0;
+        const uint32_t row_bytes = (uint32_t)(rec.bw * (int)sizeof(elem));
+        const elem *gb = src + (int64_t)rec.rmin * w + rec.cmin;
+        const uint8_t *gg = bgf + ((int64_t)I0 * w + J0) * 3;
+        for (int c = c0; c < nbox + nbg; c += 32 * NW) {
+            if (c < nbox) vl_bulk_g2s(vl_smem_u32(boxp + c * rec.bw), gb + (int64_t)c * w, row_bytes, bar0);
+            else { const int r = c - nbox; vl_bulk_g2s(vl_smem_u32(S.bgt + r * (VL_FW * 3)), gg + (int64_t)r * w * 3, VL_FW * 3, bar0); }
         }
     }
 
+    VL_T(1);                                                            // P1: issue of the bulk copies (warp 0)
     // ---- P2: column-interpolated coarse rows; thread (jc, strip) takes rows strip, strip + VL_FS, ...
     {
         const double yf = ce.frac, y1 = 1.0 - yf;
-        const double2 *Ta = Tf + (int64_t)kr0 * ny + ce.i0, *Tb = Tf + (int64_t)kr0 * ny + ce.i1;
-        constexpr int KMAX = (VL_TR + VL_FS - 1) / VL_FS;
-        double2 ta[KMAX], tb[KMAX];
-#pragma unroll
-        for (int u = 0; u < KMAX; ++u) {
-            const int k = min((int)threadIdx.y + u * VL_FS, nkr - 1);
-            ta[u] = __ldg(Ta + k * ny); tb[u] = __ldg(Tb + k * ny);
-        }
 #pragma unroll
         for (int u = 0; u < KMAX; ++u) {
             const int k = threadIdx.y + u * VL_FS;
@@ -693,8 +727,10 @@ __device__ __forceinline__ void vl_fine_tile(VlFineSmem &S, uint32_t &phase, con
             }
         }
     }
+    VL_T(2);                                                            // P2: transform window -> Cs
     vl_cta_wait(bar0, tid < 32 && used, used, phase);
     if (used) phase ^= 1u;
+    VL_T(3);                                                            // wait for the bulk copies + CTA barrier
 
     const unsigned char *bgl = S.bgt + (strip0 * VL_FW + (int)threadIdx.x) * 3;
     const double2 *Csj = S.Cs + threadIdx.x;
@@ -707,6 +743,14 @@ __device__ __forceinline__ void vl_fine_tile(VlFineSmem &S, uint32_t &phase, con
         else if (boxed)     vl_strip_tile<SRC, true, false>(src, boxp, rec.rmin, rec.cmin, rec.bw, Csj, kr0, rp, bgl, bgp, op, nrows, h, w, &outside);
         else                vl_strip_tile<SRC, false, false>(src, boxp, 0, 0, 0, Csj, kr0, rp, bgl, bgp, op, nrows, h, w, &outside);
     }
+    VL_T(4);                                                            // P3: resampling + composite
+#ifdef VL_TIMING
+    if (vl_tim) {
+        const int o = tid == 0 ? 0 : 8;
+        for (int k = 0; k < 5; ++k) atomicAdd(&g_vl_prof[o + k], vl_acc[k]);
+        atomicAdd(&g_vl_prof[o + 7], 1ull);
+    }
+#endif
 }
 
 __device__ __forceinline__ void vl_bar_init(VlFineSmem &S) {
@@ -781,6 +825,9 @@ int vm_lean_set_option(const char *key, int value) {
     if (!strcmp(key, "lean_fine_rows") && value >= 1 && value <= 256) { g_vl_fine_rows = value; return VM_OK; }
     if (!strcmp(key, "lean_floors") && (value == 0 || value == 1)) { g_vl_floors = value; return VM_OK; }
     if (!strcmp(key, "lean_b1_ctas") && value >= 0 && value <= 4096) { g_vl_b1_ctas = value; return VM_OK; }
+#ifdef VL_TIMING
+    if (!strcmp(key, "lean_abl") && value >= 0 && value < 16) return cudaMemcpyToSymbol(c_vl_abl, &value, sizeof(int)) == cudaSuccess ? VM_OK : VM_ERR_CUDA;
+#endif
     if (!strcmp(key, "lean_aug_minb") && (value == 8 || value == 12)) { g_va_minb = value; return VM_OK; }
     return VM_ERR_ARG;
 }
