@@ -648,6 +648,37 @@ __device__ __forceinline__ void vl_fine_tile(VlFineSmem &S, uint32_t &phase, con
     const vm_axis_entry rf = vm_ld_axis(rows + I0), rl = vm_ld_axis(rows + I0 + th - 1);
     vm_axis_entry myrow = {0.0, 0, 0};
     if (tid < th) myrow = vm_ld_axis(rows + I0 + tid);
+    // ---- P1: bulk async copies (TMA): background rows + source box, all on one mbarrier.  They need the tile record only
+    // and are issued while the axis entries requested above are still on their way
+    const bool bg_sm = tw == VL_FW && (w & 15) == 0 && (reinterpret_cast<uintptr_t>(bg) & 15) == 0;
+    const bool boxed = rec.bw > 0 && (reinterpret_cast<uintptr_t>(src_all) & 15) == 0;
+    const bool copy_box = boxed && !VL_ABL(1), copy_bg = bg_sm && !VL_ABL(2);
+    const bool used = copy_bg || copy_box;
+    elem *boxp = reinterpret_cast<elem *>(S.box);
+    if (used) {
+        // the copies are dealt out over all warps - copy c goes to lane c / W of warp c % W (W warps per CTA): a warp's
+        // bulk-copy instruction is executed lane by lane (~65 cycles per copy, -DVL_TIMING), so 72 copies by the lanes of ONE
+        // warp kept that warp busy for a third of the tile's time while the other seven waited at the barrier
+        constexpr int NW = VL_FW * VL_FS / 32;
+        if (tid == 0) {
+            const uint32_t bytes = (copy_bg ? (uint32_t)(th * VL_FW * 3) : 0u) + (copy_box ? (uint32_t)(rec.bh * rec.bw * (int)sizeof(elem)) : 0u);
+            // earlier generic accesses (this CTA's reads of the buffers; with XCTA also the acquired global
+            // writes of other CTAs) are ordered before the async-proxy copies
+            if (XCTA) asm volatile("fence.proxy.async;" ::: "memory");
+            else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0), "r"(bytes) : "memory");
+        }
+        const int c0 = (tid & 31) * NW + (tid >> 5);                   // this thread's first copy; further ones 32 * NW apart
+        const int nbox = copy_box ? rec.bh : 0, nbg = copy_bg ? th : 0;
+        const uint32_t row_bytes = (uint32_t)(rec.bw * (int)sizeof(elem));
+        const elem *gb = src + (int64_t)rec.rmin * w + rec.cmin;
+        const uint8_t *gg = bgf + ((int64_t)I0 * w + J0) * 3;
+        for (int c = c0; c < nbox + nbg; c += 32 * NW) {
+            if (c < nbox) vl_bulk_g2s(vl_smem_u32(boxp + c * rec.bw), gb + (int64_t)c * w, row_bytes, bar0);
+            else { const int r = c - nbox; vl_bulk_g2s(vl_smem_u32(S.bgt + r * (VL_FW * 3)), gg + (int64_t)r * w * 3, VL_FW * 3, bar0); }
+        }
+    }
+
     const int kr0 = rf.i0, kr1 = max(rl.i1, rl.i0);
     const int nkr = kr1 - kr0 + 1;
     const int kc0 = cf.i0, kc1 = max(cl.i1, cl.i0);
@@ -679,41 +710,14 @@ __device__ __forceinline__ void vl_fine_tile(VlFineSmem &S, uint32_t &phase, con
     const bool active = (int)threadIdx.x < tw && nrows > 0;
 
     if (!all_staged) {                                                  // generic axis tables: everything from global memory
+        vl_cta_wait(bar0, tid < 32 && used, used, phase);                  // (the copies are in flight: they land before the CTA moves on)
+        if (used) phase ^= 1u;
         if (active) vl_strip_generic<SRC>(src, Tf + ce.i0, Tf + ce.i1, ny, rows + I0 + strip0, ce.frac, bgp, op, nrows, h, w, &outside);
         if (tid == 0) ++slow;
         return;
     }
 
     // ---- P1: bulk async copies (TMA): background rows + source box, all on one mbarrier -------
-    const bool bg_sm = tw == VL_FW && (w & 15) == 0 && (reinterpret_cast<uintptr_t>(bg) & 15) == 0;
-    const bool boxed = rec.bw > 0 && (reinterpret_cast<uintptr_t>(src_all) & 15) == 0;
-    const bool copy_box = boxed && !VL_ABL(1), copy_bg = bg_sm && !VL_ABL(2);
-    const bool used = copy_bg || copy_box;
-    elem *boxp = reinterpret_cast<elem *>(S.box);
-    if (used) {
-        // the copies are dealt out over all warps - copy c goes to lane c / W of warp c % W (W warps per CTA): a warp's
-        // bulk-copy instruction is executed lane by lane (~65 cycles per copy, -DVL_TIMING), so 72 copies by the lanes of ONE
-        // warp kept that warp busy for a third of the tile's time while the other seven waited at the barrier
-        constexpr int NW = VL_FW * VL_FS / 32;
-        if (tid == 0) {
-            const uint32_t bytes = (copy_bg ? (uint32_t)(th * VL_FW * 3) : 0u) + (copy_box ? (uint32_t)(rec.bh * rec.bw * (int)sizeof(elem)) : 0u);
-            // earlier generic accesses (this CTA's reads of the buffers; with XCTA also the acquired global
-            // writes of other CTAs) are ordered before the async-proxy copies
-            if (XCTA) asm volatile("fence.proxy.async;" ::: "memory");
-            else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0), "r"(bytes) : "memory");
-        }
-        const int c0 = (tid & 31) * NW + (tid >> 5);                   // this thread's first copy; further ones 32 * NW apart
-        const int nbox = copy_box ? rec.bh : 0, nbg = copy_bg ? th : 0;
-        const uint32_t row_bytes = (uint32_t)(rec.bw * (int)sizeof(elem));
-        const elem *gb = src + (int64_t)rec.rmin * w + rec.cmin;
-        const uint8_t *gg = bgf + ((int64_t)I0 * w + J0) * 3;
-        for (int c = c0; c < nbox + nbg; c += 32 * NW) {
-            if (c < nbox) vl_bulk_g2s(vl_smem_u32(boxp + c * rec.bw), gb + (int64_t)c * w, row_bytes, bar0);
-            else { const int r = c - nbox; vl_bulk_g2s(vl_smem_u32(S.bgt + r * (VL_FW * 3)), gg + (int64_t)r * w * 3, VL_FW * 3, bar0); }
-        }
-    }
-
     VL_T(1);                                                            // P1: issue of the bulk copies (warp 0)
     // ---- P2: column-interpolated coarse rows; thread (jc, strip) takes rows strip, strip + VL_FS, ...
     {
