@@ -521,19 +521,21 @@ __device__ __noinline__ void vl_strip_generic(const typename VlSrc<SRC>::elem *_
 // one warp polls the mbarrier (phase 0), the CTA barrier releases everybody else without spinning;
 // every thread then observes the completed phase itself (one try_wait that succeeds at once), which is
 // what orders the async-proxy writes of the bulk copies before its own shared-memory reads
-__device__ __forceinline__ void vl_cta_wait(uint32_t bar, bool poll, bool used, uint32_t parity) {
+// `vote`: the CTA barrier doubles as an AND-vote (returned)
+__device__ __forceinline__ bool vl_cta_wait(uint32_t bar, bool poll, bool used, uint32_t parity, bool vote = true) {
     uint32_t ok = 0;
     if (poll) {
         while (!ok)
             asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                          : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     }
-    __syncthreads();
+    const bool all = __syncthreads_and(vote);
     if (used && !poll) {
         while (!ok)
             asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                          : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     }
+    return all;
 }
 
 
@@ -699,8 +701,7 @@ __device__ __forceinline__ void vl_fine_tile(VlFineSmem &S, uint32_t &phase, con
         }
     }
     if (tid < th) S.rows[tid] = myrow;
-    const bool all_staged = __syncthreads_and(row_ok && win_ok);         // (also publishes S.rows)
-    VL_T(0);                                                            // P0: set-up, axis entries, one CTA barrier
+    VL_T(0);                                                            // P0: set-up, axis entries, bulk-copy issue, transform requests
 
     const int strip0 = threadIdx.y * rpt;                               // first row of the strip inside the CTA
     const int nrows = min(rpt, th - strip0);
@@ -709,18 +710,8 @@ __device__ __forceinline__ void vl_fine_tile(VlFineSmem &S, uint32_t &phase, con
     float4 *op = out + fbase + p0;
     const bool active = (int)threadIdx.x < tw && nrows > 0;
 
-    if (!all_staged) {                                                  // generic axis tables: everything from global memory
-        vl_cta_wait(bar0, tid < 32 && used, used, phase);                  // (the copies are in flight: they land before the CTA moves on)
-        if (used) phase ^= 1u;
-        if (active) vl_strip_generic<SRC>(src, Tf + ce.i0, Tf + ce.i1, ny, rows + I0 + strip0, ce.frac, bgp, op, nrows, h, w, &outside);
-        if (tid == 0) ++slow;
-        return;
-    }
-
-    // ---- P1: bulk async copies (TMA): background rows + source box, all on one mbarrier -------
-    VL_T(1);                                                            // P1: issue of the bulk copies (warp 0)
     // ---- P2: column-interpolated coarse rows; thread (jc, strip) takes rows strip, strip + VL_FS, ...
-    {
+    if (win_ok) {
         const double yf = ce.frac, y1 = 1.0 - yf;
 #pragma unroll
         for (int u = 0; u < KMAX; ++u) {
@@ -732,9 +723,17 @@ __device__ __forceinline__ void vl_fine_tile(VlFineSmem &S, uint32_t &phase, con
         }
     }
     VL_T(2);                                                            // P2: transform window -> Cs
-    vl_cta_wait(bar0, tid < 32 && used, used, phase);
+    // one CTA barrier for three things: the bulk copies have landed, Cs / S.rows are published, and the vote whether every
+    // thread found its axis entries inside the staged windows
+    const bool all_staged = vl_cta_wait(bar0, tid < 32 && used, used, phase, row_ok && win_ok);
     if (used) phase ^= 1u;
     VL_T(3);                                                            // wait for the bulk copies + CTA barrier
+
+    if (!all_staged) {                                                  // generic axis tables: everything from global memory
+        if (active) vl_strip_generic<SRC>(src, Tf + ce.i0, Tf + ce.i1, ny, rows + I0 + strip0, ce.frac, bgp, op, nrows, h, w, &outside);
+        if (tid == 0) ++slow;
+        return;
+    }
 
     const unsigned char *bgl = S.bgt + (strip0 * VL_FW + (int)threadIdx.x) * 3;
     const double2 *Csj = S.Cs + threadIdx.x;
