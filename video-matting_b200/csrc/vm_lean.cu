@@ -635,12 +635,19 @@ __device__ __forceinline__ void vl_fine_tile(VlFineSmem &S, uint32_t &phase, con
     const int tw = min(VL_FW, w - J0), th = min(VL_FS * rpt, h - I0);
     const int jc = min((int)threadIdx.x, tw - 1), j = J0 + jc;
     const uint32_t bar0 = vl_smem_u32(&S.bar[0]);
-    const int64_t fbase = (int64_t)frame * h * w;
+    // frame offsets as ONE 32 x 32 -> 64 multiply each (h * w < 2^28 and frame < 2^16 are checked on the host)
+    const uint32_t hw = (uint32_t)h * (uint32_t)w;
+    const int64_t fbase = (int64_t)((uint64_t)(uint32_t)frame * hw);
     const elem *src = reinterpret_cast<const elem *>(src_all) + fbase;
-    int bgi = frame0 + frame;
-    if (bgi >= n_bg) bgi %= n_bg;
-    const uint8_t *bgf = bg + (int64_t)bgi * h * w * 3;
-    const double2 *Tf = T + (int64_t)frame * nx * ny;
+    // background index (frame0 + frame) mod n_bg without an integer division: float estimate of the quotient + one correction
+    uint32_t bgi = (uint32_t)(frame0 + frame);
+    if (bgi >= (uint32_t)n_bg) {
+        const uint32_t q = (uint32_t)__fmul_rz(__uint2float_rz(bgi), __frcp_rz(__uint2float_ru((uint32_t)n_bg)));   // <= true quotient, at most 1 short (operands < 2^24)
+        bgi -= q * (uint32_t)n_bg;
+        if (bgi >= (uint32_t)n_bg) bgi -= (uint32_t)n_bg;
+    }
+    const uint8_t *bgf = bg + (int64_t)((uint64_t)bgi * (hw * 3u));
+    const double2 *Tf = T + (int64_t)((uint64_t)(uint32_t)frame * ((uint32_t)nx * (uint32_t)ny));
 
     // ---- P0: axis entries.  Every load of the prologue that does not depend on another one is issued here, before the
     // first use: the column entry of the thread, the first / last column and row entries of the tile (they give the coarse
@@ -673,11 +680,11 @@ __device__ __forceinline__ void vl_fine_tile(VlFineSmem &S, uint32_t &phase, con
         const int c0 = (tid & 31) * NW + (tid >> 5);                   // this thread's first copy; further ones 32 * NW apart
         const int nbox = copy_box ? rec.bh : 0, nbg = copy_bg ? th : 0;
         const uint32_t row_bytes = (uint32_t)(rec.bw * (int)sizeof(elem));
-        const elem *gb = src + (int64_t)rec.rmin * w + rec.cmin;
-        const uint8_t *gg = bgf + ((int64_t)I0 * w + J0) * 3;
+        const elem *gb = src + ((uint32_t)rec.rmin * (uint32_t)w + (uint32_t)rec.cmin);
+        const uint8_t *gg = bgf + ((uint32_t)I0 * (uint32_t)w + (uint32_t)J0) * 3u;
         for (int c = c0; c < nbox + nbg; c += 32 * NW) {
-            if (c < nbox) vl_bulk_g2s(vl_smem_u32(boxp + c * rec.bw), gb + (int64_t)c * w, row_bytes, bar0);
-            else { const int r = c - nbox; vl_bulk_g2s(vl_smem_u32(S.bgt + r * (VL_FW * 3)), gg + (int64_t)r * w * 3, VL_FW * 3, bar0); }
+            if (c < nbox) vl_bulk_g2s(vl_smem_u32(boxp + c * rec.bw), gb + (uint32_t)c * (uint32_t)w, row_bytes, bar0);
+            else { const int r = c - nbox; vl_bulk_g2s(vl_smem_u32(S.bgt + r * (VL_FW * 3)), gg + (uint32_t)r * (uint32_t)(w * 3), VL_FW * 3, bar0); }
         }
     }
 
@@ -697,7 +704,8 @@ __device__ __forceinline__ void vl_fine_tile(VlFineSmem &S, uint32_t &phase, con
 #pragma unroll
         for (int u = 0; u < KMAX; ++u) {
             const int k = min((int)threadIdx.y + u * VL_FS, nkr - 1);
-            ta[u] = __ldg(Ta + k * ny); tb[u] = __ldg(Tb + k * ny);
+            const uint32_t o = (uint32_t)k * (uint32_t)ny;
+            ta[u] = __ldg(Ta + o); tb[u] = __ldg(Tb + o);
         }
     }
     if (tid < th) S.rows[tid] = myrow;
@@ -773,7 +781,7 @@ k_lean_fine(const void *__restrict__ src_all, const uint8_t *__restrict__ bg, in
             float4 *__restrict__ out, int32_t *__restrict__ status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     VlFineSmem &S = *reinterpret_cast<VlFineSmem *>(smem_raw);
-    const VlTileBox rec = boxes[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x];
+    const VlTileBox rec = boxes[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x];     // < 2^31 tiles per launch
     vl_bar_init(S);
     uint32_t phase = 0;
     int outside = 0, slow = 0;
