@@ -21,7 +21,7 @@ fg, fb, ff, bg = bench.make_clip(torch, 1234, n, H, W, dev)
 ctrl, coef = P.solve_grids(bench.make_grids(vm, 1, n, H, W), dev)
 out = torch.empty((n, H, W, 4), dtype=torch.float32, device=dev)
 ref = None
-DEFAULTS = {"fused_variant": P.DEFAULT_VARIANT, "flow_stage_layout": 0, "lean_minb": 4, "lean_fine_rows": 8}
+DEFAULTS = {"fused_variant": P.DEFAULT_VARIANT, "flow_stage_layout": 0, "lean_minb": 4, "lean_fine_rows": 8, "lean_tmap": 1}
 names = ["spline", "boxes", "flow", "resample"]
 iters = int(os.environ.get("VM_ITERS", 10))
 for arg in sys.argv[1:] or [""]:

@@ -18,6 +18,7 @@
 // fixed point (2^-30 weights), with an exact float64 re-evaluation of the rare samples whose
 // rounding the fixed-point value cannot decide.
 #include "vm_lean.cuh"
+#include <cuda.h>
 #include <string.h>
 #include <atomic>
 #include <mutex>
@@ -43,6 +44,7 @@ int g_vl_sub = 0;            // frames per flow-stage / resampling sub-round ins
 int g_vl_box_cap = 0;        // source-box entries per B2 tile (0: as many as the occupancy target allows)
 int g_vl_floors = 1;         // 1: the spline stage also writes packed int16 floors of T for the tile-box stage
 int g_vl_minb = 4;           // B2 occupancy target (CTAs of 256 threads per SM: 2, 3 or 4)
+int g_vl_tmap = 1;           // B2 staging: 1 = two tensor bulk copies per tile (when available), 0 = one bulk copy per row
 int g_va_minb = 12;          // k_aug_tps: CTAs of 128 threads per SM: 12 (40 registers, 60 bytes of spills, 48 warps per SM) measured 4.22 ms per
                              // augment_clip call of 64 x 1080p against 4.32-4.47 at 8 (64 registers), 4.33 at 10, 4.76 at 16: the gathers want warps
 
@@ -420,13 +422,29 @@ static int vl_launch_coarse(const double *ctrl, const double *coef, int N, int n
 #define VL_TR (VL_FROWS_MAX / 2 + 4)               // coarse rows staged per CTA (20)
 #define VL_BOX_MAX 5632                            // source-box entries staged per CTA (8 B each)
 
-struct __align__(16) VlFineSmem {
+struct __align__(128) VlFineSmem {                 // (128: destination alignment of tensor bulk copies - Cs, bgt and box qualify)
     double2 Cs[VL_TR * VL_FW];                     // coarse rows interpolated at the tile's fine columns
     unsigned char bgt[VL_FROWS_MAX * VL_FW * 3];
     vm_axis_entry rows[VL_FROWS_MAX];
     unsigned long long bar[2];
-    uint2 box[1];                                  // box_cap entries (dynamic): source rows [rmin, rmin + bh) x [cmin, cmin + bw)
+    alignas(128) uint2 box[1];                     // box_cap entries (dynamic): source rows [rmin, rmin + bh) x [cmin, cmin + bw)
 };
+
+// Tensor-map staging (default when the driver provides cuTensorMapEncodeTiled and the planes qualify): the source box of a
+// tile and its background rows arrive through TWO tensor bulk copies issued by one thread instead of one 1-D bulk copy per
+// row (~72 per tile).  A bulk-copy instruction is executed lane by lane (operands through uniform registers: 8 issue slots
+// per copy, 10 % of the kernel's instructions in the ncu source view) and the TMA unit takes ~35 cycles per small copy.  A
+// tensor copy moves a box of FIXED size, so the tile-box stage picks, per tile, the first of VL_NSHAPE shapes that holds the
+// tile's bounding box (bw x bh entries <= the shared-memory budget); taps outside the frame are zero-filled by the hardware
+// and never read.
+#define VL_NSHAPE 6
+struct alignas(64) VlTmaps {
+    CUtensorMap box[VL_NSHAPE];                    // (frames, h, w) elements of the source, box {bw[s], bh[s], 1}
+    CUtensorMap bg;                                // (n_bg, h, 3 w) bytes, box {3 VL_FW, VL_FROWS_MAX, 1}
+    int bw[VL_NSHAPE], bh[VL_NSHAPE];
+    int on;                                        // 0: one bulk copy per row (fallback)
+};
+struct VlShapes { int bw[VL_NSHAPE], bh[VL_NSHAPE], on; };
 static inline size_t vl_fine_smem_bytes(int box_cap) { return sizeof(VlFineSmem) + (size_t)(box_cap - 1) * sizeof(uint2); }
 
 // per-tile record written by k_lean_boxes: source box of the tile (bw = 0: does not fit / not usable)
@@ -546,7 +564,7 @@ template <int SRC>
 __global__ void __launch_bounds__(128)
 k_lean_boxes(const double2 *__restrict__ T, const int *__restrict__ F, int nx, int ny, const vm_axis_entry *__restrict__ rows,
              const vm_axis_entry *__restrict__ cols, int h, int w, int rpt, int tiles_x, int tiles_y, int n_tiles,
-             int box_cap, VlTileBox *__restrict__ boxes) {
+             int box_cap, VlTileBox *__restrict__ boxes, const VlShapes shapes) {
     constexpr int EPV = 16 / (int)sizeof(typename VlSrc<SRC>::elem);
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -607,7 +625,13 @@ k_lean_boxes(const double2 *__restrict__ T, const int *__restrict__ F, int nx, i
         const int bh = rmax - rmin + 1;
         const int bw = (cmax - cmin + 1 + EPV - 1) & ~(EPV - 1);
         if (cmin + bw > w) cmin = w - bw;
-        if (!bad && bh >= 1 && bw >= EPV && cmin >= 0 && (w & (EPV - 1)) == 0 && bh * bw <= box_cap) {
+        if (shapes.on) {                                                 // tensor copies: the first fixed shape that holds the box
+            if (!bad && bh >= 1 && bw >= 1 && cmin >= 0) {
+#pragma unroll
+                for (int s = VL_NSHAPE - 1; s >= 0; --s)
+                    if (bw <= shapes.bw[s] && bh <= shapes.bh[s]) { rec.rmin = rmin; rec.bh = shapes.bh[s]; rec.cmin = cmin; rec.bw = shapes.bw[s]; }
+            }
+        } else if (!bad && bh >= 1 && bw >= EPV && cmin >= 0 && (w & (EPV - 1)) == 0 && bh * bw <= box_cap) {
             rec.rmin = rmin; rec.bh = bh; rec.cmin = cmin; rec.bw = bw;
         }
     }
@@ -618,7 +642,7 @@ k_lean_boxes(const double2 *__restrict__ T, const int *__restrict__ F, int nx, i
 // CTA.  S.bar[0] must have been initialised (count 1); `phase` is its current parity and is toggled when
 // the tile used it, so the function can be called for tile after tile by a persistent CTA.
 template <int SRC, bool XCTA>      // XCTA: the source was written by other CTAs of the same kernel (full proxy fence)
-__device__ __forceinline__ void vl_fine_tile(VlFineSmem &S, uint32_t &phase, const void *__restrict__ src_all,
+__device__ __forceinline__ void vl_fine_tile(VlFineSmem &S, const VlTmaps &tm, uint32_t &phase, const void *__restrict__ src_all,
                                              const uint8_t *__restrict__ bg, int n_bg, int frame0,
                                              const double2 *__restrict__ T, int nx, int ny,
                                              const vm_axis_entry *__restrict__ rows, const vm_axis_entry *__restrict__ cols,
@@ -664,7 +688,24 @@ __device__ __forceinline__ void vl_fine_tile(VlFineSmem &S, uint32_t &phase, con
     const bool copy_box = boxed && !VL_ABL(1), copy_bg = bg_sm && !VL_ABL(2);
     const bool used = copy_bg || copy_box;
     elem *boxp = reinterpret_cast<elem *>(S.box);
-    if (used) {
+    if (used && tm.on) {
+        if (tid == 0) {                                                 // two tensor copies: the source box, the background rows
+            const uint32_t bytes = (copy_bg ? (uint32_t)(VL_FROWS_MAX * VL_FW * 3) : 0u) + (copy_box ? (uint32_t)(rec.bh * rec.bw * (int)sizeof(elem)) : 0u);
+            if (XCTA) asm volatile("fence.proxy.async;" ::: "memory");
+            else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0), "r"(bytes) : "memory");
+            if (copy_box) {
+                int sidx = 0;
+#pragma unroll
+                for (int q = 1; q < VL_NSHAPE; ++q) if (tm.bw[q] == rec.bw && tm.bh[q] == rec.bh) sidx = q;
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                             ::"r"(vl_smem_u32(boxp)), "l"(reinterpret_cast<uint64_t>(&tm.box[sidx])), "r"(rec.cmin), "r"(rec.rmin), "r"(frame), "r"(bar0) : "memory");
+            }
+            if (copy_bg)
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                             ::"r"(vl_smem_u32(S.bgt)), "l"(reinterpret_cast<uint64_t>(&tm.bg)), "r"(J0 * 3), "r"(I0), "r"((int)bgi), "r"(bar0) : "memory");
+        }
+    } else if (used) {
         // the copies are dealt out over all warps - copy c goes to lane c / W of warp c % W (W warps per CTA): a warp's
         // bulk-copy instruction is executed lane by lane (~65 cycles per copy, -DVL_TIMING), so 72 copies by the lanes of ONE
         // warp kept that warp busy for a third of the tile's time while the other seven waited at the barrier
@@ -778,14 +819,14 @@ __global__ void __launch_bounds__(VL_FW * VL_FS, MINB)
 k_lean_fine(const void *__restrict__ src_all, const uint8_t *__restrict__ bg, int n_bg, int frame0,
             const double2 *__restrict__ T, int nx, int ny, const vm_axis_entry *__restrict__ rows,
             const vm_axis_entry *__restrict__ cols, int h, int w, int rpt, const VlTileBox *__restrict__ boxes,
-            float4 *__restrict__ out, int32_t *__restrict__ status) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+            float4 *__restrict__ out, int32_t *__restrict__ status, const __grid_constant__ VlTmaps tm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     VlFineSmem &S = *reinterpret_cast<VlFineSmem *>(smem_raw);
     const VlTileBox rec = boxes[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x];     // < 2^31 tiles per launch
     vl_bar_init(S);
     uint32_t phase = 0;
     int outside = 0, slow = 0;
-    vl_fine_tile<SRC, false>(S, phase, src_all, bg, n_bg, frame0, T, nx, ny, rows, cols, h, w, rpt, rec, blockIdx.z, blockIdx.y, blockIdx.x,
+    vl_fine_tile<SRC, false>(S, tm, phase, src_all, bg, n_bg, frame0, T, nx, ny, rows, cols, h, w, rpt, rec, blockIdx.z, blockIdx.y, blockIdx.x,
                       out, outside, slow);
     if (status) {
         if (outside & (VL_NEAR_KNIFE_UNIT - 1)) atomicAdd(status + VM_STATUS_TPS_OUTSIDE, outside & (VL_NEAR_KNIFE_UNIT - 1));
@@ -836,6 +877,7 @@ int vm_lean_set_option(const char *key, int value) {
     if (!strcmp(key, "lean_fine_rows") && value >= 1 && value <= 256) { g_vl_fine_rows = value; return VM_OK; }
     if (!strcmp(key, "lean_floors") && (value == 0 || value == 1)) { g_vl_floors = value; return VM_OK; }
     if (!strcmp(key, "lean_b1_ctas") && value >= 0 && value <= 4096) { g_vl_b1_ctas = value; return VM_OK; }
+    if (!strcmp(key, "lean_tmap") && (value == 0 || value == 1)) { g_vl_tmap = value; return VM_OK; }
 #ifdef VL_TIMING
     if (!strcmp(key, "lean_abl") && value >= 0 && value < 16) return cudaMemcpyToSymbol(c_vl_abl, &value, sizeof(int)) == cudaSuccess ? VM_OK : VM_ERR_CUDA;
 #endif
@@ -854,8 +896,42 @@ struct VlCall {
     float *out;
     int32_t *status;
     size_t fine_smem;
+    VlShapes shapes;                                 // fixed box shapes of the tensor-map staging (on = 0: one bulk copy per row)
     const char *what;
 };
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*VlEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static VlEncodeTiled vl_encode_tiled() {
+    static std::mutex mu;
+    static bool tried = false;
+    static VlEncodeTiled fn = nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!tried) {
+        tried = true;
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<VlEncodeTiled>(f);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+// (d2, d1, d0) tensor of `esize`-byte elements, innermost dimension d0, box {b0, b1, 1}
+static bool vl_encode3(CUtensorMap *tm, const void *base, int esize, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1) {
+    VlEncodeTiled enc = vl_encode_tiled();
+    if (!enc) return false;
+    const CUtensorMapDataType dt = esize == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : (esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
+    const cuuint64_t dims[3] = {d0, d1, d2};
+    const cuuint64_t strides[2] = {d0 * (uint64_t)esize, d0 * d1 * (uint64_t)esize};
+    const cuuint32_t box[3] = {b0, b1, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(tm, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 // spline on the coarse grid of frames [f0, f0 + m) into slot `sl`
 static int *vl_floors_ptr(const VlCall &c, const VlSlot &sl, bool floors_in_packed) {
@@ -871,8 +947,8 @@ static int vl_enqueue_boxes(const VlCall &c, const VlSlot &sl, int m, bool floor
     int *F = vl_floors_ptr(c, sl, floors_in_packed);
     const dim3 grid((c.w + VL_FW - 1) / VL_FW, (c.h + VL_FS * c.rpt - 1) / (VL_FS * c.rpt), m);
     const int n_tiles = (int)(grid.x * grid.y * m);
-    if (c.mode != 0) k_lean_boxes<1><<<(n_tiles + 3) / 4, 128, 0, st>>>(sl.T, F, c.nx, c.ny, c.rows, c.cols, c.h, c.w, c.rpt, grid.x, grid.y, n_tiles, c.box_cap, sl.boxes);
-    else             k_lean_boxes<0><<<(n_tiles + 3) / 4, 128, 0, st>>>(sl.T, F, c.nx, c.ny, c.rows, c.cols, c.h, c.w, c.rpt, grid.x, grid.y, n_tiles, c.box_cap, sl.boxes);
+    if (c.mode != 0) k_lean_boxes<1><<<(n_tiles + 3) / 4, 128, 0, st>>>(sl.T, F, c.nx, c.ny, c.rows, c.cols, c.h, c.w, c.rpt, grid.x, grid.y, n_tiles, c.box_cap, sl.boxes, c.shapes);
+    else             k_lean_boxes<0><<<(n_tiles + 3) / 4, 128, 0, st>>>(sl.T, F, c.nx, c.ny, c.rows, c.cols, c.h, c.w, c.rpt, grid.x, grid.y, n_tiles, c.box_cap, sl.boxes, c.shapes);
     g_vl_launches += 1;
     return vm_check_launch("vm_lean box stage");
 }
@@ -896,6 +972,18 @@ static int vl_enqueue_fine(const VlCall &c, const VlSlot &sl, int f0, int fs, in
     float4 *o4 = reinterpret_cast<float4 *>(c.out) + f0 * px;
     const void *src = c.mode != 0 ? (const void *)(reinterpret_cast<const uint2 *>(sl.packed) + fs * px) : (const void *)(c.fg + f0 * px * 4);
     const size_t fine_smem = c.fine_smem;
+    VlTmaps tm;
+    memset(&tm, 0, sizeof(tm));
+    if (c.shapes.on) {
+        const int esize = c.mode != 0 ? 8 : 4;
+        bool ok = vl_encode3(&tm.bg, c.bg, 1, (uint64_t)c.w * 3, (uint64_t)c.h, (uint64_t)c.n_bg, VL_FW * 3, VL_FROWS_MAX);
+        for (int q = 0; q < VL_NSHAPE && ok; ++q) {
+            tm.bw[q] = c.shapes.bw[q]; tm.bh[q] = c.shapes.bh[q];
+            ok = vl_encode3(&tm.box[q], src, esize, (uint64_t)c.w, (uint64_t)c.h, (uint64_t)m, (uint32_t)tm.bw[q], (uint32_t)tm.bh[q]);
+        }
+        if (!ok) { vm_set_error("vm_lean: cuTensorMapEncodeTiled failed"); return VM_ERR_CUDA; }
+        tm.on = 1;
+    }
 #define VL_FINE(S, MB)                                                                                              \
     do {                                                                                                            \
         static size_t attr_set[64];                                                                                 \
@@ -904,7 +992,7 @@ static int vl_enqueue_fine(const VlCall &c, const VlSlot &sl, int f0, int fs, in
             if (e != cudaSuccess) { vm_set_error("vm_lean: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VM_ERR_CUDA; } \
             attr_set[dev & 63] = fine_smem;                                                                         \
         }                                                                                                           \
-        k_lean_fine<S, MB><<<sgrid, block, fine_smem, st>>>(src, c.bg, c.n_bg, f0, Ts, c.nx, c.ny, c.rows, c.cols, c.h, c.w, c.rpt, bs, o4, c.status); \
+        k_lean_fine<S, MB><<<sgrid, block, fine_smem, st>>>(src, c.bg, c.n_bg, f0, Ts, c.nx, c.ny, c.rows, c.cols, c.h, c.w, c.rpt, bs, o4, c.status, tm); \
     } while (0)
     if (c.mode != 0) { if (g_vl_minb == 8) VL_FINE(1, 8); else if (g_vl_minb == 6) VL_FINE(1, 6); else if (g_vl_minb == 5) VL_FINE(1, 5); else if (g_vl_minb == 4) VL_FINE(1, 4); else if (g_vl_minb == 3) VL_FINE(1, 3); else VL_FINE(1, 2); }
     else             { if (g_vl_minb == 8) VL_FINE(0, 8); else if (g_vl_minb == 6) VL_FINE(0, 6); else if (g_vl_minb == 5) VL_FINE(0, 5); else if (g_vl_minb == 4) VL_FINE(0, 4); else if (g_vl_minb == 3) VL_FINE(0, 3); else VL_FINE(0, 2); }
@@ -941,6 +1029,18 @@ int vm_lean_launch(int mode, const uint8_t *fg, const float *backward, const flo
         if (c.box_cap > 8192) c.box_cap = 8192;
     }
     c.fine_smem = vl_fine_smem_bytes(c.box_cap);
+    // tensor-map staging of the resampling stage: needs the driver entry point, 16-byte aligned planes / rows and boxes of <= 256
+    memset(&c.shapes, 0, sizeof(c.shapes));
+    if (g_vl_tmap && vl_encode_tiled() && (w & 15) == 0 && vm_aligned(bg, 16) && vm_aligned(fg, 16) && vm_aligned(scratch, 16)) {
+        static const int kBw[VL_NSHAPE] = {80, 72, 88, 64, 100, 116};       // (tried in this order: the common boxes first)
+        bool ok = true;
+        for (int q = 0; q < VL_NSHAPE; ++q) {
+            c.shapes.bw[q] = kBw[q];
+            c.shapes.bh[q] = c.box_cap / kBw[q] < 256 ? c.box_cap / kBw[q] : 256;
+            ok = ok && c.shapes.bh[q] >= 4;
+        }
+        c.shapes.on = ok ? 1 : 0;
+    }
     unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
