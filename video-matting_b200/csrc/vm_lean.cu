@@ -437,7 +437,7 @@ struct __align__(128) VlFineSmem {                 // (128: destination alignmen
 // tensor copy moves a box of FIXED size, so the tile-box stage picks, per tile, the first of VL_NSHAPE shapes that holds the
 // tile's bounding box (bw x bh entries <= the shared-memory budget); taps outside the frame are zero-filled by the hardware
 // and never read.
-#define VL_NSHAPE 6
+#define VL_NSHAPE 12
 struct alignas(64) VlTmaps {
     CUtensorMap box[VL_NSHAPE];                    // (frames, h, w) elements of the source, box {bw[s], bh[s], 1}
     CUtensorMap bg;                                // (n_bg, h, 3 w) bytes, box {3 VL_FW, VL_FROWS_MAX, 1}
@@ -1032,7 +1032,7 @@ int vm_lean_launch(int mode, const uint8_t *fg, const float *backward, const flo
     // tensor-map staging of the resampling stage: needs the driver entry point, 16-byte aligned planes / rows and boxes of <= 256
     memset(&c.shapes, 0, sizeof(c.shapes));
     if (g_vl_tmap && vl_encode_tiled() && (w & 15) == 0 && vm_aligned(bg, 16) && vm_aligned(fg, 16) && vm_aligned(scratch, 16)) {
-        static const int kBw[VL_NSHAPE] = {80, 72, 88, 64, 100, 116};       // (tried in this order: the common boxes first)
+        static const int kBw[VL_NSHAPE] = {80, 76, 84, 72, 88, 68, 92, 64, 96, 104, 112, 124};   // widths (multiples of 4), height = budget / width
         bool ok = true;
         for (int q = 0; q < VL_NSHAPE; ++q) {
             c.shapes.bw[q] = kBw[q];
