@@ -441,29 +441,50 @@ struct __align__(128) VlFineSmem {                 // (128: destination alignmen
 struct alignas(64) VlTmaps {
     CUtensorMap box[VL_NSHAPE];                    // (frames, h, w) elements of the source, box {bw[s], bh[s], 1}
     CUtensorMap bg;                                // (n_bg, h, 3 w) bytes, box {3 VL_FW, VL_FROWS_MAX, 1}
+    CUtensorMap T;                                 // (frames, nx, 2 ny) doubles, box {2 VL_TCP, VL_TR, 1}
     int bw[VL_NSHAPE], bh[VL_NSHAPE];
     int on;                                        // 0: one bulk copy per row (fallback)
 };
 struct VlShapes { int bw[VL_NSHAPE], bh[VL_NSHAPE], on; };
+#define VL_TCP 40                                  // columns of the raw coarse window in shared memory (>= VL_TC, 16-byte elements)
+struct __align__(128) VlFineSmemT {                // tensor-map kernel: the raw window instead of Cs leaves 8 KB more for the box
+    double2 Traw[VL_TR * VL_TCP];
+    unsigned char bgt[VL_FROWS_MAX * VL_FW * 3];
+    vm_axis_entry rows[VL_FROWS_MAX];
+    unsigned long long bar[2];
+    alignas(128) uint2 box[1];
+};
+static inline size_t vl_fine_smem_bytes_t(int box_cap) { return sizeof(VlFineSmemT) + (size_t)(box_cap - 1) * sizeof(uint2); }
 static inline size_t vl_fine_smem_bytes(int box_cap) { return sizeof(VlFineSmem) + (size_t)(box_cap - 1) * sizeof(uint2); }
 
 // per-tile record written by k_lean_boxes: source box of the tile (bw = 0: does not fit / not usable)
 struct __align__(16) VlTileBox { int rmin, bh, cmin, bw; };
 
 // ---- P4, tile path: Cs in shared memory; taps from the staged box (BOX) or from global memory ----
-template <int SRC, bool BOX, bool BGSM>
+// RAWT: Csj points at the thread's first column of the RAW coarse window (rows VL_TCP apart); the column interpolation
+// (weights y1, yf between the columns Csj[.] and Csj[. + dq]) is done here, per pixel, with the arithmetic of vl_col_lerp -
+// the same bits as the pre-interpolated Cs, which that variant does not have to build.
+template <int SRC, bool BOX, bool BGSM, bool RAWT = false>
 __device__ __forceinline__ void vl_strip_tile(const typename VlSrc<SRC>::elem *__restrict__ src,
                                               const typename VlSrc<SRC>::elem *__restrict__ box, int rmin, int cmin, int bw,
                                               const double2 *__restrict__ Csj, int kr0, const vm_axis_entry *__restrict__ rp,
                                               const unsigned char *__restrict__ bgl, const uint8_t *__restrict__ bgp,
-                                              float4 *__restrict__ op, int nrows, int h, int w, int *outside) {
+                                              float4 *__restrict__ op, int nrows, int h, int w, int *outside,
+                                              int dq = 0, double y1 = 0.0, double yf = 0.0) {
     typedef typename VlSrc<SRC>::elem elem;
     const int w3 = w * 3;
     constexpr int pitch = VL_FW * 3;
 #pragma unroll 2
     for (int i = 0; i < nrows; ++i) {
         const vm_axis_entry re = rp[i];
-        const double2 c0 = Csj[(re.i0 - kr0) * VL_FW], c1 = Csj[(re.i1 - kr0) * VL_FW];
+        double2 c0, c1;
+        if (RAWT) {
+            const double2 *r0 = Csj + (re.i0 - kr0) * VL_TCP, *r1 = Csj + (re.i1 - kr0) * VL_TCP;
+            const VlC u0 = vl_col_lerp(r0[0], r0[dq], y1, yf), u1 = vl_col_lerp(r1[0], r1[dq], y1, yf);
+            c0 = make_double2(u0.x, u0.y); c1 = make_double2(u1.x, u1.y);
+        } else {
+            c0 = Csj[(re.i0 - kr0) * VL_FW]; c1 = Csj[(re.i1 - kr0) * VL_FW];
+        }
         const double xf = re.frac, x1 = 1.0 - xf;
         const double t0 = fma(c1.x, xf, c0.x * x1), t1 = fma(c1.y, xf, c0.y * x1);
         int n0, n1;
@@ -835,6 +856,111 @@ k_lean_fine(const void *__restrict__ src_all, const uint8_t *__restrict__ bg, in
     }
 }
 
+// The resampling kernel with tensor-map staging.  Per tile: thread 0 reads the tile record and the first row / column
+// entries (which give the origin of the coarse window), then issues THREE tensor bulk copies on one mbarrier - the source
+// box, the background rows, the raw coarse window of the transform - and the CTA has ONE barrier before the pixel loop:
+// the copies have landed, the row entries are published, and the vote whether every thread's axis entries lie inside the
+// staged windows.  No Cs pass, no per-thread transform loads, no address arithmetic on 64-bit pointers in the prologue.
+template <int SRC, int MINB>
+__global__ void __launch_bounds__(VL_FW * VL_FS, MINB)
+k_lean_fine_tm(const void *__restrict__ src_all, const uint8_t *__restrict__ bg, int n_bg, int frame0,
+               const double2 *__restrict__ T, int nx, int ny, const vm_axis_entry *__restrict__ rows,
+               const vm_axis_entry *__restrict__ cols, int h, int w, int rpt, const VlTileBox *__restrict__ boxes,
+               float4 *__restrict__ out, int32_t *__restrict__ status, const __grid_constant__ VlTmaps tm) {
+    typedef typename VlSrc<SRC>::elem elem;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    VlFineSmemT &S = *reinterpret_cast<VlFineSmemT *>(smem_raw);
+    const int tid = threadIdx.y * VL_FW + threadIdx.x;
+    const int frame = blockIdx.z, by = blockIdx.y, bx = blockIdx.x;
+    const int J0 = bx * VL_FW, I0 = by * (VL_FS * rpt);
+    const int tw = min(VL_FW, w - J0), th = min(VL_FS * rpt, h - I0);
+    const int jc = min((int)threadIdx.x, tw - 1), j = J0 + jc;
+    const uint32_t bar0 = vl_smem_u32(&S.bar[0]);
+    // every load of the prologue is independent of the others and issued here
+    const VlTileBox rec = boxes[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x];
+    const vm_axis_entry rf = vm_ld_axis(rows + I0), rl = vm_ld_axis(rows + I0 + th - 1);
+    const vm_axis_entry cf = vm_ld_axis(cols + J0), cl = vm_ld_axis(cols + J0 + tw - 1);
+    const vm_axis_entry ce = vm_ld_axis(cols + j);
+    vm_axis_entry myrow = {0.0, 0, 0};
+    if (tid < th) myrow = vm_ld_axis(rows + I0 + tid);
+    const uint32_t hw = (uint32_t)h * (uint32_t)w;
+    const int64_t fbase = (int64_t)((uint64_t)(uint32_t)frame * hw);
+    const elem *src = reinterpret_cast<const elem *>(src_all) + fbase;
+    uint32_t bgi = (uint32_t)(frame0 + frame);
+    if (bgi >= (uint32_t)n_bg) {                                        // (frame0 + frame) mod n_bg without an integer division
+        const uint32_t q = (uint32_t)__fmul_rz(__uint2float_rz(bgi), __frcp_rz(__uint2float_ru((uint32_t)n_bg)));
+        bgi -= q * (uint32_t)n_bg;
+        if (bgi >= (uint32_t)n_bg) bgi -= (uint32_t)n_bg;
+    }
+    const uint8_t *bgf = bg + (int64_t)((uint64_t)bgi * (hw * 3u));
+    const double2 *Tf = T + (int64_t)((uint64_t)(uint32_t)frame * ((uint32_t)nx * (uint32_t)ny));
+    const int kr0 = rf.i0, kr1 = max(rl.i1, rl.i0), kc0 = cf.i0, kc1 = max(cl.i1, cl.i0);
+    const int nkr = kr1 - kr0 + 1, nkc = kc1 - kc0 + 1;
+    const bool bg_sm = tw == VL_FW;
+    const bool boxed = rec.bw > 0;
+    elem *boxp = reinterpret_cast<elem *>(S.box);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const uint32_t bytes = (uint32_t)(VL_TR * VL_TCP * 16) + (bg_sm ? (uint32_t)(VL_FROWS_MAX * VL_FW * 3) : 0u) +
+                               (boxed ? (uint32_t)(rec.bh * rec.bw * (int)sizeof(elem)) : 0u);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(vl_smem_u32(S.Traw)), "l"(reinterpret_cast<uint64_t>(&tm.T)), "r"(2 * kc0), "r"(kr0), "r"(frame), "r"(bar0) : "memory");
+        if (boxed) {
+            int sidx = 0;
+#pragma unroll
+            for (int q = 1; q < VL_NSHAPE; ++q) if (tm.bw[q] == rec.bw && tm.bh[q] == rec.bh) sidx = q;
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(vl_smem_u32(boxp)), "l"(reinterpret_cast<uint64_t>(&tm.box[sidx])), "r"(rec.cmin), "r"(rec.rmin), "r"(frame), "r"(bar0) : "memory");
+        }
+        if (bg_sm)
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(vl_smem_u32(S.bgt)), "l"(reinterpret_cast<uint64_t>(&tm.bg)), "r"(J0 * 3), "r"(I0), "r"((int)bgi), "r"(bar0) : "memory");
+    }
+    // every (i0, i1) of the tile's rows / columns must lie inside the staged window
+    const bool row_ok = tid >= th || (myrow.i0 >= kr0 && myrow.i0 <= kr1 && myrow.i1 >= kr0 && myrow.i1 <= kr1);
+    const bool win_ok = nkr >= 1 && nkr <= VL_TR && nkc >= 1 && nkc <= VL_TCP && kr0 >= 0 && kr1 < nx && kc0 >= 0 && kc1 < ny &&
+                        ce.i0 >= kc0 && ce.i0 <= kc1 && ce.i1 >= kc0 && ce.i1 <= kc1;
+    if (tid < th) S.rows[tid] = myrow;
+    const int strip0 = threadIdx.y * rpt;
+    const int nrows = min(rpt, th - strip0);
+    const uint32_t p0 = (uint32_t)(I0 + strip0) * (uint32_t)w + (uint32_t)j;
+    const uint8_t *bgp = bgf + p0 * 3u;
+    float4 *op = out + fbase + p0;
+    const bool active = (int)threadIdx.x < tw && nrows > 0;
+    // one CTA barrier: the copies have landed (warp 0 polls), S.rows is published, and the vote
+    if (tid < 32) {
+        __syncwarp();
+        vl_mbar_wait_parity(bar0, 0);
+    }
+    const bool all_staged = __syncthreads_and(row_ok && win_ok);
+    if (tid >= 32) vl_mbar_wait_parity(bar0, 0);                         // completed: one try_wait that orders the async-proxy writes
+    int outside = 0, slow = 0;
+    if (!all_staged) {                                                  // generic axis tables: everything from global memory
+        if (active) vl_strip_generic<SRC>(src, Tf + ce.i0, Tf + ce.i1, ny, rows + I0 + strip0, ce.frac, bgp, op, nrows, h, w, &outside);
+        if (tid == 0) ++slow;
+    } else {
+        if (!boxed && tid == 0) ++slow;
+        if (active) {
+            const unsigned char *bgl = S.bgt + (strip0 * VL_FW + (int)threadIdx.x) * 3;
+            const double2 *Tj = S.Traw + (ce.i0 - kc0);
+            const int dq = ce.i1 - ce.i0;
+            const double yf = ce.frac, y1 = 1.0 - yf;
+            const vm_axis_entry *rp = S.rows + strip0;
+            if (boxed && bg_sm) vl_strip_tile<SRC, true, true, true>(src, boxp, rec.rmin, rec.cmin, rec.bw, Tj, kr0, rp, bgl, bgp, op, nrows, h, w, &outside, dq, y1, yf);
+            else if (boxed)     vl_strip_tile<SRC, true, false, true>(src, boxp, rec.rmin, rec.cmin, rec.bw, Tj, kr0, rp, bgl, bgp, op, nrows, h, w, &outside, dq, y1, yf);
+            else                vl_strip_tile<SRC, false, false, true>(src, boxp, 0, 0, 0, Tj, kr0, rp, bgl, bgp, op, nrows, h, w, &outside, dq, y1, yf);
+        }
+    }
+    if (status) {
+        if (outside & (VL_NEAR_KNIFE_UNIT - 1)) atomicAdd(status + VM_STATUS_TPS_OUTSIDE, outside & (VL_NEAR_KNIFE_UNIT - 1));
+        if (outside >= VL_NEAR_KNIFE_UNIT) atomicAdd(status + VM_STATUS_NEAR_KNIFE, outside / VL_NEAR_KNIFE_UNIT);
+        if (slow) atomicAdd(status + VM_STATUS_SLOW_TILES, slow);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
@@ -981,9 +1107,27 @@ static int vl_enqueue_fine(const VlCall &c, const VlSlot &sl, int f0, int fs, in
             tm.bw[q] = c.shapes.bw[q]; tm.bh[q] = c.shapes.bh[q];
             ok = vl_encode3(&tm.box[q], src, esize, (uint64_t)c.w, (uint64_t)c.h, (uint64_t)m, (uint32_t)tm.bw[q], (uint32_t)tm.bh[q]);
         }
+        ok = ok && vl_encode3(&tm.T, Ts, 8, (uint64_t)c.ny * 2, (uint64_t)c.nx, (uint64_t)m, 2 * VL_TCP, VL_TR);
         if (!ok) { vm_set_error("vm_lean: cuTensorMapEncodeTiled failed"); return VM_ERR_CUDA; }
         tm.on = 1;
     }
+#define VL_FINE_TM(S, MB)                                                                                           \
+    do {                                                                                                            \
+        static size_t attr_set[64];                                                                                 \
+        if (attr_set[dev & 63] < fine_smem) {                                                                       \
+            cudaError_t e = cudaFuncSetAttribute(k_lean_fine_tm<S, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fine_smem); \
+            if (e != cudaSuccess) { vm_set_error("vm_lean: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VM_ERR_CUDA; } \
+            attr_set[dev & 63] = fine_smem;                                                                         \
+        }                                                                                                           \
+        k_lean_fine_tm<S, MB><<<sgrid, block, fine_smem, st>>>(src, c.bg, c.n_bg, f0, Ts, c.nx, c.ny, c.rows, c.cols, c.h, c.w, c.rpt, bs, o4, c.status, tm); \
+    } while (0)
+    if (tm.on) {
+        if (c.mode != 0) { if (g_vl_minb == 3) VL_FINE_TM(1, 3); else VL_FINE_TM(1, 4); }
+        else             { if (g_vl_minb == 3) VL_FINE_TM(0, 3); else VL_FINE_TM(0, 4); }
+        g_vl_launches += 1;
+        return vm_check_launch(c.what);
+    }
+#undef VL_FINE_TM
 #define VL_FINE(S, MB)                                                                                              \
     do {                                                                                                            \
         static size_t attr_set[64];                                                                                 \
@@ -1031,7 +1175,13 @@ int vm_lean_launch(int mode, const uint8_t *fg, const float *backward, const flo
     c.fine_smem = vl_fine_smem_bytes(c.box_cap);
     // tensor-map staging of the resampling stage: needs the driver entry point, 16-byte aligned planes / rows and boxes of <= 256
     memset(&c.shapes, 0, sizeof(c.shapes));
-    if (g_vl_tmap && vl_encode_tiled() && (w & 15) == 0 && vm_aligned(bg, 16) && vm_aligned(fg, 16) && vm_aligned(scratch, 16)) {
+    if (g_vl_tmap && (g_vl_minb == 3 || g_vl_minb == 4) && vl_encode_tiled() && (w & 15) == 0 && vm_aligned(bg, 16) && vm_aligned(fg, 16) &&
+        vm_aligned(scratch, 16)) {
+        if (g_vl_box_cap <= 0) {                                        // the raw transform window replaces Cs: more room for the box
+            const int64_t per_cta = (227 * 1024) / g_vl_minb - 1024 - (int64_t)sizeof(VlFineSmemT);
+            c.box_cap = (int)(per_cta / 8) & ~63;
+            if (c.box_cap > 8192) c.box_cap = 8192;
+        }
         static const int kBw[VL_NSHAPE] = {80, 76, 84, 72, 88, 68, 92, 64, 96, 104, 112, 124};   // widths (multiples of 4), height = budget / width
         bool ok = true;
         for (int q = 0; q < VL_NSHAPE; ++q) {
@@ -1040,6 +1190,12 @@ int vm_lean_launch(int mode, const uint8_t *fg, const float *backward, const flo
             ok = ok && c.shapes.bh[q] >= 4;
         }
         c.shapes.on = ok ? 1 : 0;
+        if (ok) c.fine_smem = vl_fine_smem_bytes_t(c.box_cap);
+        else if (g_vl_box_cap <= 0) {
+            const int64_t per_cta = (227 * 1024) / g_vl_minb - 1024 - (int64_t)sizeof(VlFineSmem);
+            c.box_cap = (int)(per_cta / 8) & ~63;
+            if (c.box_cap > 8192) c.box_cap = 8192;
+        }
     }
     unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
