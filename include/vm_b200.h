@@ -205,7 +205,7 @@ int vm_flow_tps_composite_bgra(const uint8_t *fg, const float *backward, const f
  * stage), 5 = single-pass warp-specialised kernel for the C4 entry point (no intermediate in HBM), 1 =
  * per-pixel gather kernels (generic fallback); "lean_chunk" frames per stage round (0 = automatic: about 64 frames of 1080p worth of pixels), "lean_sub", "lean_rb",
  * "lean_b1_warps", "lean_b1_dyr", "lean_b1_ctas", "lean_minb", "lean_fine_rows", "lean_box_cap", "lean_aug_minb",
- * "lean_floors", "flow_stage_layout": schedule parameters of variant 4; "fuse_ctas": persistent CTAs of
+ * "lean_floors", "flow_stage_layout", "lean_tmap" (1 = tensor-map staging of the resampling stage, the default when available; 0 = one bulk copy per row): schedule parameters of variant 4; "fuse_ctas": persistent CTAs of
  * variant 5; "lean_timing" 1 = record CUDA events around the stages of variant 4 (vm_lean_stage_ms).       */
 int vm_set_option(const char *key, int value);
 

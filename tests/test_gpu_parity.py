@@ -401,7 +401,8 @@ def _lean_case(h, w, n, n_ctrl, seed=300, stretch=1.0):
 def test_lean_partition_independent(vm, lean):
     """The result must not depend on how the work is cut: frames per stage round, coarse rows per
     spline unit, resampling occupancy target, and whether a tile's source box is staged in shared
-    memory (box capacity 64 entries forces every tile onto the global-gather path)."""
+    memory (box capacity 64 entries forces every tile onto the global-gather path), and whether the resampling stage
+    stages through tensor maps (k_lean_fine_tm, the default) or through one bulk copy per row (k_lean_fine)."""
     h, w, n = 200, 333 + 3, 5                       # w % 4 == 0 so that the box path is eligible
     P, Nt = vm.pipeline, vm._native
     frames, fb, ff, grids, bgs = _lean_case(h, w, n, 5)
@@ -412,8 +413,9 @@ def test_lean_partition_independent(vm, lean):
     assert int(st0[4]) < 4, "most tiles of a mild grid must take the shared-memory box path"
     defaults = {"lean_chunk": 0, "lean_rb": 0, "lean_minb": 4, "lean_box_cap": 0, "lean_fine_rows": 8, "lean_sub": 0,
                 "lean_b1_warps": 16, "lean_b1_dyr": 1, "flow_stage_layout": 0, "lean_floors": 1,
-                "lean_b1_ctas": 0}
-    configs = [{"lean_chunk": 1}, {"lean_chunk": 2}, {"lean_chunk": 3}, {"lean_rb": 4}, {"lean_rb": 16}, {"lean_rb": 32},
+                "lean_b1_ctas": 0, "lean_tmap": 1}
+    configs = [{"lean_tmap": 0}, {"lean_tmap": 0, "lean_box_cap": 64}, {"lean_box_cap": 512}, {"lean_tmap": 0, "lean_minb": 3},
+               {"lean_chunk": 1}, {"lean_chunk": 2}, {"lean_chunk": 3}, {"lean_rb": 4}, {"lean_rb": 16}, {"lean_rb": 32},
                {"lean_sub": 2}, {"lean_minb": 2}, {"lean_minb": 3}, {"lean_fine_rows": 3}, {"lean_fine_rows": 5},
                {"lean_box_cap": 64}, {"lean_b1_dyr": 0, "lean_b1_warps": 24}, {"lean_b1_warps": 6, "lean_b1_ctas": 40},
                {"flow_stage_layout": 1}, {"lean_floors": 0}, {"lean_floors": 0, "lean_box_cap": 64},
@@ -426,8 +428,8 @@ def test_lean_partition_independent(vm, lean):
             out3, _ = P.tps_composite(args[0], args[3], ctrl, coef)
             torch.cuda.synchronize()
             assert torch.equal(out, base) and torch.equal(out3, base3), f"{cfg} changes the result"
-            if cfg.get("lean_box_cap") == 64:
-                assert int(st[4]) > 0, "box capacity 64 must push tiles onto the gather path"
+            if cfg.get("lean_box_cap") in (64, 512):
+                assert int(st[4]) > 0, "a small box capacity must push tiles onto the gather path"
             if cfg == {"lean_floors": 0}:
                 assert int(st[4]) == int(st0[4]), "the packed floors must select the same tile boxes as T itself"
             for key in cfg:
