@@ -401,10 +401,10 @@ def kernel_stages(vm, lib, step, torch):
     traffic = load_traffic()
     names = traffic.get("kernels") or ["k_lean_coarse<25> (TPS on the coarse grid, float64)", "k_lean_boxes<1> (source box per tile)",
                                        "k_flow_warp_mask_bgra<1,2> (flow warp + consistency mask)",
-                                       "k_lean_fine<1,4> (resampling + composite)"]
+                                       "k_lean_fine_tm<1,4> (resampling + composite, tensor-map staging)"]
     info = {"kernel": traffic.get("kernel_note") or
-            "vm_flow_tps_composite_bgra = k_lean_coarse + k_lean_boxes + k_flow_warp_mask_bgra + k_lean_fine, timed as one unit "
-            "(39 B/px is defined for the whole pipeline); the dominant kernel is k_lean_fine, see stages", "stages": []}
+            "vm_flow_tps_composite_bgra = k_lean_coarse + k_lean_boxes + k_flow_warp_mask_bgra + k_lean_fine_tm, timed as one unit "
+            "(39 B/px is defined for the whole pipeline); the dominant kernel is k_lean_fine_tm, see stages", "stages": []}
     try:
         Nt.set_option("lean_timing", 1)
         rows = []
