@@ -663,7 +663,7 @@ k_lean_boxes(const double2 *__restrict__ T, const int *__restrict__ F, int nx, i
 // CTA.  S.bar[0] must have been initialised (count 1); `phase` is its current parity and is toggled when
 // the tile used it, so the function can be called for tile after tile by a persistent CTA.
 template <int SRC, bool XCTA>      // XCTA: the source was written by other CTAs of the same kernel (full proxy fence)
-__device__ __forceinline__ void vl_fine_tile(VlFineSmem &S, const VlTmaps &tm, uint32_t &phase, const void *__restrict__ src_all,
+__device__ __forceinline__ void vl_fine_tile(VlFineSmem &S, uint32_t &phase, const void *__restrict__ src_all,
                                              const uint8_t *__restrict__ bg, int n_bg, int frame0,
                                              const double2 *__restrict__ T, int nx, int ny,
                                              const vm_axis_entry *__restrict__ rows, const vm_axis_entry *__restrict__ cols,
@@ -709,24 +709,7 @@ __device__ __forceinline__ void vl_fine_tile(VlFineSmem &S, const VlTmaps &tm, u
     const bool copy_box = boxed && !VL_ABL(1), copy_bg = bg_sm && !VL_ABL(2);
     const bool used = copy_bg || copy_box;
     elem *boxp = reinterpret_cast<elem *>(S.box);
-    if (used && tm.on) {
-        if (tid == 0) {                                                 // two tensor copies: the source box, the background rows
-            const uint32_t bytes = (copy_bg ? (uint32_t)(VL_FROWS_MAX * VL_FW * 3) : 0u) + (copy_box ? (uint32_t)(rec.bh * rec.bw * (int)sizeof(elem)) : 0u);
-            if (XCTA) asm volatile("fence.proxy.async;" ::: "memory");
-            else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0), "r"(bytes) : "memory");
-            if (copy_box) {
-                int sidx = 0;
-#pragma unroll
-                for (int q = 1; q < VL_NSHAPE; ++q) if (tm.bw[q] == rec.bw && tm.bh[q] == rec.bh) sidx = q;
-                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                             ::"r"(vl_smem_u32(boxp)), "l"(reinterpret_cast<uint64_t>(&tm.box[sidx])), "r"(rec.cmin), "r"(rec.rmin), "r"(frame), "r"(bar0) : "memory");
-            }
-            if (copy_bg)
-                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                             ::"r"(vl_smem_u32(S.bgt)), "l"(reinterpret_cast<uint64_t>(&tm.bg)), "r"(J0 * 3), "r"(I0), "r"((int)bgi), "r"(bar0) : "memory");
-        }
-    } else if (used) {
+    if (used) {
         // the copies are dealt out over all warps - copy c goes to lane c / W of warp c % W (W warps per CTA): a warp's
         // bulk-copy instruction is executed lane by lane (~65 cycles per copy, -DVL_TIMING), so 72 copies by the lanes of ONE
         // warp kept that warp busy for a third of the tile's time while the other seven waited at the barrier
@@ -840,14 +823,14 @@ __global__ void __launch_bounds__(VL_FW * VL_FS, MINB)
 k_lean_fine(const void *__restrict__ src_all, const uint8_t *__restrict__ bg, int n_bg, int frame0,
             const double2 *__restrict__ T, int nx, int ny, const vm_axis_entry *__restrict__ rows,
             const vm_axis_entry *__restrict__ cols, int h, int w, int rpt, const VlTileBox *__restrict__ boxes,
-            float4 *__restrict__ out, int32_t *__restrict__ status, const __grid_constant__ VlTmaps tm) {
+            float4 *__restrict__ out, int32_t *__restrict__ status) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     VlFineSmem &S = *reinterpret_cast<VlFineSmem *>(smem_raw);
     const VlTileBox rec = boxes[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x];     // < 2^31 tiles per launch
     vl_bar_init(S);
     uint32_t phase = 0;
     int outside = 0, slow = 0;
-    vl_fine_tile<SRC, false>(S, tm, phase, src_all, bg, n_bg, frame0, T, nx, ny, rows, cols, h, w, rpt, rec, blockIdx.z, blockIdx.y, blockIdx.x,
+    vl_fine_tile<SRC, false>(S, phase, src_all, bg, n_bg, frame0, T, nx, ny, rows, cols, h, w, rpt, rec, blockIdx.z, blockIdx.y, blockIdx.x,
                       out, outside, slow);
     if (status) {
         if (outside & (VL_NEAR_KNIFE_UNIT - 1)) atomicAdd(status + VM_STATUS_TPS_OUTSIDE, outside & (VL_NEAR_KNIFE_UNIT - 1));
@@ -1136,7 +1119,7 @@ static int vl_enqueue_fine(const VlCall &c, const VlSlot &sl, int f0, int fs, in
             if (e != cudaSuccess) { vm_set_error("vm_lean: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return VM_ERR_CUDA; } \
             attr_set[dev & 63] = fine_smem;                                                                         \
         }                                                                                                           \
-        k_lean_fine<S, MB><<<sgrid, block, fine_smem, st>>>(src, c.bg, c.n_bg, f0, Ts, c.nx, c.ny, c.rows, c.cols, c.h, c.w, c.rpt, bs, o4, c.status, tm); \
+        k_lean_fine<S, MB><<<sgrid, block, fine_smem, st>>>(src, c.bg, c.n_bg, f0, Ts, c.nx, c.ny, c.rows, c.cols, c.h, c.w, c.rpt, bs, o4, c.status); \
     } while (0)
     if (c.mode != 0) { if (g_vl_minb == 8) VL_FINE(1, 8); else if (g_vl_minb == 6) VL_FINE(1, 6); else if (g_vl_minb == 5) VL_FINE(1, 5); else if (g_vl_minb == 4) VL_FINE(1, 4); else if (g_vl_minb == 3) VL_FINE(1, 3); else VL_FINE(1, 2); }
     else             { if (g_vl_minb == 8) VL_FINE(0, 8); else if (g_vl_minb == 6) VL_FINE(0, 6); else if (g_vl_minb == 5) VL_FINE(0, 5); else if (g_vl_minb == 4) VL_FINE(0, 4); else if (g_vl_minb == 3) VL_FINE(0, 3); else VL_FINE(0, 2); }
