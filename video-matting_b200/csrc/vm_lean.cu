@@ -913,13 +913,11 @@ k_lean_fine_tm(const void *__restrict__ src_all, const uint8_t *__restrict__ bg,
     const uint8_t *bgp = bgf + p0 * 3u;
     float4 *op = out + fbase + p0;
     const bool active = (int)threadIdx.x < tw && nrows > 0;
-    // one CTA barrier: the copies have landed (warp 0 polls), S.rows is published, and the vote
-    if (tid < 32) {
-        __syncwarp();
-        vl_mbar_wait_parity(bar0, 0);
-    }
+    // one CTA barrier - S.rows is published, the mbarrier's initialisation is visible, and the vote - then every warp waits
+    // for the copies on the mbarrier itself (try_wait suspends the warp in hardware): no polling warp, and no second barrier
+    // between the arrival of the data and the pixel loop
     const bool all_staged = __syncthreads_and(row_ok && win_ok);
-    if (tid >= 32) vl_mbar_wait_parity(bar0, 0);                         // completed: one try_wait that orders the async-proxy writes
+    vl_mbar_wait_parity(bar0, 0);
     int outside = 0, slow = 0;
     if (!all_staged) {                                                  // generic axis tables: everything from global memory
         if (active) vl_strip_generic<SRC>(src, Tf + ce.i0, Tf + ce.i1, ny, rows + I0 + strip0, ce.frac, bgp, op, nrows, h, w, &outside);
